@@ -1,0 +1,358 @@
+"""CPU oracle for the YOLO-DBL inference hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (cpu_baseline /
+``--impl reference`` legs) may import this module.  The product package
+``yolo_dbl_b200`` never does; it fails loudly when its CUDA library is missing.
+
+What this is
+------------
+A from-scratch *functional* restatement (plain torch fp32 on the CPU) of the
+reference's forward pass for ``yolov13_DBL.yaml`` and of its Detect decode.  It
+consumes a reference-compatible ``state_dict`` (same key names as
+``ultralytics.nn.tasks.DetectionModel``), so the very same weights can be loaded
+into the real reference, this oracle and the B200 path.
+
+Every function cites the reference file:line it follows (paths relative to
+``/root/reference/models/YOLO/ultralytics``).  The arithmetic below the module
+level (conv2d, softmax, grid_sample, bmm) is ATen — third party for the reference
+too — and is exercised rather than restated.
+
+Parity pin
+----------
+The reference ships no golden vectors.  This oracle is pinned
+against outputs of the reference itself, generated in the authoring container by
+``oracle/make_golden.py`` and committed under ``tests/golden/`` (see
+``tests/test_oracle_golden.py``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+BN_EPS = 1e-3  # utils/torch_utils.py:410-420 (initialize_weights sets eps=1e-3 on every BatchNorm2d)
+
+
+# --------------------------------------------------------------------------------------
+# architecture table  (cfg/models/v13/yolov13_DBL.yaml:8-53, resolved like nn/tasks.py:947-1208)
+# --------------------------------------------------------------------------------------
+_SCALES = {"n": (0.50, 0.25), "s": (0.50, 0.50), "l": (1.00, 1.00)}  # yaml:4-5; 'l' is BASELINE config 4 (injected)
+
+# (from, repeats, kind, args)
+_ROWS = [
+    (-1, 1, "Conv", (32, 3, 1)), (-1, 1, "Conv", (64, 3, 2)), (-1, 1, "Bottleneck", (64,)),
+    (-1, 1, "Conv", (128, 3, 2)), (-1, 2, "Bottleneck", (128,)), (-1, 1, "Conv", (256, 3, 2)),
+    (-1, 8, "Bottleneck", (256,)), (-1, 1, "Conv", (512, 1, 1)), (-1, 1, "DSConv", (512, 3, 2)),
+    (-1, 8, "DSC3k2", (512,)), (-1, 1, "DSConv", (1024, 3, 2)), (-1, 4, "LSKblock", ()),
+    ((7, 9, 11), 2, "HyperACE", (512, 8)), (-1, 1, "DySample", ()), (12, 1, "DownsampleConv", ()),
+    ((9, 12), 1, "FullPAD", ()), ((7, 13), 1, "FullPAD", ()), ((11, 14), 1, "FullPAD", ()),
+    (-1, 1, "DySample", ()), ((-1, 15), 1, "Concat", ()), (-1, 1, "Bottleneck", (512,)),
+    ((-1, 12), 1, "FullPAD", ()), (-2, 1, "DySample", ()), ((-1, 16), 1, "Concat", ()),
+    (-1, 1, "Bottleneck", (256,)), (13, 1, "Conv", (256, 1, 1)), ((-2, -1), 1, "FullPAD", ()),
+    (-1, 1, "Conv", (256, 3, 2)), ((-1, 21), 1, "Concat", ()), (-1, 1, "Bottleneck", (512,)),
+    ((-1, 12), 1, "FullPAD", ()), (-2, 1, "Conv", (512, 3, 2)), ((-1, 17), 1, "Concat", ()),
+    (-1, 1, "DSC3k2", (1024,)), ((-1, 14), 1, "FullPAD", ()), ((26, 30, 34), 1, "Detect", ()),
+]
+
+
+@dataclass
+class Layer:
+    i: int
+    f: object
+    kind: str
+    n: int
+    c1: object
+    c2: int
+    extra: dict = field(default_factory=dict)
+
+
+def _divisible8(x: float) -> int:  # utils/ops.py:130-143
+    return int(math.ceil(x / 8) * 8)
+
+
+def build_layers(scale: str = "n") -> List[Layer]:
+    """Resolve depth/width like parse_model (nn/tasks.py:979, 1047-1049, 1121-1145)."""
+    depth, width = _SCALES[scale]
+    ch: List[int] = []
+    out: List[Layer] = []
+    for i, (f, n, kind, args) in enumerate(_ROWS):
+        n = max(round(n * depth), 1) if n > 1 else n
+        cin = (lambda j: 3 if (i == 0) else ch[j])
+        extra = {}
+        if kind in ("Conv", "Bottleneck", "DSConv", "DSC3k2"):
+            c1, c2 = cin(f), _divisible8(args[0] * width)
+            if kind in ("Conv", "DSConv"):
+                extra = {"k": args[1], "s": args[2]}
+        elif kind == "HyperACE":
+            c1, c2 = ch[f[1]], _divisible8(args[0] * width)
+            he = args[1]
+            he = int(he * 0.5) if scale in "n" else he  # tasks.py:1126-1130 ("x" scale not defined for DBL)
+            extra = {"he": he}
+        elif kind == "DownsampleConv":
+            c1 = ch[f]
+            c2 = 2 * c1
+        elif kind == "Concat":
+            c1 = [ch[j] for j in f]
+            c2 = sum(c1)
+        elif kind == "FullPAD":
+            c1 = [ch[j] for j in f]
+            c2 = ch[f[0]]
+        elif kind == "Detect":
+            c1 = [ch[j] for j in f]
+            c2 = 0
+        else:  # LSKblock, DySample: channel preserving (tasks.py:1156-1187)
+            c1 = c2 = ch[f]
+        out.append(Layer(i, f, kind, n, c1, c2, extra))
+        ch.append(c2)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# leaf blocks
+# --------------------------------------------------------------------------------------
+def _bn(sd: Dict[str, Tensor], p: str, x: Tensor) -> Tensor:
+    if sd.get("__calibrate__") is not None:  # oracle/calibrate_bn.py: measure the statistics a trained BN would hold
+        sd[p + ".running_mean"] = x.mean((0, 2, 3)).clone()
+        sd[p + ".running_var"] = x.var((0, 2, 3), unbiased=False).clamp_min(0.02).clone()
+        sd["__calibrate__"][p + ".running_mean"] = sd[p + ".running_mean"]
+        sd["__calibrate__"][p + ".running_var"] = sd[p + ".running_var"]
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training=False, eps=BN_EPS)
+
+
+def conv_bn_silu(sd, p, x, s=1, g=1, act=True):
+    """``Conv.forward`` nn/modules/conv.py:39-63 — conv2d(bias=False, pad=k//2) -> BN(eval) -> SiLU."""
+    w = sd[p + ".conv.weight"]
+    y = _bn(sd, p + ".bn", F.conv2d(x, w, None, s, w.shape[-1] // 2, 1, g))
+    return F.silu(y) if act else y
+
+
+def dsconv(sd, p, x, s=1, d=1):
+    """``DSConv.forward`` conv.py:91-108 — depthwise k×k (no bias) -> 1×1 (no bias) -> BN -> SiLU."""
+    wd = sd[p + ".dw.weight"]
+    k = wd.shape[-1]
+    y = F.conv2d(x, wd, None, s, (d * (k - 1)) // 2, d, wd.shape[0])
+    y = F.conv2d(y, sd[p + ".pw.weight"])
+    return F.silu(_bn(sd, p + ".bn", y))
+
+
+def bottleneck(sd, p, x, shortcut=True):
+    """``Bottleneck.forward`` block.py:344-357 (k=(3,3), e=0.5)."""
+    y = conv_bn_silu(sd, p + ".cv2", conv_bn_silu(sd, p + ".cv1", x))
+    return x + y if (shortcut and x.shape[1] == y.shape[1]) else y
+
+
+def ds_bottleneck(sd, p, x, shortcut=True):
+    """``DSBottleneck.forward`` block.py:1408-1444 (k1=3, k2=7 as instantiated by DSC3k2/HyperACE)."""
+    y = dsconv(sd, p + ".cv2", dsconv(sd, p + ".cv1", x))
+    return x + y if (shortcut and x.shape[1] == y.shape[1]) else y
+
+
+def dsc3k(sd, p, x, n=2, shortcut=True):
+    """``DSC3k`` block.py:1447-1503 on top of ``C3.forward`` block.py:271-273."""
+    a = conv_bn_silu(sd, p + ".cv1", x)
+    for j in range(n):
+        a = ds_bottleneck(sd, f"{p}.m.{j}", a, shortcut)
+    return conv_bn_silu(sd, p + ".cv3", torch.cat((a, conv_bn_silu(sd, p + ".cv2", x)), 1))
+
+
+def dsc3k2(sd, p, x, n):
+    """``DSC3k2`` (dsc3k=True) block.py:1505-1580 on top of ``C2f.forward`` block.py:245-249."""
+    y = list(conv_bn_silu(sd, p + ".cv1", x).chunk(2, 1))
+    for j in range(n):
+        y.append(dsc3k(sd, f"{p}.m.{j}", y[-1], 2, True))
+    return conv_bn_silu(sd, p + ".cv2", torch.cat(y, 1))
+
+
+def lskblock(sd, p, x):
+    """``LSKblock.forward`` nn/modules_attention/LSKA.py:28-52."""
+    c = x.shape[1]
+    a1 = F.conv2d(x, sd[p + ".conv0.weight"], sd[p + ".conv0.bias"], 1, 2, 1, c)
+    a2 = F.conv2d(a1, sd[p + ".conv_spatial.weight"], sd[p + ".conv_spatial.bias"], 1, 9, 3, c)
+    a1 = F.conv2d(a1, sd[p + ".conv1.weight"], sd[p + ".conv1.bias"])
+    a2 = F.conv2d(a2, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"])
+    attn = torch.cat([a1, a2], 1)
+    agg = torch.cat([attn.mean(1, keepdim=True), attn.max(1, keepdim=True)[0]], 1)
+    sig = F.conv2d(agg, sd[p + ".conv_squeeze.weight"], sd[p + ".conv_squeeze.bias"], 1, 3).sigmoid()
+    attn = a1 * sig[:, 0:1] + a2 * sig[:, 1:2]
+    attn = F.conv2d(attn, sd[p + ".conv.weight"], sd[p + ".conv.bias"])
+    return x * attn
+
+
+def hyperedge_participation(sd, p, X, heads):
+    """``AdaHyperedgeGen.forward`` block.py:1582-1657 — returns A (B, N, E), softmax over the N tokens."""
+    B, N, D = X.shape
+    base = sd[p + ".prototype_base"]
+    E = base.shape[0]
+    hd = D // heads
+    ctx = torch.cat([X.mean(1), X.max(1)[0]], -1)
+    protos = base.unsqueeze(0) + F.linear(ctx, sd[p + ".context_net.weight"], sd[p + ".context_net.bias"]).view(B, E, D)
+    Xp = F.linear(X, sd[p + ".pre_head_proj.weight"], sd[p + ".pre_head_proj.bias"])
+    Xh = Xp.view(B, N, heads, hd).transpose(1, 2).reshape(B * heads, N, hd)
+    Ph = protos.view(B, E, heads, hd).permute(0, 2, 1, 3).reshape(B * heads, E, hd).transpose(1, 2)
+    logits = torch.bmm(Xh, Ph) / math.sqrt(hd)
+    logits = logits.view(B, heads, N, E).mean(1)  # dropout is identity in eval
+    return F.softmax(logits, dim=1)
+
+
+def hypergraph_conv(sd, p, X, heads):
+    """``AdaHGConv.forward`` block.py:1699-1708 — vertex->edge->vertex message passing + residual."""
+    A = hyperedge_participation(sd, p + ".edge_generator", X, heads)
+    He = torch.bmm(A.transpose(1, 2), X)
+    He = F.gelu(F.linear(He, sd[p + ".edge_proj.0.weight"], sd[p + ".edge_proj.0.bias"]))
+    Xn = torch.bmm(A, He)
+    Xn = F.gelu(F.linear(Xn, sd[p + ".node_proj.0.weight"], sd[p + ".node_proj.0.bias"]))
+    return Xn + X
+
+
+def c3ah(sd, p, x):
+    """``C3AH.forward`` block.py:1754-1795 with ``AdaHGComputation`` block.py:1747-1752 (heads = c_/16)."""
+    a = conv_bn_silu(sd, p + ".cv1", x)
+    B, C, H, W = a.shape
+    tok = hypergraph_conv(sd, p + ".m.hgnn", a.flatten(2).transpose(1, 2), C // 16)
+    a = tok.transpose(1, 2).reshape(B, C, H, W)
+    return conv_bn_silu(sd, p + ".cv3", torch.cat((a, conv_bn_silu(sd, p + ".cv2", x)), 1))
+
+
+def hyperace(sd, p, xs: Sequence[Tensor], n=1):
+    """``HyperACE.forward`` block.py:1884-1895 incl. ``FuseModule.forward`` block.py:1833-1840."""
+    fused = torch.cat([F.avg_pool2d(xs[0], 2), xs[1], F.interpolate(xs[2], scale_factor=2, mode="nearest")], 1)
+    x = conv_bn_silu(sd, p + ".fuse.conv_out", fused)
+    y = list(conv_bn_silu(sd, p + ".cv1", x).chunk(3, 1))
+    out1 = c3ah(sd, p + ".branch1", y[1])
+    out2 = c3ah(sd, p + ".branch2", y[1])
+    for j in range(n):
+        y.append(dsc3k(sd, f"{p}.m.{j}", y[-1], 2, True))  # HyperACE(..., dsc3k=True, shortcut=True) from the yaml
+    y[1] = out1
+    y.append(out2)
+    return conv_bn_silu(sd, p + ".cv2", torch.cat(y, 1))
+
+
+def dysample(sd, p, x, groups=4, scale=2):
+    """``DySample.forward_lp`` + ``sample`` nn/modules_upsample/DySample.py:49-68."""
+    B, C, H, W = x.shape
+    off = F.conv2d(x, sd[p + ".offset.weight"], sd[p + ".offset.bias"]) * 0.25 + sd[p + ".init_pos"]
+    off = off.view(B, 2, -1, H, W)
+    cw = torch.arange(W, dtype=x.dtype) + 0.5
+    chh = torch.arange(H, dtype=x.dtype) + 0.5
+    coords = torch.stack(torch.meshgrid([cw, chh], indexing="ij")).transpose(1, 2).unsqueeze(1).unsqueeze(0)
+    norm = torch.tensor([W, H], dtype=x.dtype).view(1, 2, 1, 1, 1)
+    coords = 2 * (coords + off) / norm - 1
+    coords = F.pixel_shuffle(coords.view(B, -1, H, W), scale).view(B, 2, -1, scale * H, scale * W)
+    coords = coords.permute(0, 2, 3, 4, 1).contiguous().flatten(0, 1)
+    y = F.grid_sample(x.reshape(B * groups, -1, H, W), coords, mode="bilinear", align_corners=False,
+                      padding_mode="border")
+    return y.view(B, -1, scale * H, scale * W)
+
+
+def dysample_init_pos(groups=4, scale=2) -> Tensor:
+    """``DySample._init_pos`` DySample.py:45-47."""
+    h = torch.arange((-scale + 1) / 2, (scale - 1) / 2 + 1) / scale
+    return torch.stack(torch.meshgrid([h, h], indexing="ij")).transpose(1, 2).repeat(1, groups, 1).reshape(1, -1, 1, 1)
+
+
+def downsample_conv(sd, p, x):
+    """``DownsampleConv.forward`` block.py:1897-1928."""
+    return conv_bn_silu(sd, p + ".channel_adjust", F.avg_pool2d(x, 2))
+
+
+def fullpad(sd, p, a, b):
+    """``FullPAD_Tunnel.forward`` block.py:1950-1956."""
+    return a + sd[p + ".gate"] * b
+
+
+# --------------------------------------------------------------------------------------
+# Detect head
+# --------------------------------------------------------------------------------------
+def detect_branches(sd, p, feats: Sequence[Tensor]) -> List[Tensor]:
+    """``Detect.forward`` head.py:108-118, legacy=False cv3 (head.py:93-100) -> per level (B, 64+nc, H, W)."""
+    outs = []
+    for i, x in enumerate(feats):
+        b = conv_bn_silu(sd, f"{p}.cv2.{i}.1", conv_bn_silu(sd, f"{p}.cv2.{i}.0", x))
+        b = F.conv2d(b, sd[f"{p}.cv2.{i}.2.weight"], sd[f"{p}.cv2.{i}.2.bias"])
+        c = x
+        for j in (0, 1):
+            c = conv_bn_silu(sd, f"{p}.cv3.{i}.{j}.0", c, g=c.shape[1])  # DWConv: groups = gcd(c, c) = c
+            c = conv_bn_silu(sd, f"{p}.cv3.{i}.{j}.1", c)
+        c = F.conv2d(c, sd[f"{p}.cv3.{i}.2.weight"], sd[f"{p}.cv3.{i}.2.bias"])
+        outs.append(torch.cat((b, c), 1))
+    return outs
+
+
+def make_anchors(hw: Sequence[Sequence[int]], strides: Sequence[float]):
+    """``make_anchors`` utils/tal.py:333-345 — cell centres (+0.5), levels concatenated row-major."""
+    pts, st = [], []
+    for (h, w), s in zip(hw, strides):
+        sy, sx = torch.meshgrid(torch.arange(h, dtype=torch.float32) + 0.5, torch.arange(w, dtype=torch.float32) + 0.5,
+                                indexing="ij")
+        pts.append(torch.stack((sx, sy), -1).view(-1, 2))
+        st.append(torch.full((h * w, 1), float(s)))
+    return torch.cat(pts), torch.cat(st)
+
+
+def detect_decode(x_cat: Tensor, hw, strides, reg_max=16) -> Tensor:
+    """``Detect._inference`` head.py:143-181 + ``DFL.forward`` block.py:80-83 + ``dist2bbox`` tal.py:348-357.
+
+    x_cat: (B, 4*reg_max + nc, A) raw head logits -> y (B, 4 + nc, A): xywh in pixels, sigmoid scores.
+    """
+    B, _, A = x_cat.shape
+    box, cls = x_cat.split((4 * reg_max, x_cat.shape[1] - 4 * reg_max), 1)
+    anc, st = make_anchors(hw, strides)
+    anc, st = anc.t().unsqueeze(0), st.t()
+    proj = torch.arange(reg_max, dtype=torch.float32).view(1, reg_max, 1, 1)
+    dist = F.conv2d(box.view(B, 4, reg_max, A).transpose(2, 1).softmax(1), proj).view(B, 4, A)
+    lt, rb = dist.chunk(2, 1)
+    x1y1, x2y2 = anc - lt, anc + rb
+    dbox = torch.cat(((x1y1 + x2y2) / 2, x2y2 - x1y1), 1) * st
+    return torch.cat((dbox, cls.sigmoid()), 1)
+
+
+# --------------------------------------------------------------------------------------
+# whole graph  (BaseModel._predict_once nn/tasks.py:145-172)
+# --------------------------------------------------------------------------------------
+def forward(sd: Dict[str, Tensor], x: Tensor, scale: str = "n", collect: bool = False):
+    """Returns (y, head_feats[, per-layer outputs]).  x: (B,3,H,W) fp32 in 0..1, H,W % 32 == 0."""
+    layers = build_layers(scale)
+    outs: List[Tensor] = []
+    with torch.inference_mode():
+        for L in layers:
+            p = f"model.{L.i}"
+            src = (lambda j: x if (L.i == 0) else outs[j if j >= 0 else L.i + j])
+            if L.kind == "Conv":
+                o = conv_bn_silu(sd, p, src(L.f), L.extra["s"])
+            elif L.kind == "DSConv":
+                o = dsconv(sd, p, src(L.f), L.extra["s"])
+            elif L.kind == "Bottleneck":
+                o = src(L.f)
+                for r in range(L.n):
+                    o = bottleneck(sd, f"{p}.{r}" if L.n > 1 else p, o, True)
+            elif L.kind == "DSC3k2":
+                o = dsc3k2(sd, p, src(L.f), L.n)
+            elif L.kind == "LSKblock":
+                o = src(L.f)
+                for r in range(L.n):
+                    o = lskblock(sd, f"{p}.{r}" if L.n > 1 else p, o)
+            elif L.kind == "HyperACE":
+                o = hyperace(sd, p, [src(j) for j in L.f], L.n)
+            elif L.kind == "DySample":
+                o = dysample(sd, p, src(L.f))
+            elif L.kind == "DownsampleConv":
+                o = downsample_conv(sd, p, src(L.f))
+            elif L.kind == "FullPAD":
+                o = fullpad(sd, p, src(L.f[0]), src(L.f[1]))
+            elif L.kind == "Concat":
+                o = torch.cat([src(j) for j in L.f], 1)
+            elif L.kind == "Detect":
+                feats = detect_branches(sd, p, [src(j) for j in L.f])
+                hw = [f.shape[2:] for f in feats]
+                strides = [x.shape[2] / h for h, _ in hw]  # tasks.py:338-351 (stride probe) -> 8,16,32
+                B, no = feats[0].shape[:2]
+                y = detect_decode(torch.cat([f.reshape(B, no, -1) for f in feats], 2), hw, strides)
+                o = (y, feats)
+            outs.append(o)
+    y, feats = outs[-1]
+    return (y, feats, outs[:-1]) if collect else (y, feats)

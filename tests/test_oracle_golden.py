@@ -1,0 +1,127 @@
+"""Pin the CPU oracle against outputs of the REAL reference (tests/golden/, made by oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dbl_oracle as O
+import nms_oracle as N
+from yolo_dbl_b200.synth import synth_images, synth_state_dict
+
+from conftest import GOLDEN
+
+
+def _load(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _case(name):
+    g = _load(f"fwd_{name}.npz")
+    meta = json.loads(str(g["meta"]))
+    shapes = json.load(open(os.path.join(GOLDEN, f"shapes_{meta['scale']}_nc{meta['nc']}.json")))
+    sd = synth_state_dict(shapes, meta["wseed"])
+    x = synth_images(meta["b"], meta["h"], meta["w"], meta["xseed"])
+    return g, meta, sd, x
+
+
+@pytest.mark.parametrize("name", ["n_nc3_small", "n_nc80_small", "s_nc3_small", "l_nc3_small"])
+def test_forward_matches_reference_small(name):
+    g, meta, sd, x = _case(name)
+    y, feats, outs = O.forward(sd, x, meta["scale"], collect=True)
+    ref = torch.from_numpy(g["y_unfused"])  # the oracle applies BN explicitly, like the unfused reference
+    assert y.shape == ref.shape
+    torch.testing.assert_close(y, ref, rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(y, torch.from_numpy(g["y"]), rtol=1e-3, atol=1e-3)  # reference after fuse()
+    for li, f in enumerate(feats):
+        samp = f.reshape(-1)[torch.from_numpy(g[f"feat{li}_index"])]
+        torch.testing.assert_close(samp, torch.from_numpy(g[f"feat{li}_samples"]), rtol=1e-3, atol=1e-3)
+    if "layer0_stats" in g:
+        for i, o in enumerate(outs):
+            assert tuple(o.shape) == tuple(g[f"layer{i}_shape"]), f"layer {i}"
+            samp = o.reshape(-1)[torch.from_numpy(g[f"layer{i}_index"])]
+            torch.testing.assert_close(samp, torch.from_numpy(g[f"layer{i}_samples"]), rtol=2e-4, atol=2e-4,
+                                       msg=lambda m, i=i: f"layer {i}: {m}")
+            st = g[f"layer{i}_stats"]
+            assert abs(float(o.double().mean()) - st[0]) < 1e-4 + 1e-4 * abs(st[0])
+            assert abs(float(o.double().std()) - st[1]) < 1e-4 + 1e-4 * abs(st[1])
+
+
+def test_forward_matches_reference_640():
+    g, meta, sd, x = _case("n_nc3_640")
+    y, feats, outs = O.forward(sd, x, "n", collect=True)
+    ys = y[:, :, :: meta["y_stride"]]
+    torch.testing.assert_close(ys, torch.from_numpy(g["y_unfused"]), rtol=2e-4, atol=5e-3)
+    for i, o in enumerate(outs):
+        samp = o.reshape(-1)[torch.from_numpy(g[f"layer{i}_index"])]
+        torch.testing.assert_close(samp, torch.from_numpy(g[f"layer{i}_samples"]), rtol=5e-4, atol=5e-4,
+                                   msg=lambda m, i=i: f"layer {i}: {m}")
+    # NMS oracle on the reference's own decoded y == the reference's NMS rows, bit for bit
+    for conf in (0.25, 0.001):
+        ref = _load(f"nms_model640_conf{conf}.npz")
+        rows, idx = N.non_max_suppression(g["y"], conf, 0.7, max_det=300)
+        assert rows[0].tobytes() == ref["rows"].astype(np.float32).tobytes()
+        assert len(set(idx[0].tolist())) == len(idx[0])
+
+
+def test_layer_table_matches_reference_docstring_shapes():
+    # shape-level "known answers" of the reference (block.py docstrings) + Appendix A channel table
+    L = O.build_layers("n")
+    assert [l.c2 for l in L[:15]] == [8, 16, 16, 32, 32, 64, 64, 128, 128, 128, 256, 256, 128, 128, 256]
+    assert [l.n for l in L if l.kind in ("Bottleneck", "DSC3k2", "LSKblock", "HyperACE")][:6] == [1, 1, 4, 4, 2, 1]
+    assert L[12].extra["he"] == 4 and O.build_layers("s")[12].extra["he"] == 8 and O.build_layers("l")[12].extra["he"] == 8
+    assert L[35].c1 == [64, 128, 256]
+
+
+def test_init_pos_matches_reference_buffer():
+    from yolo_dbl_b200.synth import _init_pos
+
+    torch.testing.assert_close(_init_pos(), O.dysample_init_pos())
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+def _synth_prediction(b, nc, a, seed, mu, quant=0.0, img=640.0):
+    g = torch.Generator().manual_seed(seed)
+    cx = torch.rand(b, 1, a, generator=g) * img
+    cy = torch.rand(b, 1, a, generator=g) * img
+    wh = torch.rand(b, 2, a, generator=g) * 120 + 4
+    sc = torch.sigmoid(torch.randn(b, nc, a, generator=g) * 1.5 + mu)
+    if quant:
+        sc = torch.round(sc / quant) * quant
+    return torch.cat([cx, cy, wh, sc], 1)
+
+
+NMS_CASES = ["typical_nc3", "typical_nc80", "dense_nc3", "ties_nc3", "agnostic", "classes", "maxnms", "empty", "multilabel"]
+
+
+@pytest.mark.parametrize("name", NMS_CASES)
+def test_nms_oracle_bit_exact_vs_reference(name):
+    g = _load(f"nms_{name}.npz")
+    meta = json.loads(str(g["meta"]))
+    pred = _synth_prediction(**meta["pred_args"]).numpy()
+    rows, idx = N.non_max_suppression(pred, **meta["kw"])
+    assert [r.shape[0] for r in rows] == g["counts"].tolist()
+    got = np.concatenate(rows, 0) if rows else np.zeros((0, 6), np.float32)
+    assert got.tobytes() == g["rows"].astype(np.float32).tobytes(), "rows differ from the reference bit pattern"
+    for r, i in zip(rows, idx):
+        assert len(i) == r.shape[0]
+
+
+def test_nms_kernel_matches_torchvision_random_and_ties():
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(1, 400))
+        xy = rng.uniform(0, 200, (n, 2)).astype(np.float32)
+        wh = rng.uniform(1, 80, (n, 2)).astype(np.float32)
+        if trial % 3 == 0:
+            xy, wh = np.round(xy), np.round(wh)  # integer boxes: exact-threshold IoUs
+        boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+        scores = rng.uniform(0, 1, n).astype(np.float32)
+        if trial % 2 == 0:
+            scores = np.round(scores * 8) / 8  # many ties
+        thr = float(rng.choice([0.3, 0.45, 0.5, 0.7]))
+        want = tv.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr).numpy()
+        np.testing.assert_array_equal(N.nms(boxes, scores, thr), want)
