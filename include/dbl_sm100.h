@@ -1,0 +1,157 @@
+/* libdbl_sm100.so -- C ABI of the B200-native YOLO-DBL inference path.
+ *
+ * The reference (player4771/YOLO-DBL, a fork of ultralytics 8.3.63) has no C boundary: its hot path is Python that
+ * calls torch / torchvision library ops.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces (paths relative to
+ * models/YOLO/ultralytics/ of the reference).
+ *
+ * Conventions (seam B4)
+ *   - plain pointers and sizes only; no torch / C++ types; every function returns 0 on success or a DBL_E_* code and
+ *     never throws, aborts or calls cudaDeviceSynchronize.  dbl_last_error() returns a per-thread message.
+ *   - the CALLER owns every buffer including scratch; the library never allocates or frees device memory.
+ *   - every launch goes to the stream that is passed in, so a whole forward pass is CUDA-graph capturable.
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails with DBL_E_CUDA.
+ *
+ * Activation layout: NHWC, channels innermost.  A dbl_tensor may be a channel slice of a wider buffer
+ * (`pitch` = elements per pixel of the underlying buffer), which is how concat/chunk cost nothing.
+ */
+#ifndef DBL_SM100_H
+#define DBL_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dbl_stream_t; /* a cudaStream_t */
+
+enum { DBL_OK = 0, DBL_E_ARG = 1, DBL_E_UNSUPPORTED = 2, DBL_E_CUDA = 3, DBL_E_WORKSPACE = 4 };
+enum { DBL_BF16 = 0, DBL_F32 = 1 };
+enum { DBL_ACT_NONE = 0, DBL_ACT_SILU = 1, DBL_ACT_GELU = 2 };
+enum { DBL_EPI_NONE = 0, DBL_EPI_ADD = 1 /* y = act(conv)+r */, DBL_EPI_MUL = 2 /* y = act(conv)*r */ };
+enum { DBL_IMPL_AUTO = 0, DBL_IMPL_DIRECT = 1 /* CUDA-core */, DBL_IMPL_TCGEN05 = 2 /* tensor cores + TMA */ };
+
+typedef struct dbl_tensor {
+    void* data;    /* device pointer to element (n=0,h=0,w=0,c=0) of this view */
+    int32_t n, h, w, c;
+    int32_t pitch; /* elements between consecutive pixels (>= c) */
+    int32_t dtype; /* DBL_BF16 or DBL_F32 */
+} dbl_tensor;
+
+const char* dbl_last_error(void);
+int dbl_version(void);
+/* 1 if the current CUDA device can run this library (compute capability 10.x), else 0. */
+int dbl_device_ok(void);
+/* number of kernels this library has launched from the calling process (bench.py reports it as gpu_launches) */
+int64_t dbl_launch_count(void);
+
+/* ---- dense convolutions ------------------------------------------------------------------------------------------
+ * Conv.forward_fuse + fuse_conv_and_bn (nn/modules/conv.py:39-63, utils/torch_utils.py:238-265), the pointwise half of
+ * DSConv (conv.py:91-108), the biased nn.Conv2d 1x1s of LSKblock / DySample / Detect, Bottleneck's residual add
+ * (nn/modules/block.py:344-357) and LSKblock's final x*attn (nn/modules_attention/LSKA.py:52).
+ *   x: bf16 NHWC (n,h,w,cin)      w: bf16 [cout][k][k][cin] (BatchNorm already folded)      bias: f32 [cout] or NULL
+ *   r: bf16 NHWC like y, or NULL  y: bf16 or f32 NHWC (n,ho,wo,cout), ho = (h+2*pad-dil*(k-1)-1)/stride+1
+ * impl = DBL_IMPL_TCGEN05 requires cin % 16 == 0, dil == 1, k in {1,3}, stride in {1,2} (k==1: stride 1). */
+int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
+               int k, int stride, int pad, int dil, int act, int epi, int impl, dbl_stream_t stream);
+
+/* Layer 0 of the graph (cfg/models/v13/yolov13_DBL.yaml:9, Conv [32,3,1]) fused with the input cast of
+ * BasePredictor.preprocess (engine/predictor.py:116-134): x is the user's f32 NCHW image batch (n,3,h,w) in 0..1,
+ * w f32 [cout][3][3][3], y bf16 NHWC, SiLU applied. */
+int dbl_stem_conv(const float* x_nchw, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
+                  int stride, dbl_stream_t stream);
+
+/* ---- depthwise convolution ---------------------------------------------------------------------------------------
+ * DSConv.dw (conv.py:96-99), DWConv (conv.py:128-133), LSKblock.conv0 / conv_spatial (LSKA.py:31-32).
+ *   w: f32 [k*k][c]   bias: f32 [c] or NULL   pad = dil*(k-1)/2 */
+int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bias, const dbl_tensor* y, int k, int stride, int dil,
+                 int act, dbl_stream_t stream);
+
+/* ---- bandwidth-bound glue ---------------------------------------------------------------------------------------- */
+/* nn.AvgPool2d(2) of FuseModule / DownsampleConv (block.py:1825, 1919) */
+int dbl_avgpool2(const dbl_tensor* x, const dbl_tensor* y, dbl_stream_t stream);
+/* nn.Upsample(scale_factor=2, mode='nearest') of FuseModule (block.py:1826) */
+int dbl_upsample2_nearest(const dbl_tensor* x, const dbl_tensor* y, dbl_stream_t stream);
+/* FullPAD_Tunnel.forward (block.py:1950-1956): y = a + gate*b.  y2 (optional) receives a second copy, which is how a
+ * tunnel output lands in its consumer's concat buffer as well as in its own. */
+int dbl_gated_add(const dbl_tensor* a, const dbl_tensor* b, float gate, const dbl_tensor* y, const dbl_tensor* y2,
+                  dbl_stream_t stream);
+/* copy a view (Concat of a tensor that could not be produced in place, conv.py:349-359) */
+int dbl_copy(const dbl_tensor* x, const dbl_tensor* y, dbl_stream_t stream);
+/* DySample.forward_lp + sample (nn/modules_upsample/DySample.py:49-68), scale 2.  off: f32 NHWC (n,h,w,2*groups*4) =
+ * raw output of the `offset` 1x1 conv incl. bias; the kernel applies *0.25 + init_pos, the pixel shuffle and the
+ * bilinear border-clamped gather (grid_sample align_corners=False).  y: (n,2h,2w,c). */
+int dbl_dysample(const dbl_tensor* x, const dbl_tensor* off, const dbl_tensor* y, int groups, dbl_stream_t stream);
+/* LSKblock (LSKA.py:43-50): attn = [attn1|attn2] bf16 (n,h,w,2*half); agg f32 (n,h,w,2) <- channel mean / max */
+int dbl_lsk_squeeze(const dbl_tensor* attn, const dbl_tensor* agg, dbl_stream_t stream);
+/* sig = sigmoid(conv7x7(agg; w_sq f32 [2][2][7][7], b_sq[2])); y = attn1*sig0 + attn2*sig1  (n,h,w,half) bf16 */
+int dbl_lsk_gate(const dbl_tensor* attn, const dbl_tensor* agg, const float* w_sq, const float* b_sq, const dbl_tensor* y,
+                 dbl_stream_t stream);
+
+/* ---- adaptive hypergraph (AdaHGComputation / AdaHGConv / AdaHyperedgeGen, block.py:1582-1752) -------------------
+ * x: bf16 tokens (n, h, w, d) == (B, N=h*w, D).  All weights f32, row-major [out][in] like nn.Linear.
+ * Scratch `ws` must hold dbl_hypergraph_workspace_bytes(B, N, D, E) bytes.  y = node_proj(A·edge_proj(AᵀX)) + X. */
+typedef struct dbl_hypergraph_weights {
+    const float* prototype_base; /* [E][D] */
+    const float* context_w;      /* [E*D][2D] */
+    const float* context_b;      /* [E*D] */
+    const float* pre_head_w;     /* [D][D] */
+    const float* pre_head_b;     /* [D] */
+    const float* edge_w;         /* [D][D] */
+    const float* edge_b;         /* [D] */
+    const float* node_w;         /* [D][D] */
+    const float* node_b;         /* [D] */
+    int32_t num_edges;           /* E */
+    int32_t num_heads;
+} dbl_hypergraph_weights;
+size_t dbl_hypergraph_workspace_bytes(int batch, int tokens, int dim, int edges);
+int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights* wts, const dbl_tensor* y, void* ws, size_t ws_bytes,
+                   dbl_stream_t stream);
+
+/* ---- Detect post-process -----------------------------------------------------------------------------------------
+ * Head logits live in one f32 NHWC tensor per level: channels [0,64) = cv2 (4 sides x 16 DFL bins), [64,64+nc) = cv3. */
+typedef struct dbl_head_levels {
+    const float* data[3];
+    int32_t h[3], w[3];
+    float stride[3];
+    int32_t num_levels, batch, nc, pitch; /* pitch = elements per pixel (>= 64+nc) */
+} dbl_head_levels;
+
+/* Detect._inference (nn/modules/head.py:143-181) = DFL (block.py:80-83) + make_anchors (utils/tal.py:333-345) +
+ * dist2bbox (tal.py:348-357) + sigmoid.  y: f32 [B][4+nc][A] exactly like the reference's first output. */
+int dbl_detect_decode(const dbl_head_levels* lv, float* y, dbl_stream_t stream);
+
+/* Candidate lists: per image up to `cap` entries, unordered; pos = anchor*npos_per_anchor + k is the position the
+ * entry has in the reference's filtered list and is the tie-break key of the stable sort. */
+typedef struct dbl_candidates {
+    float* box;      /* [B][cap][4] xyxy, NOT class-offset */
+    float* score;    /* [B][cap] */
+    int32_t* cls;    /* [B][cap] */
+    int32_t* pos;    /* [B][cap] */
+    int32_t* count;  /* [B]  (zeroed by the filter call) */
+    int32_t cap, batch;
+} dbl_candidates;
+
+/* non_max_suppression stage 1 (utils/ops.py:234-279): xc = amax > conf, xywh2xyxy (ops.py:416-433), best class (or
+ * multi_label expansion), optional class filter.  pred: f32, element (b,ch,a) at b*stride_b + ch*stride_c + a*stride_a
+ * (the reference's y is stride_c = A, stride_a = 1).  classes: device int32 list or NULL. */
+int dbl_nms_filter(const float* pred, int batch, int nc, int anchors, int64_t stride_b, int64_t stride_c, int64_t stride_a,
+                   float conf_thres, int multi_label, const int32_t* classes, int num_classes_kept,
+                   const dbl_candidates* cand, dbl_stream_t stream);
+/* decode + filter fused: same candidates as dbl_detect_decode -> dbl_nms_filter without materialising y. */
+int dbl_decode_filter(const dbl_head_levels* lv, float conf_thres, int multi_label, const int32_t* classes,
+                      int num_classes_kept, const dbl_candidates* cand, dbl_stream_t stream);
+/* non_max_suppression stage 2 (ops.py:281-297) + torchvision.ops.nms: stable descending sort, max_nms truncation,
+ * boxes + cls*max_wh, greedy IoU suppression in strict fp32, max_det cut.
+ *   out_rows f32 [B][max_det][6] (x1,y1,x2,y2,conf,cls), out_pos int32 [B][max_det], out_count int32 [B]
+ *   sort_keys: scratch uint64 [B][dbl_nms_sort_capacity(cap)] */
+size_t dbl_nms_sort_capacity(int cap);
+int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
+            uint64_t* sort_keys, float* out_rows, int32_t* out_pos, int32_t* out_count, dbl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBL_SM100_H */

@@ -1,0 +1,108 @@
+"""Whole-graph parity (-m gpu): the B200 path vs the CPU oracle on identical weights and inputs.
+
+Stated tolerance for the bf16 backbone (north star: "bf16 backbone within a stated tolerance"):
+  * every top-level layer output: relative L2 error <= 5e-2 and never NaN/Inf;
+  * decoded boxes: median |d| <= 1 px, p99 <= 4 px on 640-px images; scores: max |d| <= 5e-2, p99 <= 1e-2.
+The fp32 post-process on identical inputs is held to 1e-3 / bit-exactness in test_gpu_nms.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dbl_oracle as O
+import nms_oracle as N
+from yolo_dbl_b200 import DBLBackend, YOLO, _lib as L, param_shapes, resolve, synth_images, synth_state_dict
+from yolo_dbl_b200.engine import DBLEngine
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_l2(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3):
+    spec = resolve(None, scale, nc)
+    sd = synth_state_dict(param_shapes(spec), seed)
+    x = synth_images(b, h, w, xseed)
+    eng = DBLEngine(spec, sd, b, h, w, device="cuda:0", conv_impl=conv_impl, use_graph=False, keep_layers=True)
+    outs = eng.debug_layers(x.cuda())
+    y_ref, feats_ref, outs_ref = O.forward(sd, x, scale, collect=True)
+    worst = []
+    for i, (o, r) in enumerate(zip(outs, outs_ref)):
+        if o is None:
+            continue
+        assert o.shape == r.shape, f"layer {i}: shape {tuple(o.shape)} vs {tuple(r.shape)}"
+        assert bool(torch.isfinite(o).all()), f"layer {i} produced non-finite values"
+        worst.append((_rel_l2(o, r), i, spec.layers[i].kind))
+    print("per-layer rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in worst))
+    for e, i, kind in worst:
+        assert e <= 5e-2, f"layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
+    y, feats = eng.forward(x.cuda())
+    torch.cuda.synchronize()
+    return eng, sd, x, y.cpu(), y_ref
+
+
+@pytest.mark.parametrize("conv_impl", [L.IMPL_DIRECT, L.IMPL_AUTO])
+def test_layers_n_scale_small(conv_impl):
+    _check_layers("n", 3, 0, 2, 128, 160, conv_impl)
+
+
+def test_layers_s_scale_nc80():
+    _check_layers("s", 3, 5, 1, 96, 96, L.IMPL_AUTO)
+
+
+def test_full_640_vs_oracle_and_reference_golden():
+    eng, sd, x, y, y_ref = _check_layers("n", 3, 0, 1, 640, 640, L.IMPL_AUTO, xseed=2)
+    g = np.load(os.path.join(GOLDEN, "fwd_n_nc3_640.npz"))
+    y_gold = torch.from_numpy(g["y"])  # the REAL reference's output on the same weights/input
+    for name, ref in (("oracle", y_ref), ("reference", y_gold)):
+        dbox = (y[:, :4] - ref[:, :4]).abs().flatten()
+        dsc = (y[:, 4:] - ref[:, 4:]).abs().flatten()
+        print(f"vs {name}: box median {dbox.median():.3f} p99 {dbox.quantile(0.99):.3f} max {dbox.max():.3f} px | "
+              f"score p99 {dsc.quantile(0.99):.4f} max {dsc.max():.4f}")
+        assert float(dbox.median()) <= 1.0 and float(dbox.quantile(0.99)) <= 4.0
+        assert float(dsc.quantile(0.99)) <= 1e-2 and float(dsc.max()) <= 5e-2
+    # detections: same count ballpark and high overlap with the reference's own NMS output
+    rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
+    ref_rows = np.load(os.path.join(GOLDEN, "nms_model640_conf0.25.npz"))["rows"]
+    n = int(counts[0])
+    assert abs(n - len(ref_rows)) <= max(5, len(ref_rows) // 10)
+
+
+def test_cuda_graph_replay_equals_eager():
+    spec = resolve(None, "n", 3)
+    sd = synth_state_dict(param_shapes(spec), 0)
+    x = synth_images(2, 96, 128, 9).cuda()
+    e1 = DBLEngine(spec, sd, 2, 96, 128, use_graph=False)
+    e2 = DBLEngine(spec, sd, 2, 96, 128, use_graph=True)
+    y1 = e1.forward(x)[0].clone()
+    for _ in range(3):
+        y2 = e2.forward(x)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    r1 = [t.clone() for t in e1.detect(x, conf=0.1, iou=0.7)]
+    r2 = [t.clone() for t in e2.detect(x, conf=0.1, iou=0.7)]
+    r2 = [t.clone() for t in e2.detect(x, conf=0.1, iou=0.7)]
+    assert all(torch.equal(a, b) for a, b in zip(r1, r2))
+
+
+def test_backend_api_surface_and_facade():
+    m = DBLBackend.synthetic("n", 3, seed=0, device="cuda:0")
+    assert m.stride.tolist() == [8.0, 16.0, 32.0] and m.pt and not m.triton and m.task == "detect"
+    assert m.fuse() is m and m.eval() is m and m.half() is m
+    x = synth_images(2, 64, 96, 1)
+    y, feats = m(x.cuda())
+    assert tuple(y.shape) == (2, 7, 8 * 12 + 4 * 6 + 2 * 3) and [tuple(f.shape) for f in feats] == [(2, 67, 8, 12), (2, 67, 4, 6), (2, 67, 2, 3)]
+    # y and feats are consistent with each other through the oracle's decode
+    hw = [f.shape[2:] for f in feats]
+    y2 = O.detect_decode(torch.cat([f.cpu().reshape(2, 67, -1) for f in feats], 2), hw, [8.0, 16.0, 32.0])
+    torch.testing.assert_close(y.cpu(), y2, rtol=1e-3, atol=1e-3)
+    res = YOLO("yolov13n_DBL.yaml", nc=3).predict(x.cuda(), conf=0.05)
+    assert len(res) == 2 and res[0].boxes.data.shape[1] == 6 and res[0].orig_shape == (64, 96)
+    assert bool((res[0].boxes.conf[:-1] >= res[0].boxes.conf[1:]).all()) if len(res[0]) > 1 else True

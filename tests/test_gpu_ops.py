@@ -1,0 +1,253 @@
+"""Per-kernel parity (-m gpu): each C-ABI entry point vs the CPU oracle / plain torch fp32 on identical bf16-rounded inputs.
+
+Tolerances: bf16 outputs carry one rounding (2^-9 relative) on top of fp32 accumulation-order noise -> rel 2^-7 + 2e-2
+absolute on O(1..10) activations; fp32 outputs 1e-3 relative.
+"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dbl_oracle as O
+from yolo_dbl_b200 import _lib as L
+
+from gpu_util import assert_close_bf16, bf16_round, conv2d, dev, empty_nhwc, from_nhwc, pack_w, stream, to_nhwc
+
+pytestmark = pytest.mark.gpu
+
+
+def _act_ref(v, act):
+    return F.silu(v) if act == L.ACT_SILU else (F.gelu(v) if act == L.ACT_GELU else v)
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, s, act, epi, ydtype, xpad, ypad
+    (2, 20, 20, 64, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 20, 20, 64, 32, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (1, 40, 40, 32, 16, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 24, 36, 16, 8, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 40, 40, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 80, 80, 64, 64, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 40, 40, 384, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 20, 20, 128, 128, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 64, 256),
+    (2, 40, 40, 64, 128, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (3, 20, 20, 384, 256, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 20, 20, 128, 256, 1, 1, L.ACT_NONE, L.EPI_MUL, torch.bfloat16, 0, 0),
+    (2, 20, 20, 64, 64, 1, 1, L.ACT_GELU, L.EPI_ADD, torch.bfloat16, 64, 64),
+    (2, 40, 40, 64, 3, 1, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 65),
+    (1, 40, 40, 80, 80, 1, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 64),
+    (2, 40, 40, 128, 32, 1, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 0),
+    (1, 20, 20, 256, 320, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 33, 50, 32, 48, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+]
+
+
+def _run_conv_case(case, impl, seed=0):
+    n, h, w, cin, cout, k, s, act, epi, ydt, xpad, ypad = case
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.5
+    ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
+    r = bf16_round(torch.randn(n, cout, ho, wo, generator=g)) if epi else None
+    ref = _act_ref(F.conv2d(x, wt, b, s, k // 2), act)
+    if epi == L.EPI_ADD:
+        ref = ref + r
+    elif epi == L.EPI_MUL:
+        ref = ref * r
+    xbuf, xv = to_nhwc(x, pad_c=xpad, c_off=xpad // 2 // 8 * 8)
+    ybuf, yv = empty_nhwc(n, ho, wo, cout, ydt, pad_c=ypad, c_off=(ypad // 2 // 8 * 8) if ydt == torch.bfloat16 else (64 if ypad >= 64 else 0))
+    rv = None
+    if epi:
+        rbuf, rv = to_nhwc(r)
+    rc = conv2d(xv, pack_w(wt), b.to(dev()), rv, yv, k, s, act, epi, impl)
+    assert rc == 0, L.load().dbl_last_error().decode()
+    off = yv.data - ybuf.data_ptr()
+    got = from_nhwc(ybuf, off // ybuf.element_size(), cout)
+    if ydt == torch.float32:
+        torch.testing.assert_close(got, ref, rtol=1e-3, atol=2e-3)
+    else:
+        assert_close_bf16(got, ref, f"conv {case} impl={impl}")
+    # channels outside the view must be untouched
+    if ypad:
+        mask = torch.ones(ybuf.shape[-1], dtype=torch.bool)
+        c0 = off // ybuf.element_size()
+        mask[c0:c0 + cout] = False
+        assert bool((ybuf[..., mask.to(dev())].float() == -3.0).all()), "kernel wrote outside its channel slice"
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_direct(case):
+    _run_conv_case(case, L.IMPL_DIRECT)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_tcgen05(case):
+    _run_conv_case(case, L.IMPL_TCGEN05)
+
+
+def test_conv2d_tcgen05_many_tiles_persistent():
+    # more tiles than SMs so every CTA loops (pipeline phases, TMEM double buffering)
+    _run_conv_case((8, 80, 80, 64, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=3)
+    _run_conv_case((16, 80, 80, 64, 128, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=4)
+    _run_conv_case((4, 160, 160, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=5)
+
+
+def test_stem_conv():
+    g = torch.Generator().manual_seed(1)
+    for cout in (8, 16, 32):
+        x = torch.rand(2, 3, 40, 56, generator=g)
+        wt = torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5
+        b = torch.randn(cout, generator=g) * 0.3
+        ybuf, yv = empty_nhwc(2, 40, 56, cout)
+        rc = L.require_device().dbl_stem_conv(x.to(dev()).data_ptr(), 2, 40, 56, wt.to(dev()).data_ptr(), b.to(dev()).data_ptr(),
+                                              C.byref(yv), 1, stream())
+        torch.cuda.synchronize()
+        assert rc == 0
+        assert_close_bf16(from_nhwc(ybuf, 0, cout), F.silu(F.conv2d(x, wt, b, 1, 1)), f"stem cout={cout}")
+
+
+@pytest.mark.parametrize("k,s,d,act,bias", [(3, 1, 1, L.ACT_NONE, False), (3, 2, 1, L.ACT_NONE, False), (7, 1, 1, L.ACT_NONE, False),
+                                            (5, 1, 1, L.ACT_NONE, True), (7, 1, 3, L.ACT_NONE, True), (3, 1, 1, L.ACT_SILU, True)])
+def test_dwconv(k, s, d, act, bias):
+    g = torch.Generator().manual_seed(2)
+    n, c, h, w = 2, 64, 20, 28
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    wt = torch.randn(c, 1, k, k, generator=g) / k
+    b = torch.randn(c, generator=g) if bias else None
+    pad = d * (k - 1) // 2
+    ref = _act_ref(F.conv2d(x, wt, b, s, pad, d, c), act)
+    xbuf, xv = to_nhwc(x, pad_c=8)
+    ybuf, yv = empty_nhwc(n, ref.shape[2], ref.shape[3], c)
+    wd = wt.reshape(c, k * k).t().contiguous().to(dev())
+    rc = L.require_device().dbl_dwconv2d(C.byref(xv), wd.data_ptr(), None if b is None else b.to(dev()).data_ptr(), C.byref(yv), k, s, d,
+                                         act, stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(ybuf, 0, c), ref, f"dwconv k{k} s{s} d{d}")
+
+
+def test_pool_upsample_gate_copy():
+    lib = L.require_device()
+    g = torch.Generator().manual_seed(3)
+    x = bf16_round(torch.randn(2, 32, 16, 24, generator=g))
+    b = bf16_round(torch.randn(2, 32, 16, 24, generator=g))
+    xbuf, xv = to_nhwc(x, pad_c=16, c_off=8)
+    bbuf, bv = to_nhwc(b)
+    ybuf, yv = empty_nhwc(2, 8, 12, 32, pad_c=32, c_off=32)
+    assert lib.dbl_avgpool2(C.byref(xv), C.byref(yv), stream()) == 0
+    torch.cuda.synchronize()
+    assert_close_bf16(from_nhwc(ybuf, 32, 32), F.avg_pool2d(x, 2), "avgpool2", abs_=1e-2)
+    ybuf, yv = empty_nhwc(2, 32, 48, 32)
+    assert lib.dbl_upsample2_nearest(C.byref(xv), C.byref(yv), stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(from_nhwc(ybuf, 0, 32), F.interpolate(x, scale_factor=2, mode="nearest"))
+    ybuf, yv = empty_nhwc(2, 16, 24, 32)
+    y2buf, y2v = empty_nhwc(2, 16, 24, 32, pad_c=8)
+    assert lib.dbl_gated_add(C.byref(xv), C.byref(bv), C.c_float(0.5), C.byref(yv), C.byref(y2v), stream()) == 0
+    torch.cuda.synchronize()
+    assert_close_bf16(from_nhwc(ybuf, 0, 32), x + 0.5 * b, "gated_add", abs_=1e-2)
+    assert torch.equal(from_nhwc(ybuf, 0, 32), from_nhwc(y2buf, 0, 32))
+    ybuf, yv = empty_nhwc(2, 16, 24, 32)
+    assert lib.dbl_copy(C.byref(xv), C.byref(yv), stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(from_nhwc(ybuf, 0, 32), x)
+
+
+def test_dysample_vs_oracle():
+    lib = L.require_device()
+    g = torch.Generator().manual_seed(4)
+    n, c, h, w = 2, 64, 10, 14
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    off_raw = torch.randn(n, 32, h, w, generator=g) * 2.0  # large offsets: exercises the border clamp
+    # oracle: feed the same raw offsets through DySample's own math by making its 1x1 conv the identity on a stub input
+    sd = {"p.offset.weight": torch.zeros(32, c, 1, 1), "p.offset.bias": torch.zeros(32), "p.init_pos": O.dysample_init_pos()}
+    orig = F.conv2d
+
+    def fake_conv(inp, wt, bias=None, *a, **k):
+        return off_raw if wt is sd["p.offset.weight"] else orig(inp, wt, bias, *a, **k)
+
+    F.conv2d = fake_conv
+    try:
+        ref = O.dysample(sd, "p", x)
+    finally:
+        F.conv2d = orig
+    xbuf, xv = to_nhwc(x)
+    obuf, ov = to_nhwc(off_raw, dtype=torch.float32)
+    ybuf, yv = empty_nhwc(n, 2 * h, 2 * w, c)
+    assert lib.dbl_dysample(C.byref(xv), C.byref(ov), C.byref(yv), 4, stream()) == 0, lib.dbl_last_error().decode()
+    torch.cuda.synchronize()
+    assert_close_bf16(from_nhwc(ybuf, 0, c), ref, "dysample")
+
+
+def test_lsk_squeeze_gate_vs_torch():
+    lib = L.require_device()
+    g = torch.Generator().manual_seed(5)
+    n, half, h, w = 2, 64, 12, 20
+    a = bf16_round(torch.randn(n, 2 * half, h, w, generator=g))
+    wsq = torch.randn(2, 2, 7, 7, generator=g) * 0.2
+    bsq = torch.randn(2, generator=g)
+    agg = torch.cat([a.mean(1, keepdim=True), a.max(1, keepdim=True)[0]], 1)
+    sig = F.conv2d(agg, wsq, bsq, 1, 3).sigmoid()
+    ref = a[:, :half] * sig[:, 0:1] + a[:, half:] * sig[:, 1:2]
+    abuf, av = to_nhwc(a)
+    gbuf, gv = empty_nhwc(n, h, w, 2, torch.float32)
+    ybuf, yv = empty_nhwc(n, h, w, half)
+    assert lib.dbl_lsk_squeeze(C.byref(av), C.byref(gv), stream()) == 0
+    assert lib.dbl_lsk_gate(C.byref(av), C.byref(gv), wsq.reshape(-1).to(dev()).data_ptr(), bsq.to(dev()).data_ptr(), C.byref(yv),
+                            stream()) == 0
+    torch.cuda.synchronize()
+    torch.testing.assert_close(from_nhwc(gbuf, 0, 2), agg, rtol=1e-4, atol=1e-4)
+    assert_close_bf16(from_nhwc(ybuf, 0, half), ref, "lsk gate")
+
+
+@pytest.mark.parametrize("D,E,hw", [(64, 4, (20, 20)), (128, 8, (12, 10)), (256, 8, (8, 8))])
+def test_hypergraph_vs_oracle(D, E, hw):
+    lib = L.require_device()
+    g = torch.Generator().manual_seed(6)
+    B, (h, w) = 2, hw
+    x = bf16_round(torch.randn(B, D, h, w, generator=g))
+    p = "m.hgnn"
+    sd = {
+        p + ".edge_generator.prototype_base": torch.randn(E, D, generator=g) * 0.5,
+        p + ".edge_generator.context_net.weight": torch.randn(E * D, 2 * D, generator=g) / (2 * D) ** 0.5,
+        p + ".edge_generator.context_net.bias": torch.randn(E * D, generator=g) * 0.1,
+        p + ".edge_generator.pre_head_proj.weight": torch.randn(D, D, generator=g) / D ** 0.5,
+        p + ".edge_generator.pre_head_proj.bias": torch.randn(D, generator=g) * 0.1,
+        p + ".edge_proj.0.weight": torch.randn(D, D, generator=g) / D ** 0.5, p + ".edge_proj.0.bias": torch.randn(D, generator=g) * 0.1,
+        p + ".node_proj.0.weight": torch.randn(D, D, generator=g) / D ** 0.5, p + ".node_proj.0.bias": torch.randn(D, generator=g) * 0.1,
+    }
+    tok = O.hypergraph_conv(sd, p, x.flatten(2).transpose(1, 2), D // 16)
+    ref = tok.transpose(1, 2).reshape(B, D, h, w)
+    keep = {k: v.to(dev()).contiguous() for k, v in sd.items()}
+    wt = L.HypergraphWeights(*[keep[p + s].data_ptr() for s in (
+        ".edge_generator.prototype_base", ".edge_generator.context_net.weight", ".edge_generator.context_net.bias",
+        ".edge_generator.pre_head_proj.weight", ".edge_generator.pre_head_proj.bias", ".edge_proj.0.weight", ".edge_proj.0.bias",
+        ".node_proj.0.weight", ".node_proj.0.bias")], E, D // 16)
+    xbuf, xv = to_nhwc(x, pad_c=D)  # tokens are a channel slice, as inside C3AH
+    ybuf, yv = empty_nhwc(B, h, w, D)
+    nbytes = lib.dbl_hypergraph_workspace_bytes(B, h * w, D, E)
+    ws = torch.zeros(nbytes // 4 + 4, device=dev())
+    rc = lib.dbl_hypergraph(C.byref(xv), C.byref(wt), C.byref(yv), ws.data_ptr(), C.c_size_t(nbytes), stream())
+    torch.cuda.synchronize()
+    assert rc == 0, lib.dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(ybuf, 0, D), ref, f"hypergraph D={D} E={E}")
+    # in place (as the engine uses it)
+    rc = lib.dbl_hypergraph(C.byref(xv), C.byref(wt), C.byref(xv), ws.data_ptr(), C.c_size_t(nbytes), stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert_close_bf16(from_nhwc(xbuf, 0, D), ref, f"hypergraph in place D={D}")
+
+
+def test_argument_errors_are_reported_not_thrown():
+    lib = L.require_device()
+    xbuf, xv = empty_nhwc(1, 8, 8, 16)
+    ybuf, yv = empty_nhwc(1, 8, 8, 16)
+    assert lib.dbl_conv2d(C.byref(xv), None, None, None, C.byref(yv), 3, 1, 1, 1, 0, 0, 0, stream()) == 1  # DBL_E_ARG
+    assert b"null" in lib.dbl_last_error()
+    bad = L.view(ybuf, 0, 16)
+    bad.h = 9
+    w = torch.zeros(16 * 9 * 16, dtype=torch.bfloat16, device=dev())
+    assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(bad), 3, 1, 1, 1, 0, 0, 0, stream()) == 1
+    assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(yv), 3, 1, 1, 2, 0, 0, L.IMPL_TCGEN05, stream()) == 2  # unsupported

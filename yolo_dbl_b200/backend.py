@@ -1,0 +1,291 @@
+"""Drop-in seams of the reference, re-hosted on libdbl_sm100.
+
+B1  ``DBLBackend``            - a ``DetectionModel``-compatible ``nn.Module`` (reference ``nn/tasks.py:313-359``):
+                                ``forward(x) -> (y, feats)``, ``.stride``, ``.names``, ``.yaml``, ``.fuse()`` ...
+B2  the attribute surface ``BasePredictor`` reads off its model (reference ``engine/predictor.py:306-321``).
+B3  ``non_max_suppression``   - same signature and return type as ``utils/ops.py:167-182``.
+    ``YOLO`` / ``Results`` / ``Boxes`` - the thin facade the GPU box needs (the reference's own facade is unavailable
+    there); same names and fields as ``engine/model.py:501-560`` and ``engine/results.py:938-1059``.
+
+Everything here is host glue: shapes, buffers, streams.  All arithmetic runs in the CUDA library; a missing library or
+GPU raises ``DblError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import graph as G
+from .engine import DBLEngine
+from .synth import synth_state_dict
+
+
+class DBLBackend(nn.Module):
+    """B200 executor behind the reference's model interface.
+
+    Build from a graph description + a reference-compatible ``state_dict`` (``from_state_dict``), from a live reference
+    ``DetectionModel`` (``from_reference``) or with synthetic weights (``synthetic``).  Engines are specialised per input
+    shape and cached.
+    """
+
+    def __init__(self, spec: G.GraphSpec, state_dict: Dict[str, torch.Tensor], device="cuda", names=None, cfg=None,
+                 use_graph: bool = True, conv_impl: int = L.IMPL_AUTO):
+        super().__init__()
+        L.load()  # fail early and loudly when the CUDA library has not been built
+        self.spec = spec
+        self._sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        missing = [k for k in G.param_shapes(spec) if k not in self._sd]
+        if missing:
+            raise KeyError(f"state_dict lacks {len(missing)} keys, e.g. {missing[:3]}")
+        self._device = torch.device(device)
+        self._engines: Dict[tuple, DBLEngine] = {}
+        self.use_graph, self.conv_impl = use_graph, conv_impl
+        # --- attribute surface read by AutoBackend / BasePredictor
+        self.stride = torch.tensor([float(s) for s in spec.strides])
+        self.names = names or {i: f"{i}" for i in range(spec.nc)}
+        self.nc = spec.nc
+        self.yaml = cfg if isinstance(cfg, dict) else dict(G.load_cfg(cfg), scale=spec.scale, nc=spec.nc)
+        self.args = {}
+        self.task = "detect"
+        self.pt, self.triton, self.fp16, self.dynamic, self.imx = True, False, False, False, False
+        self.training = False
+
+    # ---- construction -------------------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, state_dict, scale="n", nc=None, cfg=None, **kw) -> "DBLBackend":
+        if nc is None:
+            nc = [v.shape[0] for k, v in state_dict.items() if ".cv3." in k and k.endswith(".2.weight")][0]
+        return cls(G.resolve(cfg, scale, nc), state_dict, cfg=cfg, **kw)
+
+    @classmethod
+    def from_reference(cls, model, **kw) -> "DBLBackend":
+        """model: the reference's DetectionModel (fused or not; BN is folded here either way)."""
+        y = model.yaml
+        sd = model.state_dict()
+        if not any(k.endswith(".bn.weight") for k in sd):
+            raise ValueError("pass the UNFUSED reference model: fuse() drops the BatchNorm buffers the packer folds itself")
+        return cls(G.resolve(y, y.get("scale", "n"), y.get("nc")), sd, names=getattr(model, "names", None), cfg=y, **kw)
+
+    @classmethod
+    def synthetic(cls, scale="n", nc=80, seed=0, cfg=None, **kw) -> "DBLBackend":
+        spec = G.resolve(cfg, scale, nc)
+        return cls(spec, synth_state_dict(G.param_shapes(spec), seed), cfg=cfg, **kw)
+
+    # ---- nn.Module-ish no-ops the callers expect --------------------------------------------------------------------
+    def fuse(self, verbose=False):
+        return self  # BatchNorm is always folded at pack time
+
+    def eval(self):
+        return self
+
+    def half(self):
+        return self  # activations are bf16 already; the post-process stays fp32
+
+    def float(self):
+        return self
+
+    def to(self, device=None, *a, **k):
+        if device is not None and torch.device(device).type == "cuda" and torch.device(device) != self._device:
+            self._device = torch.device(device)
+            self._engines.clear()
+        return self
+
+    @property
+    def device(self):
+        return self._device
+
+    def warmup(self, imgsz=(1, 3, 640, 640)):
+        self.engine(imgsz[0], imgsz[2], imgsz[3])
+
+    def state_dict(self, *a, **k):
+        return dict(self._sd)
+
+    # ---- execution ----------------------------------------------------------------------------------------------
+    def engine(self, b: int, h: int, w: int) -> DBLEngine:
+        key = (int(b), int(h), int(w))
+        if key not in self._engines:
+            self._engines[key] = DBLEngine(self.spec, self._sd, *key, device=self._device, use_graph=self.use_graph,
+                                           conv_impl=self.conv_impl)
+        return self._engines[key]
+
+    def _prep(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected BCHW input with 3 channels, got {tuple(x.shape)}")
+        L.require_device()  # no GPU / wrong GPU -> DblError, never a silent fallback
+        return x.to(self._device, torch.float32, non_blocking=True)
+
+    def forward(self, x, augment=False, visualize=False, embed=None):
+        if augment or visualize or embed is not None:
+            raise NotImplementedError("augment / visualize / embed are outside the B200 hot path")
+        x = self._prep(x)
+        y, feats = self.engine(*x.shape[0:1], *x.shape[2:]).forward(x)
+        return y.clone(), [f.clone() for f in feats]
+
+    __call__ = forward
+
+    def detect(self, x, conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None,
+               max_nms=30000):
+        """Fused forward + decode + NMS.  Returns (rows [B,max_det,6], counts [B]) living in engine-owned buffers."""
+        x = self._prep(x)
+        rows, counts, _ = self.engine(x.shape[0], x.shape[2], x.shape[3]).detect(
+            x, conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms)
+        return rows, counts
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# B3: non_max_suppression
+# ---------------------------------------------------------------------------------------------------------------------
+class _NmsWorkspace:
+    """Buffers for one (batch, capacity, max_det) shape, reused across calls."""
+
+    _cache: Dict[tuple, "_NmsWorkspace"] = {}
+
+    def __init__(self, dev, B, cap, max_det):
+        lib = L.load()
+        self.box = torch.zeros(B, cap, 4, device=dev)
+        self.score = torch.zeros(B, cap, device=dev)
+        self.cls = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+        self.pos = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+        self.count = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.keys = torch.zeros(B * lib.dbl_nms_sort_capacity(cap), dtype=torch.int64, device=dev)
+        self.rows = torch.zeros(B, max_det, 6, device=dev)
+        self.out_pos = torch.zeros(B, max_det, dtype=torch.int32, device=dev)
+        self.out_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.cand = L.Candidates(self.box.data_ptr(), self.score.data_ptr(), self.cls.data_ptr(), self.pos.data_ptr(),
+                                 self.count.data_ptr(), cap, B)
+
+    @classmethod
+    def get(cls, dev, B, cap, max_det):
+        key = (str(dev), B, cap, max_det)
+        if key not in cls._cache:
+            cls._cache[key] = cls(dev, B, cap, max_det)
+        return cls._cache[key]
+
+
+def nms_raw(prediction: torch.Tensor, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+            max_det=300, max_nms=30000, max_wh=7680):
+    """Device-side result of the two NMS kernels: (rows [B,max_det,6], counts [B] int32, positions [B,max_det] int32).
+
+    ``positions`` is the index each kept box had in the reference's filtered list ordering: the anchor index (or
+    anchor*nc + class with multi_label).  No host synchronisation happens here.
+    """
+    lib = L.require_device()
+    if prediction.dim() != 3:
+        raise ValueError("prediction must be (B, 4+nc, A)")
+    pred = prediction if prediction.dtype == torch.float32 else prediction.float()
+    B, no, A = pred.shape
+    nc = no - 4
+    ml = bool(multi_label) and nc > 1
+    ws = _NmsWorkspace.get(pred.device, B, A * (nc if ml else 1), int(max_det))
+    cls_t = torch.tensor(list(classes), dtype=torch.int32, device=pred.device) if classes is not None else None
+    with torch.cuda.device(pred.device):
+        s = L.current_stream()
+        sb, sc, sa = pred.stride()
+        L.check(lib.dbl_nms_filter(pred.data_ptr(), B, nc, A, sb, sc, sa, C.c_float(conf_thres), int(ml), L.ptr(cls_t),
+                                   0 if cls_t is None else cls_t.numel(), C.byref(ws.cand), s), "dbl_nms_filter")
+        L.check(lib.dbl_nms(C.byref(ws.cand), C.c_float(iou_thres), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
+                            ws.keys.data_ptr(), ws.rows.data_ptr(), ws.out_pos.data_ptr(), ws.out_count.data_ptr(), s), "dbl_nms")
+    return ws.rows, ws.out_count, ws.out_pos
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                        labels=(), max_det=300, nc=0, max_time_img=0.05, max_nms=30000, max_wh=7680, in_place=True,
+                        rotated=False) -> List[torch.Tensor]:
+    """Drop-in for ``ultralytics.utils.ops.non_max_suppression`` (reference ``utils/ops.py:167-316``).
+
+    Same arguments, same return type: a list of ``(n_i, 6)`` tensors ``(x1, y1, x2, y2, conf, cls)`` in descending score
+    order.  Differences, all deliberate: the input is never modified (``in_place`` is accepted and ignored), there is
+    no wall-clock abort (``max_time_img`` ignored; reference ops.py:312-314 silently drops images), and the paths the
+    YOLO-DBL head never takes (``rotated``, mask channels ``nc < C-4``, a-priori ``labels``) raise NotImplementedError.
+    """
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]
+    if rotated or (labels and any(len(l) for l in labels)) or (nc and nc != prediction.shape[1] - 4):
+        raise NotImplementedError("rotated boxes, a-priori labels and mask channels are outside the YOLO-DBL hot path")
+    if prediction.shape[-1] == 6:  # end2end models (not YOLO-DBL): pass through like the reference
+        return [p[p[:, 4] > conf_thres][:max_det] for p in prediction]
+    rows, counts, _ = nms_raw(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    counts = counts.tolist()  # the one host sync: callers of this API want variable-length tensors
+    return [rows[i, : counts[i]].clone() for i in range(len(counts))]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# facade: YOLO(...).predict(...) -> list[Results]
+# ---------------------------------------------------------------------------------------------------------------------
+class Boxes:
+    """Subset of ``ultralytics.engine.results.Boxes`` (reference ``engine/results.py:938-1059``)."""
+
+    def __init__(self, data: torch.Tensor, orig_shape):
+        self.data, self.orig_shape = data, orig_shape
+
+    xyxy = property(lambda s: s.data[:, :4])
+    conf = property(lambda s: s.data[:, 4])
+    cls = property(lambda s: s.data[:, 5])
+
+    @property
+    def xywh(self):
+        b = self.data[:, :4]
+        return torch.stack([(b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], 1)
+
+    @property
+    def xyxyn(self):
+        h, w = self.orig_shape
+        return self.data[:, :4] / torch.tensor([w, h, w, h], device=self.data.device, dtype=self.data.dtype)
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def cpu(self):
+        return Boxes(self.data.cpu(), self.orig_shape)
+
+
+class Results:
+    """Subset of ``ultralytics.engine.results.Results`` (reference ``engine/results.py:187-271``)."""
+
+    def __init__(self, boxes: torch.Tensor, orig_shape, names, path="", speed=None):
+        self.boxes = Boxes(boxes, orig_shape)
+        self.orig_shape, self.names, self.path = orig_shape, names, path
+        self.speed = speed or {}
+
+    def __len__(self):
+        return len(self.boxes)
+
+
+class YOLO:
+    """``YOLO('yolov13n_DBL.yaml').predict(tensor)`` on the B200 path (reference ``models/yolo/model.py:11`` and
+    ``engine/model.py:501-560``).  Only the tensor source of ``LoadTensor`` (``data/loaders.py:516-584``) is supported:
+    BCHW float in 0..1 with H, W divisible by 32, so boxes need no rescaling (``scale_boxes`` is the identity)."""
+
+    def __init__(self, model="yolov13n_DBL.yaml", task="detect", nc: Optional[int] = None, seed: int = 0, device="cuda",
+                 state_dict=None, verbose=False):
+        if task != "detect":
+            raise NotImplementedError("only the detect task is on the YOLO-DBL hot path")
+        import os
+
+        scale = G.scale_from_name(os.path.basename(str(model)))
+        cfg = model if (isinstance(model, dict) or (isinstance(model, str) and os.path.exists(model))) else None
+        spec = G.resolve(cfg, scale, nc)
+        sd = state_dict if state_dict is not None else synth_state_dict(G.param_shapes(spec), seed)
+        self.model = DBLBackend(spec, sd, device=device, cfg=cfg)
+        self.names = self.model.names
+        self.overrides = {"conf": 0.25, "iou": 0.7, "max_det": 300, "agnostic_nms": False, "classes": None}  # cfg/default.yaml:51-65
+
+    def predict(self, source, conf=None, iou=None, max_det=None, agnostic_nms=None, classes=None, **kw) -> List[Results]:
+        o = self.overrides
+        if not isinstance(source, torch.Tensor):
+            raise NotImplementedError("pass a BCHW float tensor in 0..1 (LoadTensor source)")
+        rows, counts = self.model.detect(
+            source, conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
+            agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
+            max_det=o["max_det"] if max_det is None else max_det, classes=classes if classes is not None else o["classes"])
+        counts = counts.tolist()
+        shape = tuple(source.shape[2:])
+        return [Results(rows[i, : counts[i]].clone(), shape, self.names, path=f"image{i}.jpg") for i in range(len(counts))]
+
+    __call__ = predict

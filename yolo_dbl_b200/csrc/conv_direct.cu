@@ -1,0 +1,278 @@
+// CUDA-core convolutions: the fp32 NCHW -> bf16 NHWC stem, a generic direct convolution (used where the tensor-core
+// implicit GEMM does not apply: Cin % 16 != 0, dilation, forced by the caller) and the depthwise convolution.
+#include "dbl_common.cuh"
+
+namespace dbl {
+int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int k,
+                   int stride, int pad, int act, int epi, cudaStream_t st);
+bool conv2d_tcgen05_eligible(const dbl_tensor* x, const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int pad,
+                             int dil);
+
+// ------------------------------------------------------------------------------------------------------------------
+// stem: x f32 NCHW (n,3,h,w) -> y bf16 NHWC (n,ho,wo,COUT), 3x3, pad 1, SiLU
+// ------------------------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                        int n, int h, int wd, int ho, int wo, int stride, int ypitch) {
+    __shared__ __align__(16) float sw[27 * COUT];  // [ci][ky][kx][co]
+    __shared__ float sb[COUT];
+    for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
+        int co = i % COUT, j = i / COUT;  // j = ci*9 + ky*3 + kx ; source layout [co][ci][ky][kx]
+        sw[i] = w[co * 27 + j];
+    }
+    if (threadIdx.x < COUT) sb[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    if (ox >= wo) return;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = sb[c];
+    const int iy0 = oy * stride - 1, ix0 = ox * stride - 1;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+        const float* xp = x + ((size_t)b * 3 + ci) * h * wd;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ix0 + kx;
+                if (ix < 0 || ix >= wd) continue;
+                const float v = __ldg(xp + (size_t)iy * wd + ix);
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * COUT);
+#pragma unroll
+                for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                    const float4 ww = wp[c4];
+                    acc[4 * c4 + 0] = fmaf(v, ww.x, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+                }
+            }
+        }
+    }
+    __nv_bfloat16* yp = y + (((size_t)b * ho + oy) * wo + ox) * ypitch;
+#pragma unroll
+    for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = silu_f(acc[c8 * 8 + i]);
+        stg8(yp + c8 * 8, pack8(o));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic direct conv.  One thread = one output pixel x 8 output channels; weights of the 8-channel group staged in
+// shared memory as f32 [tap*cin][8] so a warp reads them as broadcasts.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DC_THREADS = 128;
+constexpr int DC_CO = 8;
+
+__global__ void __launch_bounds__(DC_THREADS) conv_direct_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+    const __nv_bfloat16* __restrict__ r, void* __restrict__ y, int n, int h, int wd, int cin, int xpitch, int ho, int wo,
+    int cout, int ypitch, int ydtype, int rpitch, int k, int stride, int pad, int dil, int act, int epi, int cin_chunk) {
+    extern __shared__ __align__(16) float swt[];  // [k*k][cin_chunk][8]
+    const int co0 = blockIdx.y * DC_CO;
+    const long long total = (long long)n * ho * wo;
+    const long long pix = (long long)blockIdx.x * DC_THREADS + threadIdx.x;
+    const bool live = pix < total;
+    int b = 0, oy = 0, ox = 0;
+    if (live) {
+        ox = (int)(pix % wo);
+        oy = (int)((pix / wo) % ho);
+        b = (int)(pix / ((long long)wo * ho));
+    }
+    float acc[DC_CO];
+#pragma unroll
+    for (int i = 0; i < DC_CO; ++i) acc[i] = (bias && co0 + i < cout) ? bias[co0 + i] : 0.f;
+    const int kk = k * k;
+    for (int c0 = 0; c0 < cin; c0 += cin_chunk) {
+        const int cc = min(cin_chunk, cin - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kk * cc * DC_CO; i += DC_THREADS) {
+            const int co = i % DC_CO, ci = (i / DC_CO) % cc, tap = i / (DC_CO * cc);
+            swt[i] = (co0 + co < cout) ? __bfloat162float(w[((size_t)(co0 + co) * kk + tap) * cin + c0 + ci]) : 0.f;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int tap = 0; tap < kk; ++tap) {
+            const int iy = oy * stride - pad + (tap / k) * dil;
+            const int ix = ox * stride - pad + (tap % k) * dil;
+            if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
+            const __nv_bfloat16* xp = x + (((size_t)b * h + iy) * wd + ix) * xpitch + c0;
+            const float* wp = swt + (size_t)tap * cc * DC_CO;
+            for (int ci = 0; ci < cc; ci += 8) {
+                float xv[8];
+                unpack8(ldg8(xp + ci), xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp + (ci + j) * DC_CO);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wp + (ci + j) * DC_CO + 4);
+                    acc[0] = fmaf(xv[j], w0.x, acc[0]);
+                    acc[1] = fmaf(xv[j], w0.y, acc[1]);
+                    acc[2] = fmaf(xv[j], w0.z, acc[2]);
+                    acc[3] = fmaf(xv[j], w0.w, acc[3]);
+                    acc[4] = fmaf(xv[j], w1.x, acc[4]);
+                    acc[5] = fmaf(xv[j], w1.y, acc[5]);
+                    acc[6] = fmaf(xv[j], w1.z, acc[6]);
+                    acc[7] = fmaf(xv[j], w1.w, acc[7]);
+                }
+            }
+        }
+    }
+    if (!live) return;
+    const size_t opix = ((size_t)b * ho + oy) * wo + ox;
+#pragma unroll
+    for (int i = 0; i < DC_CO; ++i) {
+        if (co0 + i >= cout) break;
+        float v = apply_act(acc[i], act);
+        if (epi != DBL_EPI_NONE) {
+            const float rv = __bfloat162float(r[opix * rpitch + co0 + i]);
+            v = (epi == DBL_EPI_ADD) ? v + rv : v * rv;
+        }
+        st_elem(y, ydtype, opix * ypitch + co0 + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// depthwise conv: one thread = one output pixel x 8 channels (one 16-byte load per tap)
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n,
+                                                     int h, int wd, int c, int xpitch, int ho, int wo, int ypitch,
+                                                     int stride, int dil, int act) {
+    const int cg = c / 8;
+    const long long total = (long long)n * ho * wo * cg;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % cg);
+    const long long pix = idx / cg;
+    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), b = (int)(pix / ((long long)wo * ho));
+    const int pad = dil * (K - 1) / 2;
+    float acc[8];
+    if (bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
+        acc[0] = b0.x, acc[1] = b0.y, acc[2] = b0.z, acc[3] = b0.w, acc[4] = b1.x, acc[5] = b1.y, acc[6] = b1.z, acc[7] = b1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    }
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * stride - pad + ky * dil;
+        if (iy < 0 || iy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const int ix = ox * stride - pad + kx * dil;
+            if (ix < 0 || ix >= wd) continue;
+            float xv[8];
+            unpack8(ldg8(x + (((size_t)b * h + iy) * wd + ix) * xpitch + g * 8), xv);
+            const float* wp = w + (size_t)(ky * K + kx) * c + g * 8;
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+            acc[0] = fmaf(xv[0], w0.x, acc[0]);
+            acc[1] = fmaf(xv[1], w0.y, acc[1]);
+            acc[2] = fmaf(xv[2], w0.z, acc[2]);
+            acc[3] = fmaf(xv[3], w0.w, acc[3]);
+            acc[4] = fmaf(xv[4], w1.x, acc[4]);
+            acc[5] = fmaf(xv[5], w1.y, acc[5]);
+            acc[6] = fmaf(xv[6], w1.z, acc[6]);
+            acc[7] = fmaf(xv[7], w1.w, acc[7]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = apply_act(acc[i], act);
+    stg8(y + (((size_t)b * ho + oy) * wo + ox) * ypitch + g * 8, pack8(acc));
+}
+
+}  // namespace dbl
+
+using namespace dbl;
+
+extern "C" int dbl_stem_conv(const float* x, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
+                             int stride, dbl_stream_t stream) {
+    DBL_REQUIRE(x && w && valid_tensor(y), DBL_E_ARG, "dbl_stem_conv: null/invalid argument");
+    DBL_REQUIRE(stride == 1 || stride == 2, DBL_E_ARG, "dbl_stem_conv: stride %d", stride);
+    const int ho = (h + 2 - 3) / stride + 1, wo = (w_ + 2 - 3) / stride + 1;
+    DBL_REQUIRE(y->n == n && y->h == ho && y->w == wo, DBL_E_ARG, "dbl_stem_conv: output shape mismatch");
+    DBL_REQUIRE(vec8_ok(y), DBL_E_ARG, "dbl_stem_conv: y must be bf16 with 16-byte aligned channel groups");
+    dim3 grid(cdiv(wo, 256), ho, n), block(256);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
+    cudaStream_t st = as_stream(stream);
+    switch (y->c) {
+        case 8: stem_conv_kernel<8><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 16: stem_conv_kernel<16><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 32: stem_conv_kernel<32><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_stem_conv: cout %d not in {8,16,32}", y->c);
+    }
+    count_launch();
+    return check_launch("dbl_stem_conv");
+}
+
+extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
+                          int k, int stride, int pad, int dil, int act, int epi, int impl, dbl_stream_t stream) {
+    DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w, DBL_E_ARG, "dbl_conv2d: null/invalid tensor");
+    DBL_REQUIRE(x->dtype == DBL_BF16, DBL_E_ARG, "dbl_conv2d: x must be bf16");
+    DBL_REQUIRE(k >= 1 && k <= 7 && stride >= 1 && dil >= 1 && pad >= 0, DBL_E_ARG, "dbl_conv2d: bad geometry");
+    DBL_REQUIRE(act >= 0 && act <= 2 && epi >= 0 && epi <= 2, DBL_E_ARG, "dbl_conv2d: bad act/epi");
+    const int ho = (x->h + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    const int wo = (x->w + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    DBL_REQUIRE(y->n == x->n && y->h == ho && y->w == wo, DBL_E_ARG, "dbl_conv2d: output shape (%d,%d,%d) != expected (%d,%d,%d)",
+                y->n, y->h, y->w, x->n, ho, wo);
+    if (epi != DBL_EPI_NONE) {
+        DBL_REQUIRE(valid_tensor(r) && same_shape(r, y) && r->dtype == DBL_BF16, DBL_E_ARG, "dbl_conv2d: residual mismatch");
+    }
+    cudaStream_t st = as_stream(stream);
+    const bool tc_ok = conv2d_tcgen05_eligible(x, r, y, k, stride, pad, dil);
+    if (impl == DBL_IMPL_TCGEN05) DBL_REQUIRE(tc_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the tcgen05 path");
+    if (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && tc_ok))
+        return conv2d_tcgen05(x, w, bias, epi ? r : nullptr, y, k, stride, pad, act, epi, st);
+
+    DBL_REQUIRE(vec8_ok(x), DBL_E_UNSUPPORTED, "dbl_conv2d(direct): cin/pitch must be multiples of 8 and 16-byte aligned");
+    int chunk = (48 * 1024) / (k * k * DC_CO * 4);
+    chunk = (chunk / 8) * 8;
+    if (chunk > x->c) chunk = x->c;
+    DBL_REQUIRE(chunk >= 8, DBL_E_UNSUPPORTED, "dbl_conv2d(direct): kernel too large");
+    const size_t smem = (size_t)k * k * chunk * DC_CO * sizeof(float);
+    const long long total = (long long)x->n * ho * wo;
+    dim3 grid((unsigned)((total + DC_THREADS - 1) / DC_THREADS), cdiv(y->c, DC_CO));
+    conv_direct_kernel<<<grid, DC_THREADS, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x->data), reinterpret_cast<const __nv_bfloat16*>(w), bias,
+        epi ? reinterpret_cast<const __nv_bfloat16*>(r->data) : nullptr, y->data, x->n, x->h, x->w, x->c, x->pitch, ho, wo,
+        y->c, y->pitch, y->dtype, epi ? r->pitch : 0, k, stride, pad, dil, act, epi, chunk);
+    count_launch();
+    return check_launch("dbl_conv2d(direct)");
+}
+
+extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bias, const dbl_tensor* y, int k, int stride,
+                            int dil, int act, dbl_stream_t stream) {
+    DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w, DBL_E_ARG, "dbl_dwconv2d: null/invalid tensor");
+    DBL_REQUIRE(vec8_ok(x) && vec8_ok(y) && x->c == y->c, DBL_E_ARG, "dbl_dwconv2d: needs bf16, c %% 8 == 0, aligned, cin == cout");
+    DBL_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0), DBL_E_ARG,
+                "dbl_dwconv2d: weights must be 16-byte aligned");
+    const int pad = dil * (k - 1) / 2;
+    const int ho = (x->h + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    const int wo = (x->w + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+    DBL_REQUIRE(y->n == x->n && y->h == ho && y->w == wo, DBL_E_ARG, "dbl_dwconv2d: output shape mismatch");
+    const long long total = (long long)x->n * ho * wo * (x->c / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    auto* xp = reinterpret_cast<const __nv_bfloat16*>(x->data);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
+    cudaStream_t st = as_stream(stream);
+#define DBL_DW(K) dwconv_kernel<K><<<grid, 256, 0, st>>>(xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, stride, dil, act)
+    switch (k) {
+        case 3: DBL_DW(3); break;
+        case 5: DBL_DW(5); break;
+        case 7: DBL_DW(7); break;
+        default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_dwconv2d: k=%d not in {3,5,7}", k);
+    }
+#undef DBL_DW
+    count_launch();
+    return check_launch("dbl_dwconv2d");
+}

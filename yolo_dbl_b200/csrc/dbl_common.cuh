@@ -1,0 +1,82 @@
+// Shared device/host helpers for libdbl_sm100 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dbl_sm100.h"
+
+namespace dbl {
+
+// ---- error plumbing (no exceptions across the C ABI) -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> DBL_E_CUDA
+
+#define DBL_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::dbl::set_error(__VA_ARGS__); \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+static inline cudaStream_t as_stream(dbl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline bool valid_tensor(const dbl_tensor* t) {
+    return t && t->data && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && t->pitch >= t->c &&
+           (t->dtype == DBL_BF16 || t->dtype == DBL_F32);
+}
+static inline bool same_shape(const dbl_tensor* a, const dbl_tensor* b) {
+    return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
+}
+
+// ---- device math ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float apply_act(float v, int act) {
+    return act == DBL_ACT_SILU ? silu_f(v) : (act == DBL_ACT_GELU ? gelu_f(v) : v);
+}
+
+// 8 bf16 <-> 8 floats through one 16-byte access
+struct alignas(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+__device__ __forceinline__ bf16x8 ldg8(const __nv_bfloat16* p) {
+    return *reinterpret_cast<const bf16x8*>(p);
+}
+__device__ __forceinline__ void stg8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+
+// generic element access for views whose channel count / pitch / base is not 16-byte friendly
+__device__ __forceinline__ float ld_elem(const void* base, int dtype, size_t idx) {
+    return dtype == DBL_F32 ? reinterpret_cast<const float*>(base)[idx]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+__device__ __forceinline__ void st_elem(void* base, int dtype, size_t idx, float v) {
+    if (dtype == DBL_F32)
+        reinterpret_cast<float*>(base)[idx] = v;
+    else
+        reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+static inline bool vec8_ok(const dbl_tensor* t) {  // 16-byte vector access along channels is legal
+    return t->dtype == DBL_BF16 && (t->c % 8 == 0) && (t->pitch % 8 == 0) && ((reinterpret_cast<uintptr_t>(t->data) & 15) == 0);
+}
+
+}  // namespace dbl

@@ -1,0 +1,380 @@
+// Detect post-process: DFL decode, confidence filter with compaction, stable sort + class-offset greedy NMS.
+// Arithmetic that decides WHICH boxes survive (xywh->xyxy, class offset, IoU) is written with explicit round-to-nearest
+// intrinsics so the compiler can never contract a multiply-add: the keep set must equal the reference's
+// torchvision.ops.nms result bit for bit.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "dbl_common.cuh"
+
+namespace dbl {
+
+constexpr int REG_MAX = 16;
+
+struct LevelGeom {
+    const float* data[3];
+    int h[3], w[3];
+    float stride[3];
+    int start[3];  // first anchor index of each level
+    int nl, nc, pitch, A;
+};
+
+static bool make_geom(const dbl_head_levels* lv, LevelGeom* g) {
+    if (!lv || lv->num_levels < 1 || lv->num_levels > 3 || lv->nc < 1 || lv->batch < 1 || lv->pitch < 64 + lv->nc) return false;
+    int a = 0;
+    for (int i = 0; i < 3; ++i) {
+        const bool on = i < lv->num_levels;
+        if (on && (!lv->data[i] || lv->h[i] < 1 || lv->w[i] < 1)) return false;
+        g->data[i] = on ? lv->data[i] : nullptr;
+        g->h[i] = on ? lv->h[i] : 0;
+        g->w[i] = on ? lv->w[i] : 0;
+        g->stride[i] = on ? lv->stride[i] : 0.f;
+        g->start[i] = a;
+        a += g->h[i] * g->w[i];
+    }
+    g->nl = lv->num_levels, g->nc = lv->nc, g->pitch = lv->pitch, g->A = a;
+    return true;
+}
+
+// ---- shared arithmetic -------------------------------------------------------------------------------------------
+// One DFL side: expectation of softmax over 16 bins (block.py:80-83).
+__device__ __forceinline__ float dfl_side(const float* __restrict__ p) {
+    float v[REG_MAX];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+        v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
+    }
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < REG_MAX; ++j) m = fmaxf(m, v[j]);
+    float s = 0.f, e = 0.f;
+#pragma unroll
+    for (int j = 0; j < REG_MAX; ++j) {
+        const float t = expf(v[j] - m);
+        s += t;
+        e = fmaf((float)j, t, e);
+    }
+    return e / s;
+}
+
+// dist2bbox(xywh=True) * stride (tal.py:348-357, head.py:178)
+__device__ __forceinline__ float4 dist_to_xywh(float l, float t, float r, float b, float ax, float ay, float stride) {
+    const float x1 = ax - l, y1 = ay - t, x2 = ax + r, y2 = ay + b;
+    return make_float4((x1 + x2) * 0.5f * stride, (y1 + y2) * 0.5f * stride, (x2 - x1) * stride, (y2 - y1) * stride);
+}
+
+// xywh2xyxy (ops.py:416-433): half = wh/2, xy -+ half, each step rounded once.
+__device__ __forceinline__ float4 xywh_to_xyxy(float4 v) {
+    const float hw = __fmul_rn(v.z, 0.5f), hh = __fmul_rn(v.w, 0.5f);
+    return make_float4(__fsub_rn(v.x, hw), __fsub_rn(v.y, hh), __fadd_rn(v.x, hw), __fadd_rn(v.y, hh));
+}
+
+__device__ __forceinline__ float sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ bool class_allowed(int c, const int32_t* __restrict__ classes, int ncls) {
+    if (!classes) return true;
+    for (int i = 0; i < ncls; ++i)
+        if (classes[i] == c) return true;
+    return false;
+}
+
+// Append one candidate; one atomic per warp (all lanes of a warp belong to the same image).
+__device__ __forceinline__ void push_candidate(bool pred, const dbl_candidates& cd, int b, float4 box, float score, int cls, int pos) {
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cd.count + b, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        const int slot = base + __popc(mask & ((1u << lane) - 1));
+        if (slot < cd.cap) {
+            const size_t o = (size_t)b * cd.cap + slot;
+            reinterpret_cast<float4*>(cd.box)[o] = box;
+            cd.score[o] = score;
+            cd.cls[o] = cls;
+            cd.pos[o] = pos;
+        }
+    }
+}
+
+__device__ __forceinline__ void locate_anchor(const LevelGeom& g, int a, int& lvl, int& cell) {
+    lvl = (g.nl > 2 && a >= g.start[2]) ? 2 : ((g.nl > 1 && a >= g.start[1]) ? 1 : 0);
+    cell = a - g.start[lvl];
+}
+
+// ---- decode to the reference's y layout ---------------------------------------------------------------------------
+// grid (ceil(A/256), B); thread per anchor.
+__global__ void __launch_bounds__(256) decode_kernel(LevelGeom g, float* __restrict__ y) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (a >= g.A) return;
+    int lvl, cell;
+    locate_anchor(g, a, lvl, cell);
+    const float* row = g.data[lvl] + ((size_t)b * g.h[lvl] * g.w[lvl] + cell) * g.pitch;
+    const float ax = (float)(cell % g.w[lvl]) + 0.5f, ay = (float)(cell / g.w[lvl]) + 0.5f;
+    const float4 v = dist_to_xywh(dfl_side(row), dfl_side(row + 16), dfl_side(row + 32), dfl_side(row + 48), ax, ay, g.stride[lvl]);
+    float* yo = y + (size_t)b * (4 + g.nc) * g.A + a;
+    yo[0] = v.x;
+    yo[(size_t)g.A] = v.y;
+    yo[(size_t)2 * g.A] = v.z;
+    yo[(size_t)3 * g.A] = v.w;
+    for (int c = 0; c < g.nc; ++c) yo[(size_t)(4 + c) * g.A] = sigmoid_exact(row[64 + c]);
+}
+
+// ---- fused decode + filter ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_filter_kernel(LevelGeom g, float conf, int multi_label, const int32_t* __restrict__ classes,
+                                                            int ncls, dbl_candidates cd) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const bool live = a < g.A;
+    int lvl = 0, cell = 0;
+    if (live) locate_anchor(g, a, lvl, cell);
+    const float* row = live ? g.data[lvl] + ((size_t)b * g.h[lvl] * g.w[lvl] + cell) * g.pitch : nullptr;
+    float best = -CUDART_INF_F;
+    int bi = 0;
+    if (live) {
+        for (int c = 0; c < g.nc; ++c) {
+            const float s = sigmoid_exact(row[64 + c]);
+            if (s > best) best = s, bi = c;
+        }
+    }
+    const bool any = live && best > conf;
+    float4 box = make_float4(0, 0, 0, 0);
+    if (any) {
+        const float ax = (float)(cell % g.w[lvl]) + 0.5f, ay = (float)(cell / g.w[lvl]) + 0.5f;
+        box = xywh_to_xyxy(dist_to_xywh(dfl_side(row), dfl_side(row + 16), dfl_side(row + 32), dfl_side(row + 48), ax, ay, g.stride[lvl]));
+    }
+    if (!multi_label) {
+        push_candidate(any && class_allowed(bi, classes, ncls), cd, b, box, best, bi, a);
+    } else {
+        for (int c = 0; c < g.nc; ++c) {
+            const float s = any ? sigmoid_exact(row[64 + c]) : 0.f;
+            push_candidate(any && s > conf && class_allowed(c, classes, ncls), cd, b, box, s, c, a * g.nc + c);
+        }
+    }
+}
+
+// ---- filter from a materialised prediction (the reference's y) ----------------------------------------------------
+__global__ void __launch_bounds__(256) filter_kernel(const float* __restrict__ pred, int nc, int A, long long sb, long long sc, long long sa,
+                                                     float conf, int multi_label, const int32_t* __restrict__ classes, int ncls,
+                                                     dbl_candidates cd) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const bool live = a < A;
+    const float* p = pred + (size_t)b * sb + (size_t)(live ? a : 0) * sa;
+    float best = -CUDART_INF_F;
+    int bi = 0;
+    if (live) {
+        for (int c = 0; c < nc; ++c) {
+            const float s = p[(size_t)(4 + c) * sc];
+            if (s > best) best = s, bi = c;
+        }
+    }
+    const bool any = live && best > conf;
+    float4 box = make_float4(0, 0, 0, 0);
+    if (any) box = xywh_to_xyxy(make_float4(p[0], p[(size_t)sc], p[(size_t)2 * sc], p[(size_t)3 * sc]));
+    if (!multi_label) {
+        push_candidate(any && class_allowed(bi, classes, ncls), cd, b, box, best, bi, a);
+    } else {
+        for (int c = 0; c < nc; ++c) {
+            const float s = any ? p[(size_t)(4 + c) * sc] : 0.f;
+            push_candidate(any && s > conf && class_allowed(c, classes, ncls), cd, b, box, s, c, a * nc + c);
+        }
+    }
+}
+
+// ---- sort + NMS ---------------------------------------------------------------------------------------------------
+constexpr int NMS_THREADS = 1024;
+constexpr int NMS_FLAG_CAP = 40960;  // candidates per image the suppression flags can hold (smem bytes)
+
+__host__ __device__ inline size_t next_pow2(size_t v) {
+    size_t p = 32;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Scratch per image (in uint64 units): keys[P] | payload u32[P] (P/2 u64) | boxes float4[P] (2P u64)
+__global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd, float iou_thr, float cls_scale, int max_nms, int max_det,
+                                                               uint64_t* __restrict__ scratch, size_t per_image, float* __restrict__ out_rows,
+                                                               int32_t* __restrict__ out_pos, int32_t* __restrict__ out_count) {
+    __shared__ unsigned char dead[NMS_FLAG_CAP];
+    __shared__ int s_pivot;
+    __shared__ int s_keep[1024];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(cd.count[b], cd.cap);
+    const size_t P = next_pow2((size_t)(n > 0 ? n : 1));
+    uint64_t* keys = scratch + (size_t)b * per_image;
+    const size_t Pcap = next_pow2((size_t)cd.cap);
+    uint32_t* slot_of = reinterpret_cast<uint32_t*>(keys + Pcap);
+    float4* sbox = reinterpret_cast<float4*>(keys + Pcap + Pcap / 2);
+    const size_t cbase = (size_t)b * cd.cap;
+
+    // 1. keys: descending score, ascending position (scores are positive floats: their bit patterns order like the values)
+    for (size_t i = tid; i < P; i += NMS_THREADS) {
+        if (i < (size_t)n) {
+            const uint32_t sbits = __float_as_uint(cd.score[cbase + i]);
+            keys[i] = ((uint64_t)(~sbits) << 32) | (uint32_t)cd.pos[cbase + i];
+            slot_of[i] = (uint32_t)i;
+        } else {
+            keys[i] = ~0ull;
+            slot_of[i] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    // 2. bitonic sort (keys are unique, so the result equals a stable sort by score)
+    for (size_t k = 2; k <= P; k <<= 1) {
+        for (size_t j = k >> 1; j > 0; j >>= 1) {
+            for (size_t t = tid; t < P / 2; t += NMS_THREADS) {
+                const size_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const size_t l = i | j;
+                const uint64_t ki = keys[i], kl = keys[l];
+                const bool up = (i & k) == 0;
+                if ((ki > kl) == up) {
+                    keys[i] = kl, keys[l] = ki;
+                    const uint32_t si = slot_of[i];
+                    slot_of[i] = slot_of[l], slot_of[l] = si;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // 3. class-offset boxes in sorted order (ops.py:289-295), truncated to max_nms (ops.py:285-286)
+    int m = min(n, max_nms);
+    m = min(m, NMS_FLAG_CAP);
+    for (int i = tid; i < m; i += NMS_THREADS) {
+        const size_t s = cbase + slot_of[i];
+        const float4 bx = reinterpret_cast<const float4*>(cd.box)[s];
+        const float off = __fmul_rn((float)cd.cls[s], cls_scale);
+        sbox[i] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+        dead[i] = 0;
+    }
+    if (tid == 0) s_pivot = 0;
+    __syncthreads();
+    // 4. greedy suppression: at most max_det pivots, each one parallel pass over the tail.  `kept` and `cursor` are
+    //    uniform across the block (every thread follows the same pivots).
+    int cursor = 0, kept = 0;
+    while (kept < max_det) {
+        if (tid < 32) {  // warp 0 finds the next live candidate at or after cursor
+            int c = cursor, found = -1;
+            while (c < m) {
+                const int idx = c + tid;
+                const unsigned live = __ballot_sync(0xffffffffu, idx < m && !dead[idx]);
+                if (live) {
+                    found = c + __ffs(live) - 1;
+                    break;
+                }
+                c += 32;
+            }
+            if (tid == 0) {
+                s_pivot = found;
+                if (found >= 0) s_keep[kept] = found;
+            }
+        }
+        __syncthreads();
+        const int pv = s_pivot;
+        if (pv < 0) break;
+        ++kept;
+        if (kept < max_det) {
+            const float4 pb = sbox[pv];
+            const float pa = __fmul_rn(__fsub_rn(pb.z, pb.x), __fsub_rn(pb.w, pb.y));
+            for (int j = pv + 1 + tid; j < m; j += NMS_THREADS) {
+                if (dead[j]) continue;
+                const float4 q = sbox[j];
+                const float qa = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+                const float w = fmaxf(0.f, __fsub_rn(fminf(pb.z, q.z), fmaxf(pb.x, q.x)));
+                const float h = fmaxf(0.f, __fsub_rn(fminf(pb.w, q.w), fmaxf(pb.y, q.y)));
+                const float inter = __fmul_rn(w, h);
+                const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(pa, qa), inter));
+                if (ovr > iou_thr) dead[j] = 1;
+            }
+        }
+        cursor = pv + 1;
+        __syncthreads();  // also orders this round's s_pivot reads before the next round's write
+    }
+    __syncthreads();
+    // 5. emit rows in keep order: x1,y1,x2,y2 (no class offset), conf, cls
+    for (int k = tid; k < max_det; k += NMS_THREADS) {
+        float* ro = out_rows + ((size_t)b * max_det + k) * 6;
+        if (k < kept) {
+            const size_t s = cbase + slot_of[s_keep[k]];
+            const float4 bx = reinterpret_cast<const float4*>(cd.box)[s];
+            ro[0] = bx.x, ro[1] = bx.y, ro[2] = bx.z, ro[3] = bx.w, ro[4] = cd.score[s], ro[5] = (float)cd.cls[s];
+            out_pos[(size_t)b * max_det + k] = cd.pos[s];
+        } else {
+            ro[0] = ro[1] = ro[2] = ro[3] = ro[4] = ro[5] = 0.f;
+            out_pos[(size_t)b * max_det + k] = -1;
+        }
+    }
+    if (tid == 0) out_count[b] = kept;
+}
+
+static bool valid_cand(const dbl_candidates* c) {
+    return c && c->box && c->score && c->cls && c->pos && c->count && c->cap > 0 && c->batch > 0 &&
+           (reinterpret_cast<uintptr_t>(c->box) & 15) == 0;
+}
+
+}  // namespace dbl
+
+using namespace dbl;
+
+extern "C" int dbl_detect_decode(const dbl_head_levels* lv, float* y, dbl_stream_t stream) {
+    LevelGeom g;
+    DBL_REQUIRE(make_geom(lv, &g) && y, DBL_E_ARG, "dbl_detect_decode: invalid head description");
+    DBL_REQUIRE(g.pitch % 4 == 0, DBL_E_ARG, "dbl_detect_decode: pitch must be a multiple of 4 floats");
+    decode_kernel<<<dim3(cdiv(g.A, 256), lv->batch), 256, 0, as_stream(stream)>>>(g, y);
+    count_launch();
+    return check_launch("dbl_detect_decode");
+}
+
+extern "C" int dbl_decode_filter(const dbl_head_levels* lv, float conf_thres, int multi_label, const int32_t* classes,
+                                 int num_classes_kept, const dbl_candidates* cand, dbl_stream_t stream) {
+    LevelGeom g;
+    DBL_REQUIRE(make_geom(lv, &g) && valid_cand(cand), DBL_E_ARG, "dbl_decode_filter: invalid argument");
+    DBL_REQUIRE(g.pitch % 4 == 0 && cand->batch == lv->batch, DBL_E_ARG, "dbl_decode_filter: pitch/batch mismatch");
+    const int ml = (multi_label && g.nc > 1) ? 1 : 0;
+    DBL_REQUIRE(cand->cap >= (ml ? g.A * g.nc : g.A), DBL_E_ARG, "dbl_decode_filter: candidate capacity %d too small", cand->cap);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(cand->count, 0, sizeof(int32_t) * cand->batch, st);
+    DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_decode_filter: memset: %s", cudaGetErrorString(e));
+    decode_filter_kernel<<<dim3(cdiv(g.A, 256), lv->batch), 256, 0, st>>>(g, conf_thres, ml, classes, num_classes_kept, *cand);
+    count_launch();
+    return check_launch("dbl_decode_filter");
+}
+
+extern "C" int dbl_nms_filter(const float* pred, int batch, int nc, int anchors, int64_t stride_b, int64_t stride_c, int64_t stride_a,
+                              float conf_thres, int multi_label, const int32_t* classes, int num_classes_kept,
+                              const dbl_candidates* cand, dbl_stream_t stream) {
+    DBL_REQUIRE(pred && batch > 0 && nc > 0 && anchors > 0 && valid_cand(cand) && cand->batch == batch, DBL_E_ARG,
+                "dbl_nms_filter: invalid argument");
+    const int ml = (multi_label && nc > 1) ? 1 : 0;
+    DBL_REQUIRE(cand->cap >= (ml ? anchors * nc : anchors), DBL_E_ARG, "dbl_nms_filter: candidate capacity %d too small", cand->cap);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(cand->count, 0, sizeof(int32_t) * batch, st);
+    DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_nms_filter: memset: %s", cudaGetErrorString(e));
+    filter_kernel<<<dim3(cdiv(anchors, 256), batch), 256, 0, st>>>(pred, nc, anchors, stride_b, stride_c, stride_a, conf_thres, ml, classes,
+                                                                   num_classes_kept, *cand);
+    count_launch();
+    return check_launch("dbl_nms_filter");
+}
+
+extern "C" size_t dbl_nms_sort_capacity(int cap) {
+    if (cap <= 0) return 0;
+    const size_t P = next_pow2((size_t)cap);
+    return P + P / 2 + 2 * P;
+}
+
+extern "C" int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
+                       uint64_t* sort_keys, float* out_rows, int32_t* out_pos, int32_t* out_count, dbl_stream_t stream) {
+    DBL_REQUIRE(valid_cand(cand) && sort_keys && out_rows && out_pos && out_count, DBL_E_ARG, "dbl_nms: invalid argument");
+    DBL_REQUIRE(max_det >= 1 && max_det <= 1024, DBL_E_UNSUPPORTED, "dbl_nms: max_det %d not in [1,1024]", max_det);
+    DBL_REQUIRE(max_nms >= 1, DBL_E_ARG, "dbl_nms: max_nms");
+    DBL_REQUIRE(std::min(cand->cap, max_nms) <= NMS_FLAG_CAP, DBL_E_UNSUPPORTED,
+                "dbl_nms: min(cap,max_nms)=%d exceeds the %d candidates one image may hold", std::min(cand->cap, max_nms), NMS_FLAG_CAP);
+    DBL_REQUIRE((reinterpret_cast<uintptr_t>(sort_keys) & 15) == 0, DBL_E_ARG, "dbl_nms: scratch must be 16-byte aligned");
+    sort_nms_kernel<<<cand->batch, NMS_THREADS, 0, as_stream(stream)>>>(*cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
+                                                                        sort_keys, dbl_nms_sort_capacity(cand->cap), out_rows, out_pos,
+                                                                        out_count);
+    count_launch();
+    return check_launch("dbl_nms");
+}

@@ -1,0 +1,467 @@
+"""Lowering of the YOLO-DBL layer table to a static list of libdbl_sm100 launches (the B200 executor).
+
+One ``DBLEngine`` is built per (weights, batch, height, width).  Building it
+  * folds every BatchNorm into the preceding convolution (including DSConv's, which the reference leaves unfolded,
+    ``nn/tasks.py:217``) and repacks weights to the kernels' layouts (bf16 ``[Cout][kh][kw][Cin]`` for the implicit
+    GEMM, f32 ``[kh*kw][C]`` for depthwise),
+  * allocates every activation once (NHWC bf16; concat / chunk are channel slices of shared buffers, so the
+    reference's ``torch.cat`` copies disappear),
+  * records the launches as plain ctypes calls, which are then captured into a CUDA graph.
+Replays are sync-free: fixed-capacity outputs + device-side counts.
+
+Reference control flow being replaced: ``BaseModel._predict_once`` (``nn/tasks.py:145-172``) and the module
+``forward`` methods cited next to each ``_lower_*`` function.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .graph import GraphSpec, LayerSpec, detect_channels
+
+BN_EPS = 1e-3  # utils/torch_utils.py:410-420
+
+
+class Act:
+    """Channel slice [off, off+c) of a dense NHWC device buffer."""
+
+    __slots__ = ("buf", "off", "c", "_desc")
+
+    def __init__(self, buf: torch.Tensor, off: int = 0, c: Optional[int] = None):
+        self.buf, self.off = buf, off
+        self.c = buf.shape[3] - off if c is None else c
+        self._desc = None
+
+    n = property(lambda s: s.buf.shape[0])
+    h = property(lambda s: s.buf.shape[1])
+    w = property(lambda s: s.buf.shape[2])
+
+    @property
+    def desc(self) -> L.Tensor:
+        if self._desc is None:
+            self._desc = L.view(self.buf, self.off, self.c)
+        return self._desc
+
+    def slice(self, off: int, c: int) -> "Act":
+        assert off + c <= self.c
+        return Act(self.buf, self.off + off, c)
+
+    def nchw(self) -> torch.Tensor:
+        """fp32 NCHW copy (tests / API compatibility)."""
+        return self.buf[..., self.off:self.off + self.c].permute(0, 3, 1, 2).float().contiguous()
+
+
+def _fold(w: torch.Tensor, sd, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fuse_conv_and_bn (utils/torch_utils.py:238-265) for a bias-free conv."""
+    scale = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + BN_EPS)
+    return w.float() * scale.view(-1, 1, 1, 1), sd[bn + ".bias"].float() - sd[bn + ".running_mean"].float() * scale
+
+
+class DBLEngine:
+    def __init__(self, spec: GraphSpec, state_dict: Dict[str, torch.Tensor], batch: int, height: int, width: int,
+                 device: torch.device | str = "cuda", conv_impl: int = L.IMPL_AUTO, use_graph: bool = True,
+                 keep_layers: bool = False):
+        self.lib = L.require_device()
+        self.spec, self.B, self.H, self.W = spec, int(batch), int(height), int(width)
+        if self.H % 32 or self.W % 32:
+            raise ValueError("input height/width must be multiples of 32 (reference data/loaders.py:516-584)")
+        self.dev = torch.device(device)
+        self.conv_impl = conv_impl
+        self.use_graph = use_graph
+        self.sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
+        self._keep: List[object] = []        # weights, ctypes structs, scratch: everything launches point at
+        self.ops: List[Tuple[Callable, tuple, str]] = []
+        self.layer_out: List[Optional[Act]] = []
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._post_bufs: Dict[tuple, dict] = {}
+        with torch.cuda.device(self.dev):
+            self.x_in = torch.zeros(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
+            self._build()
+        if not keep_layers:
+            self.sd = None
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    def _alloc(self, h: int, w: int, c: int, dtype=torch.bfloat16) -> Act:
+        buf = torch.zeros(self.B, h, w, c, dtype=dtype, device=self.dev)
+        self._keep.append(buf)  # launches hold raw pointers: the engine owns every buffer for its whole life
+        return Act(buf)
+
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        t = t.to(dtype).contiguous().to(self.dev)
+        self._keep.append(t)
+        return t
+
+    def _emit(self, fn, args: tuple, what: str):
+        self._keep.append(args)
+        self.ops.append((fn, args, what))
+
+    def _pack_w(self, w: torch.Tensor) -> torch.Tensor:
+        """[Cout,Cin,kh,kw] f32 -> device bf16 [Cout][kh][kw][Cin]"""
+        return self._dev(w.permute(0, 2, 3, 1), torch.bfloat16)
+
+    def _conv(self, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], y: Act, k: int, s: int, act: int,
+              epi: int = L.EPI_NONE, r: Optional[Act] = None, what: str = "conv"):
+        wd = self._pack_w(w)
+        bd = self._dev(b, torch.float32) if b is not None else None
+        args = (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(r.desc) if r is not None else None, C.byref(y.desc), k, s,
+                k // 2, 1, act, epi, self.conv_impl)
+        self._emit(self.lib.dbl_conv2d, args, what)
+
+    def _conv_bn(self, x: Act, p: str, y: Act, s: int = 1, act: int = L.ACT_SILU, epi=L.EPI_NONE, r=None):
+        """Conv module: conv(bias=False)+BN+SiLU (nn/modules/conv.py:39-63)"""
+        w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
+        self._conv(x, w, b, y, w.shape[-1], s, act, epi, r, what=p)
+
+    def _conv_bn_pair(self, x: Act, p1: str, p2: str, y: Act):
+        """two 1x1 Conv modules reading the same input as ONE GEMM writing [p1 | p2] (C3-style cv1 / cv2)"""
+        w1, b1 = _fold(self.sd[p1 + ".conv.weight"], self.sd, p1 + ".bn")
+        w2, b2 = _fold(self.sd[p2 + ".conv.weight"], self.sd, p2 + ".bn")
+        self._conv(x, torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), y, 1, 1, L.ACT_SILU, what=f"{p1}|cv2")
+
+    def _conv_bias(self, x: Act, p: str, y: Act, epi=L.EPI_NONE, r=None):
+        """plain nn.Conv2d 1x1 with bias, no activation"""
+        self._conv(x, self.sd[p + ".weight"].float(), self.sd[p + ".bias"].float(), y, 1, 1, L.ACT_NONE, epi, r, what=p)
+
+    def _dw(self, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], y: Act, k: int, s: int, d: int, act: int, what: str):
+        wd = self._dev(w.reshape(w.shape[0], k * k).t(), torch.float32)  # [C,1,k,k] -> [k*k][C]
+        bd = self._dev(b, torch.float32) if b is not None else None
+        self._emit(self.lib.dbl_dwconv2d, (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(y.desc), k, s, d, act), what)
+
+    def _dsconv(self, x: Act, p: str, y: Act, s: int = 1, epi=L.EPI_NONE, r=None):
+        """DSConv (conv.py:91-108): depthwise -> pointwise -> BN -> SiLU, BN folded into the pointwise GEMM"""
+        wdw = self.sd[p + ".dw.weight"].float()
+        k = wdw.shape[-1]
+        t = self._alloc(x.h // s, x.w // s, x.c)
+        self._dw(x, wdw, None, t, k, s, 1, L.ACT_NONE, p + ".dw")
+        w, b = _fold(self.sd[p + ".pw.weight"], self.sd, p + ".bn")
+        self._conv(t, w, b, y, 1, 1, L.ACT_SILU, epi, r, what=p + ".pw")
+
+    # ------------------------------------------------------------------------------------------------ blocks
+    def _lower_bottleneck(self, x: Act, p: str, y: Act, shortcut: bool):
+        """Bottleneck.forward (block.py:344-357)"""
+        c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
+        t = self._alloc(x.h, x.w, c_)
+        self._conv_bn(x, p + ".cv1", t)
+        add = shortcut and x.c == y.c
+        self._conv_bn(t, p + ".cv2", y, epi=L.EPI_ADD if add else L.EPI_NONE, r=x if add else None)
+
+    def _lower_dsbottleneck_inplace(self, x: Act, p: str):
+        """DSBottleneck.forward (block.py:1408-1444), residual variant, result written over x"""
+        t = self._alloc(x.h, x.w, self.sd[p + ".cv1.pw.weight"].shape[0])
+        self._dsconv(x, p + ".cv1", t)
+        self._dsconv(t, p + ".cv2", x, epi=L.EPI_ADD, r=x)
+
+    def _lower_dsc3k(self, x: Act, p: str, y: Act, n: int = 2):
+        """DSC3k (block.py:1447-1503) over C3.forward (block.py:271-273)"""
+        c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
+        t = self._alloc(x.h, x.w, 2 * c_)
+        self._conv_bn_pair(x, p + ".cv1", p + ".cv2", t)
+        for j in range(n):
+            self._lower_dsbottleneck_inplace(t.slice(0, c_), f"{p}.m.{j}")
+        self._conv_bn(t, p + ".cv3", y)
+
+    def _lower_dsc3k2(self, x: Act, L_: LayerSpec, p: str, y: Act):
+        """DSC3k2(dsc3k=True) (block.py:1505-1580) over C2f.forward (block.py:245-249)"""
+        c = self.sd[p + ".cv1.conv.weight"].shape[0] // 2
+        z = self._alloc(x.h, x.w, (2 + L_.n) * c)
+        self._conv_bn(x, p + ".cv1", z.slice(0, 2 * c))
+        for j in range(L_.n):
+            self._lower_dsc3k(z.slice((1 + j) * c, c), f"{p}.m.{j}", z.slice((2 + j) * c, c))
+        self._conv_bn(z, p + ".cv2", y)
+
+    def _lower_lsk(self, x: Act, p: str, y: Act):
+        """LSKblock.forward (nn/modules_attention/LSKA.py:28-52)"""
+        d, sd = x.c, self.sd
+        a1, a2 = self._alloc(x.h, x.w, d), self._alloc(x.h, x.w, d)
+        self._dw(x, sd[p + ".conv0.weight"].float(), sd[p + ".conv0.bias"].float(), a1, 5, 1, 1, L.ACT_NONE, p + ".conv0")
+        self._dw(a1, sd[p + ".conv_spatial.weight"].float(), sd[p + ".conv_spatial.bias"].float(), a2, 7, 1, 3, L.ACT_NONE,
+                 p + ".conv_spatial")
+        t = self._alloc(x.h, x.w, d)
+        self._conv_bias(a1, p + ".conv1", t.slice(0, d // 2))
+        self._conv_bias(a2, p + ".conv2", t.slice(d // 2, d // 2))
+        agg = self._alloc(x.h, x.w, 2, torch.float32)
+        self._emit(self.lib.dbl_lsk_squeeze, (C.byref(t.desc), C.byref(agg.desc)), p + ".squeeze")
+        g = self._alloc(x.h, x.w, d // 2)
+        wsq = self._dev(sd[p + ".conv_squeeze.weight"].reshape(-1), torch.float32)
+        bsq = self._dev(sd[p + ".conv_squeeze.bias"], torch.float32)
+        self._emit(self.lib.dbl_lsk_gate, (C.byref(t.desc), C.byref(agg.desc), L.ptr(wsq), L.ptr(bsq), C.byref(g.desc)), p + ".gate")
+        self._conv_bias(g, p + ".conv", y, epi=L.EPI_MUL, r=x)
+
+    def _lower_c3ah(self, x: Act, p: str, y: Act, he: int):
+        """C3AH.forward (block.py:1754-1795) with AdaHGComputation (block.py:1710-1752)"""
+        c, sd = x.c, self.sd
+        t = self._alloc(x.h, x.w, 2 * c)
+        self._conv_bn_pair(x, p + ".cv1", p + ".cv2", t)
+        g = p + ".m.hgnn"
+        f32 = torch.float32
+        wt = L.HypergraphWeights(
+            L.ptr(self._dev(sd[g + ".edge_generator.prototype_base"], f32)),
+            L.ptr(self._dev(sd[g + ".edge_generator.context_net.weight"], f32)),
+            L.ptr(self._dev(sd[g + ".edge_generator.context_net.bias"], f32)),
+            L.ptr(self._dev(sd[g + ".edge_generator.pre_head_proj.weight"], f32)),
+            L.ptr(self._dev(sd[g + ".edge_generator.pre_head_proj.bias"], f32)),
+            L.ptr(self._dev(sd[g + ".edge_proj.0.weight"], f32)), L.ptr(self._dev(sd[g + ".edge_proj.0.bias"], f32)),
+            L.ptr(self._dev(sd[g + ".node_proj.0.weight"], f32)), L.ptr(self._dev(sd[g + ".node_proj.0.bias"], f32)),
+            he, c // 16)
+        nbytes = self.lib.dbl_hypergraph_workspace_bytes(self.B, x.h * x.w, c, he)
+        ws = torch.zeros(nbytes // 4 + 4, dtype=f32, device=self.dev)
+        self._keep += [wt, ws]
+        tok = t.slice(0, c)
+        self._emit(self.lib.dbl_hypergraph, (C.byref(tok.desc), C.byref(wt), C.byref(tok.desc), ws.data_ptr(), C.c_size_t(nbytes)),
+                   p + ".hypergraph")
+        self._conv_bn(t, p + ".cv3", y)
+
+    def _lower_hyperace(self, xs: Sequence[Act], L_: LayerSpec, p: str, y: Act):
+        """HyperACE.forward (block.py:1884-1895) incl. FuseModule.forward (block.py:1833-1840)"""
+        x0, x1, x2 = xs
+        f = self._alloc(x1.h, x1.w, x0.c + x1.c + x2.c)
+        self._emit(self.lib.dbl_avgpool2, (C.byref(x0.desc), C.byref(f.slice(0, x0.c).desc)), p + ".fuse.down")
+        self._emit(self.lib.dbl_copy, (C.byref(x1.desc), C.byref(f.slice(x0.c, x1.c).desc)), p + ".fuse.copy")
+        self._emit(self.lib.dbl_upsample2_nearest, (C.byref(x2.desc), C.byref(f.slice(x0.c + x1.c, x2.c).desc)), p + ".fuse.up")
+        x = self._alloc(x1.h, x1.w, x1.c)
+        self._conv_bn(f, p + ".fuse.conv_out", x)
+        c = self.sd[p + ".cv1.conv.weight"].shape[0] // 3
+        n = L_.n
+        z = self._alloc(x.h, x.w, (4 + n) * c)  # [y0 | out1 | y2 | m_0..m_{n-1} | out2]
+        self._conv_bn(x, p + ".cv1", z.slice(0, 3 * c))
+        self._lower_c3ah(z.slice(c, c), p + ".branch2", z.slice((3 + n) * c, c), L_.he)  # reads y1 before branch1 overwrites it
+        for j in range(n):
+            self._lower_dsc3k(z.slice((2 + j) * c, c), f"{p}.m.{j}", z.slice((3 + j) * c, c))
+        self._lower_c3ah(z.slice(c, c), p + ".branch1", z.slice(c, c), L_.he)
+        self._conv_bn(z, p + ".cv2", y)
+
+    def _lower_dysample(self, x: Act, p: str, y: Act):
+        """DySample.forward_lp + sample (nn/modules_upsample/DySample.py:49-68)"""
+        off = self._alloc(x.h, x.w, 32, torch.float32)
+        self._conv_bias(x, p + ".offset", off)
+        self._emit(self.lib.dbl_dysample, (C.byref(x.desc), C.byref(off.desc), C.byref(y.desc), 4), p + ".sample")
+
+    def _lower_detect(self, xs: Sequence[Act], p: str):
+        """Detect.forward (nn/modules/head.py:108-118), legacy=False class branch (head.py:93-100)"""
+        sd, nc = self.sd, self.spec.nc
+        pitch = (64 + nc + 3) // 4 * 4
+        self.head_pitch = pitch
+        self.head: List[Act] = []
+        for i, x in enumerate(xs):
+            hd = self._alloc(x.h, x.w, pitch, torch.float32)
+            self.head.append(hd)
+            c2b = sd[f"{p}.cv2.{i}.0.conv.weight"].shape[0]
+            b1, b2 = self._alloc(x.h, x.w, c2b), self._alloc(x.h, x.w, c2b)
+            self._conv_bn(x, f"{p}.cv2.{i}.0", b1)
+            self._conv_bn(b1, f"{p}.cv2.{i}.1", b2)
+            self._conv_bias(b2, f"{p}.cv2.{i}.2", hd.slice(0, 64))
+            c3 = sd[f"{p}.cv3.{i}.0.1.conv.weight"].shape[0]
+            cur = x
+            for j, cj in ((0, x.c), (1, c3)):
+                q = f"{p}.cv3.{i}.{j}"
+                wdw, bdw = _fold(sd[q + ".0.conv.weight"], sd, q + ".0.bn")  # DWConv = Conv(g=c) + BN + SiLU
+                d = self._alloc(x.h, x.w, cj)
+                self._dw(cur, wdw, bdw, d, 3, 1, 1, L.ACT_SILU, q + ".0")
+                cur = self._alloc(x.h, x.w, c3)
+                self._conv_bn(d, q + ".1", cur)
+            self._conv_bias(cur, f"{p}.cv3.{i}.2", hd.slice(64, nc))
+
+    # ------------------------------------------------------------------------------------------------ graph
+    def _build(self):
+        spec, sd = self.spec, self.sd
+        # concat buffers are allocated first; producers that feed a Concat write straight into their slice
+        alias: Dict[int, Tuple[int, int]] = {}
+        for Lc in spec.layers:
+            if Lc.kind == "Concat":
+                off = 0
+                for j, cj in zip(Lc.src, Lc.c1):
+                    if j >= 0 and j not in alias and spec.layers[j].kind != "Concat":
+                        alias[j] = (Lc.i, off)
+                    off += cj
+        cat_buf: Dict[int, Act] = {}
+
+        def out_act(Lx: LayerSpec) -> Act:
+            h, w = self.H // Lx.extra["out_stride"], self.W // Lx.extra["out_stride"]
+            if Lx.i in alias:
+                ci, off = alias[Lx.i]
+                if ci not in cat_buf:
+                    cat_buf[ci] = self._alloc(h, w, spec.layers[ci].c2)
+                return cat_buf[ci].slice(off, Lx.c2)
+            if Lx.kind == "Concat":
+                if Lx.i not in cat_buf:
+                    cat_buf[Lx.i] = self._alloc(h, w, Lx.c2)
+                return cat_buf[Lx.i]
+            return self._alloc(h, w, Lx.c2)
+
+        outs: List[Optional[Act]] = []
+        for Lx in spec.layers:
+            p = f"model.{Lx.i}"
+            ins = [outs[j] if j >= 0 else None for j in Lx.src]
+            if Lx.kind == "Detect":
+                self._lower_detect(ins, p)
+                outs.append(None)
+                continue
+            y = out_act(Lx)
+            if Lx.i == 0:
+                if not (Lx.kind == "Conv" and Lx.k == 3):
+                    raise NotImplementedError("layer 0 must be a 3x3 Conv")
+                w, b = _fold(sd[p + ".conv.weight"], sd, p + ".bn")
+                wd, bd = self._dev(w, torch.float32), self._dev(b, torch.float32)
+                self._emit(self.lib.dbl_stem_conv, (self.x_in.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s),
+                           p + ".stem")
+            elif Lx.kind == "Conv":
+                self._conv_bn(ins[0], p, y, s=Lx.s)
+            elif Lx.kind == "DSConv":
+                self._dsconv(ins[0], p, y, s=Lx.s)
+            elif Lx.kind == "Bottleneck":
+                cur = ins[0]
+                for r in range(Lx.n):
+                    dst = y if r == Lx.n - 1 else self._alloc(y.h, y.w, Lx.c2)
+                    self._lower_bottleneck(cur, f"{p}.{r}" if Lx.n > 1 else p, dst, Lx.shortcut)
+                    cur = dst
+            elif Lx.kind == "DSC3k2":
+                self._lower_dsc3k2(ins[0], Lx, p, y)
+            elif Lx.kind == "LSKblock":
+                cur = ins[0]
+                for r in range(Lx.n):
+                    dst = y if r == Lx.n - 1 else self._alloc(y.h, y.w, Lx.c2)
+                    self._lower_lsk(cur, f"{p}.{r}" if Lx.n > 1 else p, dst)
+                    cur = dst
+            elif Lx.kind == "HyperACE":
+                self._lower_hyperace(ins, Lx, p, y)
+            elif Lx.kind == "DySample":
+                self._lower_dysample(ins[0], p, y)
+            elif Lx.kind == "DownsampleConv":
+                t = self._alloc(y.h, y.w, ins[0].c)
+                self._emit(self.lib.dbl_avgpool2, (C.byref(ins[0].desc), C.byref(t.desc)), p + ".down")
+                self._conv_bn(t, p + ".channel_adjust", y)
+            elif Lx.kind == "FullPAD_Tunnel":
+                gate = float(sd[p + ".gate"])
+                self._emit(self.lib.dbl_gated_add, (C.byref(ins[0].desc), C.byref(ins[1].desc), C.c_float(gate), C.byref(y.desc), None),
+                           p + ".gate")
+            elif Lx.kind == "Concat":
+                off = 0
+                for j, a in zip(Lx.src, ins):
+                    if alias.get(j, (None,))[0] != Lx.i:
+                        self._emit(self.lib.dbl_copy, (C.byref(a.desc), C.byref(y.slice(off, a.c).desc)), f"{p}.copy{j}")
+                    off += a.c
+            else:
+                raise NotImplementedError(Lx.kind)
+            outs.append(y)
+        self.layer_out = outs
+        det = spec.detect
+        self.level_hw = [(a.h, a.w) for a in self.head]
+        self.A = sum(h * w for h, w in self.level_hw)
+        lv = L.HeadLevels()
+        for i, a in enumerate(self.head):
+            lv.data[i], lv.h[i], lv.w[i], lv.stride[i] = a.buf.data_ptr(), a.h, a.w, float(det.extra["strides"][i])
+        lv.num_levels, lv.batch, lv.nc, lv.pitch = len(self.head), self.B, spec.nc, self.head_pitch
+        self.levels = lv
+        self.y = torch.zeros(self.B, 4 + spec.nc, self.A, dtype=torch.float32, device=self.dev)
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def _launch_forward(self, stream: int):
+        for fn, args, what in self.ops:
+            rc = fn(*args, stream)
+            if rc:
+                raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
+
+    def _launch_decode(self, stream: int):
+        L.check(self.lib.dbl_detect_decode(C.byref(self.levels), self.y.data_ptr(), stream), "dbl_detect_decode")
+
+    def _post(self, key: tuple) -> dict:
+        if key not in self._post_bufs:
+            conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = key
+            ml = bool(multi_label) and self.spec.nc > 1
+            cap = self.A * (self.spec.nc if ml else 1)
+            dev, B = self.dev, self.B
+            d = dict(
+                box=torch.zeros(B, cap, 4, device=dev), score=torch.zeros(B, cap, device=dev),
+                cls=torch.zeros(B, cap, dtype=torch.int32, device=dev), pos=torch.zeros(B, cap, dtype=torch.int32, device=dev),
+                count=torch.zeros(B, dtype=torch.int32, device=dev),
+                keys=torch.zeros(B * self.lib.dbl_nms_sort_capacity(cap), dtype=torch.int64, device=dev),
+                rows=torch.zeros(B, max_det, 6, device=dev), out_pos=torch.zeros(B, max_det, dtype=torch.int32, device=dev),
+                out_count=torch.zeros(B, dtype=torch.int32, device=dev),
+                classes=torch.tensor(list(classes), dtype=torch.int32, device=dev) if classes else None,
+            )
+            d["cand"] = L.Candidates(d["box"].data_ptr(), d["score"].data_ptr(), d["cls"].data_ptr(), d["pos"].data_ptr(),
+                                     d["count"].data_ptr(), cap, B)
+            self._post_bufs[key] = d
+        return self._post_bufs[key]
+
+    def _launch_post(self, key: tuple, stream: int):
+        conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = key
+        d = self._post(key)
+        ncls = len(classes) if classes else 0
+        L.check(self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]), ncls,
+                                           C.byref(d["cand"]), stream), "dbl_decode_filter")
+        L.check(self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
+                                 d["keys"].data_ptr(), d["rows"].data_ptr(), d["out_pos"].data_ptr(), d["out_count"].data_ptr(), stream),
+                "dbl_nms")
+
+    def _run(self, key: Optional[tuple], want_y: bool):
+        """Launch forward (+decode) (+post-process) on the current stream, through a cached CUDA graph when enabled."""
+        gkey = (key, want_y)
+        if not self.use_graph:
+            s = L.current_stream()
+            self._launch_forward(s)
+            if want_y:
+                self._launch_decode(s)
+            if key is not None:
+                self._launch_post(key, s)
+            return
+        g = self._graphs.get(gkey)
+        if g is None:
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):  # warm-up outside capture: one-time attribute / descriptor setup happens here
+                self._launch_forward(s.cuda_stream)
+                if want_y:
+                    self._launch_decode(s.cuda_stream)
+                if key is not None:
+                    self._launch_post(key, s.cuda_stream)
+            s.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                cs = L.current_stream()
+                self._launch_forward(cs)
+                if want_y:
+                    self._launch_decode(cs)
+                if key is not None:
+                    self._launch_post(key, cs)
+            self._graphs[gkey] = g
+        g.replay()
+
+    @staticmethod
+    def post_key(conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None, max_nms=30000, max_wh=7680):
+        return (float(conf), float(iou), bool(agnostic), bool(multi_label), int(max_det), tuple(classes) if classes else (),
+                int(max_nms), float(max_wh))
+
+    def set_input(self, im: torch.Tensor):
+        if tuple(im.shape) != tuple(self.x_in.shape):
+            raise ValueError(f"engine was built for input {tuple(self.x_in.shape)}, got {tuple(im.shape)}")
+        self.x_in.copy_(im, non_blocking=True)
+
+    def forward(self, im: torch.Tensor):
+        """(y [B,4+nc,A] fp32, feats list of [B,64+nc,h,w] fp32 views) like DetectionModel.forward in eval mode."""
+        with torch.cuda.device(self.dev):
+            self.set_input(im)
+            self._run(None, True)
+        feats = [a.buf[..., : 64 + self.spec.nc].permute(0, 3, 1, 2) for a in self.head]
+        return self.y, feats
+
+    def detect(self, im: Optional[torch.Tensor], **nms_kw):
+        """Fused path: image batch -> (rows [B,max_det,6], counts [B], kept anchor positions [B,max_det]); no host sync."""
+        key = self.post_key(**nms_kw)
+        with torch.cuda.device(self.dev):
+            if im is not None:
+                self.set_input(im)
+            self._run(key, False)
+        d = self._post(key)
+        return d["rows"], d["out_count"], d["out_pos"]
+
+    def debug_layers(self, im: torch.Tensor) -> List[Optional[torch.Tensor]]:
+        """fp32 NCHW copy of every top-level layer output (parity tests)."""
+        with torch.cuda.device(self.dev):
+            self.set_input(im)
+            self._launch_forward(L.current_stream())
+            torch.cuda.synchronize(self.dev)
+            return [a.nchw() if a is not None else None for a in self.layer_out]
