@@ -1,8 +1,13 @@
 """Whole-graph parity (-m gpu): the B200 path vs the CPU oracle on identical weights and inputs.
 
 Stated tolerance for the bf16 backbone (north star: "bf16 backbone within a stated tolerance"):
-  * every top-level layer output: relative L2 error <= 5e-2 and never NaN/Inf;
-  * decoded boxes: median |d| <= 1 px, p99 <= 4 px on 640-px images; scores: max |d| <= 5e-2, p99 <= 1e-2.
+  * teacher-forced, every top-level layer (inputs = the oracle's outputs rounded to bf16): relative L2 error of the
+    layer's output <= 3e-2 (bf16 rounding of every intermediate inside the block, fp32 accumulation); head logits <= 3e-2;
+  * free-running at 640x640 (n scale): every layer <= 5e-2 relative L2; decoded boxes median |d| <= 0.25 px,
+    p99 <= 1.5 px, max <= 6 px; scores p99 <= 1e-2, max <= 5e-2 -- the same size as the drift of the reference run
+    with its activations rounded to bf16 (measured with the oracle: p99 0.2 px / 2e-3);
+  * wider scales (s, l) are held to the teacher-forced bound; their free-running drift is only required to stay
+    finite and <= 0.25 relative L2 because the synthetic s/l weights amplify rounding noise.
 The fp32 post-process on identical inputs is held to 1e-3 / bit-exactness in test_gpu_nms.py.
 """
 import json
@@ -26,23 +31,29 @@ def _rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3):
+def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, free_tol=5e-2, forced_tol=3e-2):
     spec = resolve(None, scale, nc)
     sd = synth_state_dict(param_shapes(spec), seed)
     x = synth_images(b, h, w, xseed)
     eng = DBLEngine(spec, sd, b, h, w, device="cuda:0", conv_impl=conv_impl, use_graph=False, keep_layers=True)
-    outs = eng.debug_layers(x.cuda())
     y_ref, feats_ref, outs_ref = O.forward(sd, x, scale, collect=True)
-    worst = []
-    for i, (o, r) in enumerate(zip(outs, outs_ref)):
-        if o is None:
-            continue
+    head_ref = torch.cat([f.reshape(b, f.shape[1], -1) for f in feats_ref], 2)
+    # --- teacher-forced: each layer on the oracle's inputs
+    forced = eng.debug_layers_forced(x.cuda(), outs_ref)
+    errs = []
+    for i, (o, r) in enumerate(zip(forced, outs_ref + [head_ref])):
         assert o.shape == r.shape, f"layer {i}: shape {tuple(o.shape)} vs {tuple(r.shape)}"
         assert bool(torch.isfinite(o).all()), f"layer {i} produced non-finite values"
-        worst.append((_rel_l2(o, r), i, spec.layers[i].kind))
-    print("per-layer rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in worst))
-    for e, i, kind in worst:
-        assert e <= 5e-2, f"layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
+        errs.append((_rel_l2(o, r), i, spec.layers[i].kind))
+    print(f"[{scale} {h}x{w} impl={conv_impl}] teacher-forced rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in errs))
+    for e, i, kind in errs:
+        assert e <= forced_tol, f"teacher-forced layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
+    # --- free-running
+    outs = eng.debug_layers(x.cuda())
+    free = [(_rel_l2(o, r), i, spec.layers[i].kind) for i, (o, r) in enumerate(zip(outs, outs_ref)) if o is not None]
+    print(f"[{scale} {h}x{w} impl={conv_impl}] free-running  rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in free))
+    for e, i, kind in free:
+        assert e <= free_tol, f"free-running layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
     y, feats = eng.forward(x.cuda())
     torch.cuda.synchronize()
     return eng, sd, x, y.cpu(), y_ref
@@ -53,8 +64,16 @@ def test_layers_n_scale_small(conv_impl):
     _check_layers("n", 3, 0, 2, 128, 160, conv_impl)
 
 
-def test_layers_s_scale_nc80():
-    _check_layers("s", 3, 5, 1, 96, 96, L.IMPL_AUTO)
+def test_layers_n_scale_nc80():
+    _check_layers("n", 80, 3, 1, 96, 64, L.IMPL_AUTO)
+
+
+def test_layers_s_scale():
+    _check_layers("s", 3, 5, 1, 96, 96, L.IMPL_AUTO, free_tol=0.25)
+
+
+def test_layers_l_scale():
+    _check_layers("l", 3, 7, 1, 64, 64, L.IMPL_AUTO, free_tol=0.25)
 
 
 def test_full_640_vs_oracle_and_reference_golden():
@@ -66,13 +85,19 @@ def test_full_640_vs_oracle_and_reference_golden():
         dsc = (y[:, 4:] - ref[:, 4:]).abs().flatten()
         print(f"vs {name}: box median {dbox.median():.3f} p99 {dbox.quantile(0.99):.3f} max {dbox.max():.3f} px | "
               f"score p99 {dsc.quantile(0.99):.4f} max {dsc.max():.4f}")
-        assert float(dbox.median()) <= 1.0 and float(dbox.quantile(0.99)) <= 4.0
+        assert float(dbox.median()) <= 0.25 and float(dbox.quantile(0.99)) <= 1.5 and float(dbox.max()) <= 6.0
         assert float(dsc.quantile(0.99)) <= 1e-2 and float(dsc.max()) <= 5e-2
-    # detections: same count ballpark and high overlap with the reference's own NMS output
+    # detections vs the reference's own NMS output: nearly every reference box has a twin (IoU > 0.9, same class)
     rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
-    ref_rows = np.load(os.path.join(GOLDEN, "nms_model640_conf0.25.npz"))["rows"]
-    n = int(counts[0])
-    assert abs(n - len(ref_rows)) <= max(5, len(ref_rows) // 10)
+    ref_rows = torch.from_numpy(np.load(os.path.join(GOLDEN, "nms_model640_conf0.25.npz"))["rows"])
+    got = rows[0, : int(counts[0])].cpu()
+    import torchvision
+
+    iou = torchvision.ops.box_iou(ref_rows[:, :4], got[:, :4])
+    same = ref_rows[:, 5:6] == got[:, 5].unsqueeze(0)
+    matched = ((iou > 0.9) & same).any(1).float().mean()
+    print(f"detections: reference {len(ref_rows)}, ours {len(got)}, matched {float(matched) * 100:.1f}%")
+    assert abs(len(got) - len(ref_rows)) <= max(3, len(ref_rows) // 10) and float(matched) >= 0.9
 
 
 def test_cuda_graph_replay_equals_eager():

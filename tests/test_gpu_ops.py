@@ -101,8 +101,8 @@ def test_stem_conv():
         wt = torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5
         b = torch.randn(cout, generator=g) * 0.3
         ybuf, yv = empty_nhwc(2, 40, 56, cout)
-        rc = L.require_device().dbl_stem_conv(x.to(dev()).data_ptr(), 2, 40, 56, wt.to(dev()).data_ptr(), b.to(dev()).data_ptr(),
-                                              C.byref(yv), 1, stream())
+        xd, wd, bd = x.to(dev()), wt.to(dev()), b.to(dev())  # keep the device copies alive across the launch
+        rc = L.require_device().dbl_stem_conv(xd.data_ptr(), 2, 40, 56, wd.data_ptr(), bd.data_ptr(), C.byref(yv), 1, stream())
         torch.cuda.synchronize()
         assert rc == 0
         assert_close_bf16(from_nhwc(ybuf, 0, cout), F.silu(F.conv2d(x, wt, b, 1, 1)), f"stem cout={cout}")
@@ -121,7 +121,8 @@ def test_dwconv(k, s, d, act, bias):
     xbuf, xv = to_nhwc(x, pad_c=8)
     ybuf, yv = empty_nhwc(n, ref.shape[2], ref.shape[3], c)
     wd = wt.reshape(c, k * k).t().contiguous().to(dev())
-    rc = L.require_device().dbl_dwconv2d(C.byref(xv), wd.data_ptr(), None if b is None else b.to(dev()).data_ptr(), C.byref(yv), k, s, d,
+    bd = None if b is None else b.to(dev())
+    rc = L.require_device().dbl_dwconv2d(C.byref(xv), wd.data_ptr(), None if bd is None else bd.data_ptr(), C.byref(yv), k, s, d,
                                          act, stream())
     torch.cuda.synchronize()
     assert rc == 0, L.load().dbl_last_error().decode()
@@ -195,8 +196,8 @@ def test_lsk_squeeze_gate_vs_torch():
     gbuf, gv = empty_nhwc(n, h, w, 2, torch.float32)
     ybuf, yv = empty_nhwc(n, h, w, half)
     assert lib.dbl_lsk_squeeze(C.byref(av), C.byref(gv), stream()) == 0
-    assert lib.dbl_lsk_gate(C.byref(av), C.byref(gv), wsq.reshape(-1).to(dev()).data_ptr(), bsq.to(dev()).data_ptr(), C.byref(yv),
-                            stream()) == 0
+    wsd, bsd = wsq.reshape(-1).to(dev()), bsq.to(dev())
+    assert lib.dbl_lsk_gate(C.byref(av), C.byref(gv), wsd.data_ptr(), bsd.data_ptr(), C.byref(yv), stream()) == 0
     torch.cuda.synchronize()
     torch.testing.assert_close(from_nhwc(gbuf, 0, 2), agg, rtol=1e-4, atol=1e-4)
     assert_close_bf16(from_nhwc(ybuf, 0, half), ref, "lsk gate")
@@ -250,4 +251,4 @@ def test_argument_errors_are_reported_not_thrown():
     bad.h = 9
     w = torch.zeros(16 * 9 * 16, dtype=torch.bfloat16, device=dev())
     assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(bad), 3, 1, 1, 1, 0, 0, 0, stream()) == 1
-    assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(yv), 3, 1, 1, 2, 0, 0, L.IMPL_TCGEN05, stream()) == 2  # unsupported
+    assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(yv), 3, 1, 2, 2, 0, 0, L.IMPL_TCGEN05, stream()) == 2  # unsupported

@@ -51,7 +51,7 @@ class Act:
 
     def nchw(self) -> torch.Tensor:
         """fp32 NCHW copy (tests / API compatibility)."""
-        return self.buf[..., self.off:self.off + self.c].permute(0, 3, 1, 2).float().contiguous()
+        return self.buf[..., self.off:self.off + self.c].permute(0, 3, 1, 2).float().contiguous().cpu()
 
 
 def _fold(w: torch.Tensor, sd, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -74,6 +74,8 @@ class DBLEngine:
         self.sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[object] = []        # weights, ctypes structs, scratch: everything launches point at
         self.ops: List[Tuple[Callable, tuple, str]] = []
+        self.op_meta: List[dict] = []
+        self.kernels_per_step: Dict[tuple, int] = {}
         self.layer_out: List[Optional[Act]] = []
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._post_bufs: Dict[tuple, dict] = {}
@@ -94,9 +96,19 @@ class DBLEngine:
         self._keep.append(t)
         return t
 
-    def _emit(self, fn, args: tuple, what: str):
+    def _emit(self, fn, args: tuple, what: str, kern: str = "", flops: float = 0.0, nbytes: float = 0.0):
+        """Record one launch.  kern / flops / nbytes = kernel family and ALGORITHMIC work: every
+        declared input and output tensor counted once, weights once; halo re-reads and scratch are not counted."""
         self._keep.append(args)
         self.ops.append((fn, args, what))
+        if not nbytes:  # bandwidth-bound glue: every tensor view in the argument list, once
+            for a in args:
+                t = getattr(a, "_obj", None)
+                if isinstance(t, L.Tensor):
+                    nbytes += t.n * t.h * t.w * t.c * (2 if t.dtype == L.DBL_BF16 else 4)
+            if fn is self.lib.dbl_stem_conv:
+                nbytes += self.x_in.numel() * 4
+        self.op_meta.append(dict(what=what, kern=kern or fn.__name__, flops=float(flops), bytes=float(nbytes)))
 
     def _pack_w(self, w: torch.Tensor) -> torch.Tensor:
         """[Cout,Cin,kh,kw] f32 -> device bf16 [Cout][kh][kw][Cin]"""
@@ -108,7 +120,11 @@ class DBLEngine:
         bd = self._dev(b, torch.float32) if b is not None else None
         args = (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(r.desc) if r is not None else None, C.byref(y.desc), k, s,
                 k // 2, 1, act, epi, self.conv_impl)
-        self._emit(self.lib.dbl_conv2d, args, what)
+        npix = self.B * y.h * y.w
+        ysz = 2 if y.buf.dtype == torch.bfloat16 else 4
+        nbytes = 2 * self.B * x.h * x.w * x.c + ysz * npix * y.c + 2 * w.numel() + 4 * y.c + (2 * npix * y.c if r is not None else 0)
+        tc = self.conv_impl != L.IMPL_DIRECT and x.c % 16 == 0 and k in (1, 3)
+        self._emit(self.lib.dbl_conv2d, args, what, "conv_tc" if tc else "conv_direct", 2.0 * npix * y.c * x.c * k * k, nbytes)
 
     def _conv_bn(self, x: Act, p: str, y: Act, s: int = 1, act: int = L.ACT_SILU, epi=L.EPI_NONE, r=None):
         """Conv module: conv(bias=False)+BN+SiLU (nn/modules/conv.py:39-63)"""
@@ -128,7 +144,9 @@ class DBLEngine:
     def _dw(self, x: Act, w: torch.Tensor, b: Optional[torch.Tensor], y: Act, k: int, s: int, d: int, act: int, what: str):
         wd = self._dev(w.reshape(w.shape[0], k * k).t(), torch.float32)  # [C,1,k,k] -> [k*k][C]
         bd = self._dev(b, torch.float32) if b is not None else None
-        self._emit(self.lib.dbl_dwconv2d, (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(y.desc), k, s, d, act), what)
+        npix = self.B * y.h * y.w
+        self._emit(self.lib.dbl_dwconv2d, (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(y.desc), k, s, d, act), what, "dwconv",
+                   2.0 * npix * y.c * k * k, 2 * self.B * x.h * x.w * x.c + 2 * npix * y.c + 4 * k * k * y.c)
 
     def _dsconv(self, x: Act, p: str, y: Act, s: int = 1, epi=L.EPI_NONE, r=None):
         """DSConv (conv.py:91-108): depthwise -> pointwise -> BN -> SiLU, BN folded into the pointwise GEMM"""
@@ -292,12 +310,15 @@ class DBLEngine:
             return self._alloc(h, w, Lx.c2)
 
         outs: List[Optional[Act]] = []
+        self.layer_ops: List[Tuple[int, int]] = []  # [first, last) launch index of every top-level layer
         for Lx in spec.layers:
             p = f"model.{Lx.i}"
             ins = [outs[j] if j >= 0 else None for j in Lx.src]
+            self.layer_ops.append((len(self.ops), len(self.ops)))
             if Lx.kind == "Detect":
                 self._lower_detect(ins, p)
                 outs.append(None)
+                self.layer_ops[-1] = (self.layer_ops[-1][0], len(self.ops))
                 continue
             y = out_act(Lx)
             if Lx.i == 0:
@@ -306,7 +327,7 @@ class DBLEngine:
                 w, b = _fold(sd[p + ".conv.weight"], sd, p + ".bn")
                 wd, bd = self._dev(w, torch.float32), self._dev(b, torch.float32)
                 self._emit(self.lib.dbl_stem_conv, (self.x_in.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s),
-                           p + ".stem")
+                           p + ".stem", "stem_conv", 2.0 * 27 * y.c * self.B * y.h * y.w)
             elif Lx.kind == "Conv":
                 self._conv_bn(ins[0], p, y, s=Lx.s)
             elif Lx.kind == "DSConv":
@@ -346,6 +367,7 @@ class DBLEngine:
             else:
                 raise NotImplementedError(Lx.kind)
             outs.append(y)
+            self.layer_ops[-1] = (self.layer_ops[-1][0], len(self.ops))
         self.layer_out = outs
         det = spec.detect
         self.level_hw = [(a.h, a.w) for a in self.head]
@@ -412,6 +434,7 @@ class DBLEngine:
         if g is None:
             s = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream(self.dev))
+            n0 = self.lib.dbl_launch_count()
             with torch.cuda.stream(s):  # warm-up outside capture: one-time attribute / descriptor setup happens here
                 self._launch_forward(s.cuda_stream)
                 if want_y:
@@ -419,6 +442,7 @@ class DBLEngine:
                 if key is not None:
                     self._launch_post(key, s.cuda_stream)
             s.synchronize()
+            self.kernels_per_step[gkey] = int(self.lib.dbl_launch_count() - n0)  # kernels one replay of this graph runs
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 cs = L.current_stream()
@@ -457,6 +481,75 @@ class DBLEngine:
             self._run(key, False)
         d = self._post(key)
         return d["rows"], d["out_count"], d["out_pos"]
+
+    def profile_ops(self, reps: int = 5, post_key: Optional[tuple] = None) -> List[dict]:
+        """Time every launch of one step on its own (CUDA events on the launching stream, eager, after one warm-up pass).
+
+        Returns op_meta rows extended with ``ms`` (mean over reps).  Used by bench.py for the per-kernel roofline table;
+        the whole-step number always comes from graph replays, never from this."""
+        rows = []
+        with torch.cuda.device(self.dev):
+            st = L.current_stream()
+            self._launch_forward(st)
+            if post_key is not None:
+                self._launch_post(post_key, st)
+            torch.cuda.synchronize(self.dev)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(len(self.ops) + 2)]
+            acc = [0.0] * (len(self.ops) + 2)
+            for _ in range(reps):
+                for i, (fn, args, what) in enumerate(self.ops):
+                    ev[i][0].record()
+                    fn(*args, st)
+                    ev[i][1].record()
+                if post_key is not None:
+                    conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = post_key
+                    d = self._post(post_key)
+                    n = len(self.ops)
+                    ev[n][0].record()
+                    self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
+                                               len(classes), C.byref(d["cand"]), st)
+                    ev[n][1].record()
+                    ev[n + 1][0].record()
+                    self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(agnostic), C.c_float(max_wh), int(max_nms), int(max_det),
+                                     d["keys"].data_ptr(), d["rows"].data_ptr(), d["out_pos"].data_ptr(), d["out_count"].data_ptr(), st)
+                    ev[n + 1][1].record()
+                torch.cuda.synchronize(self.dev)
+                for i in range(len(acc)):
+                    if i < len(self.ops) or post_key is not None:
+                        acc[i] += ev[i][0].elapsed_time(ev[i][1])
+            for i, m in enumerate(self.op_meta):
+                rows.append(dict(m, ms=acc[i] / reps))
+            if post_key is not None:
+                no = 64 + self.spec.nc
+                rows.append(dict(what="decode_filter", kern="decode_filter", flops=0.0, bytes=float(self.B * self.A * no * 4),
+                                 ms=acc[len(self.ops)] / reps))
+                rows.append(dict(what="sort_nms", kern="sort_nms", flops=0.0, bytes=0.0, ms=acc[len(self.ops) + 1] / reps))
+        return rows
+
+    def debug_layers_forced(self, im: torch.Tensor, ref_outs: Sequence[torch.Tensor]) -> List[Optional[torch.Tensor]]:
+        """Teacher-forced run (parity tests): before each top-level layer executes, its inputs are overwritten with the
+        given reference outputs (fp32 NCHW, rounded to bf16 here), so errors cannot accumulate from layer to layer.
+        Returns every layer's own output; the last entry is the stacked raw head logits (B, 64+nc, A)."""
+        res: List[Optional[torch.Tensor]] = []
+        with torch.cuda.device(self.dev):
+            self.set_input(im)
+            st = L.current_stream()
+            for Lx, (a, b) in zip(self.spec.layers, self.layer_ops):
+                for j in Lx.src:
+                    if j >= 0:
+                        act = self.layer_out[j]
+                        act.buf[..., act.off:act.off + act.c] = ref_outs[j].to(self.dev).permute(0, 2, 3, 1).to(act.buf.dtype)
+                for fn, args, what in self.ops[a:b]:
+                    rc = fn(*args, st)
+                    if rc:
+                        raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
+                torch.cuda.synchronize(self.dev)
+                if Lx.kind == "Detect":
+                    no = 64 + self.spec.nc
+                    res.append(torch.cat([h.buf[..., :no].permute(0, 3, 1, 2).reshape(self.B, no, -1) for h in self.head], 2).cpu())
+                else:
+                    res.append(self.layer_out[Lx.i].nchw())
+        return res
 
     def debug_layers(self, im: torch.Tensor) -> List[Optional[torch.Tensor]]:
         """fp32 NCHW copy of every top-level layer output (parity tests)."""

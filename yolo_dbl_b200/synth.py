@@ -65,7 +65,9 @@ def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=()) -> 
     if parent.endswith(".dfl.conv"):
         return torch.arange(shape[1], dtype=torch.float32).view(shape)
     if parent.endswith(".bn"):
-        return uniform(0.5, 1.5) if leaf == "weight" else normal(0.1)
+        # small gammas keep SiLU near its linear range: a random deep stack with gamma ~ 1 is chaotic (it amplifies
+        # bf16 rounding noise ~1.1x per layer, 50x end to end), which no trained detector is.
+        return uniform(0.2, 0.5) if leaf == "weight" else normal(0.1)
     is_cls_out = ".cv3." in key and parent.endswith(".2")  # Detect.cv3[i][-1]
     is_box_out = ".cv2." in key and parent.endswith(".2") and len(parent.split(".")) == 5  # Detect.cv2[i][-1]
     is_lsk_out = parent.endswith(".conv") and f"{parent.rsplit('.', 1)[0]}.conv_squeeze.weight" in siblings
@@ -85,8 +87,8 @@ def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=()) -> 
             fan_in *= d
         if len(shape) == 2:  # nn.Linear
             return normal(1.0 / math.sqrt(fan_in))
-        if is_cls_out:
-            return normal(1.0 / math.sqrt(fan_in))
+        if is_cls_out or is_box_out:  # wide head logits: varied scores / peaky DFL distributions
+            return normal((2.5 if is_cls_out else 1.0) / math.sqrt(fan_in))
         if is_lsk_out:
             return normal(0.06 / math.sqrt(fan_in))
         return normal(1.0 / math.sqrt(fan_in))
