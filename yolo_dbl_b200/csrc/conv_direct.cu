@@ -127,14 +127,26 @@ __global__ void __launch_bounds__(DC_THREADS) conv_direct_kernel(
     if (!live) return;
     const size_t opix = ((size_t)b * ho + oy) * wo + ox;
 #pragma unroll
-    for (int i = 0; i < DC_CO; ++i) {
-        if (co0 + i >= cout) break;
-        float v = apply_act(acc[i], act);
-        if (epi != DBL_EPI_NONE) {
-            const float rv = __bfloat162float(r[opix * rpitch + co0 + i]);
-            v = (epi == DBL_EPI_ADD) ? v + rv : v * rv;
+    for (int i = 0; i < DC_CO; ++i) acc[i] = apply_act(acc[i], act);
+    const bool full = co0 + DC_CO <= cout;
+    if (epi != DBL_EPI_NONE) {
+        const __nv_bfloat16* rp = r + opix * rpitch + co0;
+        float rr[DC_CO];
+        if (full && (rpitch % 8 == 0) && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+            unpack8(ld8(rp), rr);
+        } else {
+#pragma unroll
+            for (int i = 0; i < DC_CO; ++i) rr[i] = (co0 + i < cout) ? __bfloat162float(rp[i]) : 0.f;
         }
-        st_elem(y, ydtype, opix * ypitch + co0 + i, v);
+#pragma unroll
+        for (int i = 0; i < DC_CO; ++i) acc[i] = (epi == DBL_EPI_ADD) ? acc[i] + rr[i] : acc[i] * rr[i];
+    }
+    if (ydtype == DBL_BF16 && full && (ypitch % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0)) {
+        stg8(reinterpret_cast<__nv_bfloat16*>(y) + opix * ypitch + co0, pack8(acc));
+    } else {
+#pragma unroll
+        for (int i = 0; i < DC_CO; ++i)
+            if (co0 + i < cout) st_elem(y, ydtype, opix * ypitch + co0 + i, acc[i]);
     }
 }
 

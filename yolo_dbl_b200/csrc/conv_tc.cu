@@ -20,7 +20,8 @@
 
 namespace dbl {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                      // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TILE_M = 128;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
@@ -136,6 +137,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
     return d;
 }
 
+// SiLU through one MUFU: x*sigmoid(x) = 0.5x(1 + tanh(0.5x)); tanh.approx is ~2^-11 accurate, far below bf16 rounding
+__device__ __forceinline__ float silu_fast(float v) {
+    float t;
+    const float h = 0.5f * v;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+    if (ACT == DBL_ACT_SILU) return silu_fast(v);
+    if (ACT == DBL_ACT_GELU) return gelu_f(v);
+    return v;
+}
+
+template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A][stages x B][bias f32 cout_pad][barriers][tmem ptr]
@@ -167,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);
+            mbar_init(&tempty[a], TC_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -253,7 +269,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int lg = warp & 3;  // TMEM lane group this warp may access
+        const int lg = warp & 3;          // TMEM lane group this warp may access
+        const int chalf = (warp - 2) >> 2;  // which interleaved share of the column chunks this warp converts
         const int row = lg * 32 + lane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -275,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_fence_after();
             const int n0 = nt * p.npad;
             const int ncols = min(p.npad, ((p.cout - n0) + 15) & ~15);
-            for (int c0 = 0; c0 < ncols; c0 += 16) {
+            for (int c0 = chalf * 16; c0 < ncols; c0 += 16 * (TC_EPI_WARPS / 4)) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.npad + c0, v);
                 tmem_ld_wait();
@@ -283,25 +300,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int cg = n0 + c0;  // first global output channel of this chunk
                 float f[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = apply_act(__uint_as_float(v[i]) + sBias[cg + i], p.act);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 bq = *reinterpret_cast<const float4*>(sBias + cg + 4 * q);
+                    f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
+                    f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
+                    f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);
+                    f[4 * q + 3] = act_t<ACT>(__uint_as_float(v[4 * q + 3]) + bq.w);
+                }
                 const bool full16 = cg + 16 <= p.cout;
                 if (p.epi != DBL_EPI_NONE) {
                     const __nv_bfloat16* rp = p.r + (size_t)opix * p.rpitch + cg;
-                    if (full16 && p.r_vec) {
-                        float r0[8], r1[8];
-                        unpack8(ldg8(rp), r0);
-                        unpack8(ldg8(rp + 8), r1);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            f[i] = p.epi == DBL_EPI_ADD ? f[i] + r0[i] : f[i] * r0[i];
-                            f[8 + i] = p.epi == DBL_EPI_ADD ? f[8 + i] + r1[i] : f[8 + i] * r1[i];
-                        }
+                    float rr[16];
+                    if (full16 && p.r_vec) {  // coherent loads: r may be the very tensor this kernel overwrites (in-place residual)
+                        unpack8(ld8(rp), rr);
+                        unpack8(ld8(rp + 8), rr + 8);
                     } else {
-                        for (int i = 0; i < 16 && cg + i < p.cout; ++i) {
-                            const float rv = __bfloat162float(rp[i]);
-                            f[i] = p.epi == DBL_EPI_ADD ? f[i] + rv : f[i] * rv;
-                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) rr[i] = (cg + i < p.cout) ? __bfloat162float(rp[i]) : 0.f;
                     }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = p.epi == DBL_EPI_ADD ? f[i] + rr[i] : f[i] * rr[i];
                 }
                 if (p.ydtype == DBL_BF16) {
                     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)opix * p.ypitch + cg;
@@ -309,7 +327,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         stg8(yp, pack8(f));
                         stg8(yp + 8, pack8(f + 8));
                     } else {
-                        for (int i = 0; i < 16 && cg + i < p.cout; ++i) yp[i] = __float2bfloat16_rn(f[i]);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (cg + i < p.cout) yp[i] = __float2bfloat16_rn(f[i]);
                     }
                 } else {
                     float* yp = reinterpret_cast<float*>(p.y) + (size_t)opix * p.ypitch + cg;
@@ -318,7 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         for (int q = 0; q < 4; ++q)
                             reinterpret_cast<float4*>(yp)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
                     } else {
-                        for (int i = 0; i < 16 && cg + i < p.cout; ++i) yp[i] = f[i];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (cg + i < p.cout) yp[i] = f[i];
                     }
                 }
             }
@@ -415,7 +437,9 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) {
             set_error("conv_tc: cannot opt in to %d bytes of shared memory: %s", max_smem, cudaGetErrorString(e));
             num_sms = 0;
@@ -494,7 +518,12 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     const size_t smem = fixed + (size_t)stages * (p.a_bytes + p.b_bytes);
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps, p);
+    if (act == DBL_ACT_SILU)
+        conv_tc_kernel<DBL_ACT_SILU><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    else if (act == DBL_ACT_GELU)
+        conv_tc_kernel<DBL_ACT_GELU><<<grid, TC_THREADS, smem, st>>>(maps, p);
+    else
+        conv_tc_kernel<DBL_ACT_NONE><<<grid, TC_THREADS, smem, st>>>(maps, p);
     count_launch();
     return check_launch("dbl_conv2d(tcgen05)");
 }

@@ -33,35 +33,50 @@ static inline bool same_shape(const dbl_tensor* a, const dbl_tensor* b) {
 }
 
 // ---- device math ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
     return act == DBL_ACT_SILU ? silu_f(v) : (act == DBL_ACT_GELU ? gelu_f(v) : v);
 }
 
-// 8 bf16 <-> 8 floats through one 16-byte access
-struct alignas(16) bf16x8 {
-    __nv_bfloat162 v[4];
+// 8 bf16 <-> 8 floats through ONE 16-byte access.  The transport type is a plain uint4: a struct of __nv_bfloat162
+// members is copied member-wise by nvcc (four 32-bit LDG/STG), which quarters the achieved bandwidth.
+struct bf16x8 {
+    uint4 u;
 };
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi) {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+}
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 t = __bfloat1622float2(p.v[i]);
-        f[2 * i] = t.x;
-        f[2 * i + 1] = t.y;
-    }
+    unpack2(p.u.x, f[0], f[1]);
+    unpack2(p.u.y, f[2], f[3]);
+    unpack2(p.u.z, f[4], f[5]);
+    unpack2(p.u.w, f[6], f[7]);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
     bf16x8 p;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    p.u = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     return p;
 }
+// read-only path (ld.global.nc): only for tensors no thread of the running kernel writes
 __device__ __forceinline__ bf16x8 ldg8(const __nv_bfloat16* p) {
-    return *reinterpret_cast<const bf16x8*>(p);
+    bf16x8 v;
+    v.u = __ldg(reinterpret_cast<const uint4*>(p));
+    return v;
 }
-__device__ __forceinline__ void stg8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+// coherent load: for tensors that may alias the kernel's output (in-place residuals)
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
+    bf16x8 v;
+    v.u = *reinterpret_cast<const uint4*>(p);
+    return v;
+}
+__device__ __forceinline__ void stg8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = v.u; }
 
 // generic element access for views whose channel count / pitch / base is not 16-byte friendly
 __device__ __forceinline__ float ld_elem(const void* base, int dtype, size_t idx) {

@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(256) hg_edges_kernel(const __nv_bfloat16* __re
 }
 
 // K5: y[n] = GELU(sum_e A[n,e] Q[e] + bn) + X[n].  grid (nblk, B), block HG_TOK_BLOCK, thread per token.
-__global__ void __launch_bounds__(HG_TOK_BLOCK) hg_nodes_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ A,
+__global__ void __launch_bounds__(HG_TOK_BLOCK) hg_nodes_kernel(const __nv_bfloat16* x, const float* __restrict__ A,
                                                                 const float* __restrict__ Q, const float* __restrict__ node_b,
-                                                                __nv_bfloat16* __restrict__ y, int N, int D, int E, int xpitch,
+                                                                __nv_bfloat16* y, int N, int D, int E, int xpitch,
                                                                 int ypitch) {
     extern __shared__ float sm[];  // Q[E*D] | bn[D]
     float* sQ = sm;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_nodes_kernel(const __nv_bfloa
     __nv_bfloat16* yr = y + ((size_t)b * N + n) * ypitch;
     for (int d0 = 0; d0 < D; d0 += 8) {
         float xv[8], o[8];
-        unpack8(ldg8(xr + d0), xv);
+        unpack8(ld8(xr + d0), xv);  // x may alias y (in-place use inside C3AH): coherent load
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = sb[d0 + j];
 #pragma unroll
