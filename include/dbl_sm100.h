@@ -31,7 +31,12 @@ enum { DBL_OK = 0, DBL_E_ARG = 1, DBL_E_UNSUPPORTED = 2, DBL_E_CUDA = 3, DBL_E_W
 enum { DBL_BF16 = 0, DBL_F32 = 1 };
 enum { DBL_ACT_NONE = 0, DBL_ACT_SILU = 1, DBL_ACT_GELU = 2 };
 enum { DBL_EPI_NONE = 0, DBL_EPI_ADD = 1 /* y = act(conv)+r */, DBL_EPI_MUL = 2 /* y = act(conv)*r */ };
-enum { DBL_IMPL_AUTO = 0, DBL_IMPL_DIRECT = 1 /* CUDA-core */, DBL_IMPL_TCGEN05 = 2 /* tensor cores + TMA */ };
+enum {
+    DBL_IMPL_AUTO = 0,
+    DBL_IMPL_DIRECT = 1,      /* CUDA-core direct convolution */
+    DBL_IMPL_TCGEN05 = 2,     /* tensor cores: halo-reuse kernel for 3x3, TMA kernel for 1x1 */
+    DBL_IMPL_TCGEN05_TMA = 3  /* tensor cores, first-generation kernel (one TMA box per filter tap) */
+};
 
 typedef struct dbl_tensor {
     void* data;    /* device pointer to element (n=0,h=0,w=0,c=0) of this view */
@@ -53,7 +58,8 @@ int64_t dbl_launch_count(void);
  * (nn/modules/block.py:344-357) and LSKblock's final x*attn (nn/modules_attention/LSKA.py:52).
  *   x: bf16 NHWC (n,h,w,cin)      w: bf16 [cout][k][k][cin] (BatchNorm already folded)      bias: f32 [cout] or NULL
  *   r: bf16 NHWC like y, or NULL  y: bf16 or f32 NHWC (n,ho,wo,cout), ho = (h+2*pad-dil*(k-1)-1)/stride+1
- * impl = DBL_IMPL_TCGEN05 requires cin % 16 == 0, dil == 1, k in {1,3}, stride in {1,2} (k==1: stride 1). */
+ * impl = DBL_IMPL_TCGEN05 requires dil == 1, k in {1,3}, stride in {1,2} (k==1: stride 1), cin % 16 == 0 (k==3 also
+ * accepts cin == 8). */
 int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
                int k, int stride, int pad, int dil, int act, int epi, int impl, dbl_stream_t stream);
 

@@ -87,6 +87,29 @@ def test_conv2d_tcgen05(case):
     _run_conv_case(case, L.IMPL_TCGEN05)
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] == 3])
+def test_conv2d_tcgen05_tma_generation(case):
+    _run_conv_case(case, L.IMPL_TCGEN05_TMA)
+
+
+THIN_CASES = [  # the 8-channel path (two filter taps per K=16 step) and awkward tile geometries of the halo-reuse kernel
+    (2, 64, 96, 8, 16, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 48, 80, 8, 16, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (1, 320, 320, 16, 8, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 20, 20, 256, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 128, 0),
+    (1, 40, 40, 192, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 20, 20, 128, 320, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 18, 130, 32, 32, 3, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 0),
+    (3, 34, 38, 48, 24, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES)
+def test_conv3x3_halo_reuse_kernel(case):
+    _run_conv_case(case, L.IMPL_TCGEN05, seed=7)
+    _run_conv_case(case, L.IMPL_DIRECT, seed=7)
+
+
 def test_conv2d_tcgen05_many_tiles_persistent():
     # more tiles than SMs so every CTA loops (pipeline phases, TMEM double buffering)
     _run_conv_case((8, 80, 80, 64, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=3)

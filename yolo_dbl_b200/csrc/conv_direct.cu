@@ -7,6 +7,10 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
                    int stride, int pad, int act, int epi, cudaStream_t st);
 bool conv2d_tcgen05_eligible(const dbl_tensor* x, const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int pad,
                              int dil);
+int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int stride, int act,
+                int epi, cudaStream_t st);
+bool conv3x3_tc3_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil);
+bool conv3x3_tc3_preferred(const dbl_tensor* x, const dbl_tensor* y, int stride);
 
 // ------------------------------------------------------------------------------------------------------------------
 // stem: x f32 NCHW (n,3,h,w) -> y bf16 NHWC (n,ho,wo,COUT), 3x3, pad 1, SiLU
@@ -242,8 +246,12 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
     }
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = conv2d_tcgen05_eligible(x, r, y, k, stride, pad, dil);
-    if (impl == DBL_IMPL_TCGEN05) DBL_REQUIRE(tc_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the tcgen05 path");
-    if (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && tc_ok))
+    const bool tc3_ok = conv3x3_tc3_eligible(x, y, k, stride, pad, dil);
+    if (impl == DBL_IMPL_TCGEN05) DBL_REQUIRE(tc_ok || tc3_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for a tcgen05 path");
+    if (impl == DBL_IMPL_TCGEN05_TMA) DBL_REQUIRE(tc_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the TMA tcgen05 path");
+    if (tc3_ok && (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && (!tc_ok || conv3x3_tc3_preferred(x, y, stride)))))
+        return conv3x3_tc3(x, w, bias, epi ? r : nullptr, y, stride, act, epi, st);
+    if (impl == DBL_IMPL_TCGEN05 || impl == DBL_IMPL_TCGEN05_TMA || (impl == DBL_IMPL_AUTO && tc_ok))
         return conv2d_tcgen05(x, w, bias, epi ? r : nullptr, y, k, stride, pad, act, epi, st);
 
     DBL_REQUIRE(vec8_ok(x), DBL_E_UNSUPPORTED, "dbl_conv2d(direct): cin/pitch must be multiples of 8 and 16-byte aligned");
