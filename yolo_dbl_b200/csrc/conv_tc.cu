@@ -23,6 +23,7 @@ namespace dbl {
 constexpr int TC_EPI_WARPS = 8;                      // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int TC_MAX_STAGES = 8;
+constexpr int MAX_ACC = 8;
 constexpr int TILE_M = 128;
 
 struct TcParams {
@@ -40,7 +41,7 @@ struct TcParams {
     int m_tiles, n_tiles;      // totals
     int npad;                  // N of the MMA (multiple of 16, <= 256)
     int tmem_cols;             // power of two >= 2*npad, >= 32
-    int stages;
+    int stages, nacc;
     uint32_t a_bytes, b_bytes; // per stage (a_bytes: 128 rows reserved)
     uint32_t a_tx, b_tx;       // bytes one A / B box actually delivers
     // epilogue
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t* full = bars;
     uint64_t* empty = bars + TC_MAX_STAGES;
     uint64_t* tfull = bars + 2 * TC_MAX_STAGES;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + MAX_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < bias_n; i += TC_THREADS) sBias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < p.nacc; ++a) {
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], TC_EPI_WARPS);
         }
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
             if (lane == 0) mbar_wait(&tempty[acc], aphase ^ 1);
             __syncwarp();
             tc_fence_after();
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int row = lg * 32 + lane;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             // which output pixel does this thread own?
             long long opix = -1;
@@ -376,8 +377,12 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     p.n_tiles = cdiv(y->c, 256);
     p.npad = ((cdiv(y->c, p.n_tiles) + 15) / 16) * 16;
     p.n_tiles = cdiv(y->c, p.npad);
+    // accumulator ring in TMEM: as many buffers as fit (<= MAX_ACC); two are not enough to hide the MMA -> epilogue ->
+    // MMA latency chain when tiles are small
+    p.nacc = 512 / p.npad;
+    if (p.nacc > MAX_ACC) p.nacc = MAX_ACC;
     int cols = 32;
-    while (cols < 2 * p.npad) cols <<= 1;
+    while (cols < p.nacc * p.npad) cols <<= 1;
     p.tmem_cols = cols;
     if (p.flat) {
         p.tw = TILE_M, p.th = 1, p.tiles_x = p.tiles_y = 0;
@@ -393,7 +398,7 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     p.b_bytes = (p.b_bytes + 1023u) & ~1023u;  // keep every stage buffer 1024-byte aligned
     p.a_tx = (uint32_t)(p.flat ? TILE_M : p.tw * p.th) * row_bytes;
     p.b_tx = (uint32_t)p.npad * row_bytes;
-    const size_t fixed = 1024 /*align slack*/ + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * TC_MAX_STAGES + 4) * 8 + 16;
+    const size_t fixed = 1024 /*align slack*/ + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * TC_MAX_STAGES + 2 * MAX_ACC) * 8 + 16;
     int stages = (int)(((size_t)max_smem - fixed) / (p.a_bytes + p.b_bytes));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     DBL_REQUIRE(stages >= 2, DBL_E_UNSUPPORTED, "conv_tc: tile does not fit shared memory");

@@ -25,6 +25,10 @@ constexpr int C3_PROD_WARPS = 4;
 constexpr int C3_EPI_WARPS = 8;
 constexpr int C3_THREADS = 32 * (1 + C3_PROD_WARPS + C3_EPI_WARPS);  // warp 0 MMA, 1..4 producers, 5..12 epilogue
 constexpr int C3_MAX_STAGES = 8;
+constexpr int MAX_ACC = 8;
+#ifndef DBL_C3_NO_FENCE
+#define DBL_C3_NO_FENCE 0
+#endif
 
 struct C3Params {
     const __nv_bfloat16* x;
@@ -35,9 +39,10 @@ struct C3Params {
     int tw, th, wl;           // output tile and local row length (tw + 2, or tw + 1 for stride 2)
     int tiles_x, tiles_y, m_tiles, n_tiles, npad, tmem_cols;
     int npar, hq, halo_px;    // parity planes (1 or 4), pixels per parity array, pixels filled per plane
+    int rows_h, tail_px, gc_log2;  // halo rows per parity array, overrun pixels after them, log2(Gc)
     int ps, psb;              // plane strides in bytes: activations / weights
     int a_bytes, b_bytes;     // per stage
-    int stages, b_resident;
+    int stages, b_resident, nacc;
     int off[9];               // pixel offset of each tap inside a plane (sorted ascending)
     int tap[9];               // which filter tap (ky*3+kx) sits at sorted position j
     // epilogue
@@ -69,8 +74,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
     uint64_t* full = bars;
     uint64_t* empty = bars + C3_MAX_STAGES;
     uint64_t* tfull = bars + 2 * C3_MAX_STAGES;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* tempty = tfull + MAX_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_ACC);
+    uint64_t* sDesc = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [<=36][2] descriptor templates (A, B) of one unit
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < bias_n; i += C3_THREADS) sBias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
             mbar_init(&full[s], 32 * C3_PROD_WARPS);
             mbar_init(&empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < p.nacc; ++a) {
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], C3_EPI_WARPS);
         }
@@ -99,10 +105,27 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
 
     if (warp == 0) {
         // ===================== MMA issuer =====================
+        // One thread issues every MMA, so its instruction count per MMA is the kernel's pace for thin layers.  The
+        // descriptors of a pipeline unit differ from stage to stage only in their start address: build the sequence once
+        // (all 32 lanes, into shared memory) and add the stage base at issue time.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const int nmma = (p.G == 1) ? 5 : 9 * (p.Gc >> 1);
+        for (int k = lane; k < nmma; k += 32) {
+            uint32_t a_rel, a_lbo, b_rel;
+            if (p.G == 1) {
+                const int o0 = p.off[2 * k], o1 = (2 * k + 1 < 9) ? p.off[2 * k + 1] : o0 + 1;
+                a_rel = o0 * 16, a_lbo = (uint32_t)(o1 - o0) * 16, b_rel = (2 * k) * p.psb;
+            } else {
+                const int pairs = p.Gc >> 1, j = k / pairs, pp = k - j * pairs;
+                a_rel = (2 * pp) * p.ps + p.off[j] * 16, a_lbo = (uint32_t)p.ps, b_rel = (j * p.Gc + 2 * pp) * p.psb;
+            }
+            sDesc[2 * k] = make_noswz_desc(a_rel, a_lbo);
+            sDesc[2 * k + 1] = make_noswz_desc(b_rel, (uint32_t)p.psb);
+        }
+        __syncwarp();
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
             if (lane == 0) mbar_wait(&tempty[acc], aphase ^ 1);
             __syncwarp();
             tc_fence_after();
@@ -110,27 +133,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
             for (int cc = 0; cc < p.ncc; ++cc) {
                 if (lane == 0) {
                     mbar_wait(&full[stage], phase);
-                    fence_proxy_async();  // cp.async wrote through the generic proxy; the tensor core reads through the async proxy
+                    if (!DBL_C3_NO_FENCE) fence_proxy_async();  // cp.async wrote through the generic proxy; tcgen05 reads through the async proxy
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(sRing + (size_t)stage * stage_bytes);
                     const uint32_t b_base = p.b_resident ? smem_u32(sBres) : a_base + p.a_bytes;
-                    if (p.G == 1) {
-                        for (int s = 0; s < 5; ++s) {  // two taps per K=16 step; the 10th "tap" has zero weights
-                            const int o0 = p.off[2 * s], o1 = (2 * s + 1 < 9) ? p.off[2 * s + 1] : o0 + 1;
-                            const uint64_t ad = make_noswz_desc(a_base + o0 * 16, (uint32_t)(o1 - o0) * 16);
-                            const uint64_t bd = make_noswz_desc(b_base + (2 * s) * p.psb, (uint32_t)p.psb);
-                            umma_bf16(d_tmem, ad, bd, idesc, (cc | s) ? 1u : 0u);
-                        }
-                    } else {
-                        const int pairs = p.Gc >> 1;
-                        for (int j = 0; j < 9; ++j) {
-                            for (int pp = 0; pp < pairs; ++pp) {
-                                const uint64_t ad = make_noswz_desc(a_base + (2 * pp) * p.ps + p.off[j] * 16, (uint32_t)p.ps);
-                                const uint64_t bd = make_noswz_desc(b_base + (j * p.Gc + 2 * pp) * p.psb, (uint32_t)p.psb);
-                                umma_bf16(d_tmem, ad, bd, idesc, (cc | j | pp) ? 1u : 0u);
-                            }
-                        }
-                    }
+                    const uint64_t a_add = (uint64_t)(a_base >> 4), b_add = (uint64_t)(b_base >> 4);
+                    umma_bf16(d_tmem, sDesc[0] + a_add, sDesc[1] + b_add, idesc, cc ? 1u : 0u);
+                    for (int k = 1; k < nmma; ++k) umma_bf16(d_tmem, sDesc[2 * k] + a_add, sDesc[2 * k + 1] + b_add, idesc, 1u);
                     umma_commit(&empty[stage]);
                     if (cc == p.ncc - 1) umma_commit(&tfull[acc]);
                 }
@@ -153,25 +162,35 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
                 if (lane == 0) mbar_wait(&empty[stage], phase ^ 1);
                 __syncwarp();
                 const uint32_t a_dst = smem_u32(sRing + (size_t)stage * stage_bytes);
-                // ---- activations
-                const int items = p.halo_px * p.Gc;
-                for (int i = pt; i < items; i += NP) {
-                    const int g = i % p.Gc, qq = i / p.Gc;
-                    int iy, ix;
-                    bool ok;
-                    if (p.npar == 1) {
-                        const int ly = qq / p.wl, lx = qq - ly * p.wl;
-                        iy = oy0 - 1 + ly, ix = ox0 - 1 + lx;
-                        ok = ly < p.th + 2;
-                    } else {
-                        const int par = qq / p.hq, q = qq - par * p.hq;
-                        const int la = q / p.wl, lb = q - la * p.wl;
-                        iy = 2 * (oy0 - 1 + la) + (par >> 1), ix = 2 * (ox0 - 1 + lb) + (par & 1);
-                        ok = la < p.th + 1;
+                // ---- activations: walk the halo row by row; (row, item) advance incrementally, no per-item division
+                {
+                    const int row_items = p.wl << p.gc_log2;          // 16-byte items per halo row
+                    const int rows = p.npar * p.rows_h;               // halo rows over all parity arrays
+                    const int dq = NP / row_items, dr = NP - dq * row_items;
+                    int hr = pt / row_items, t = pt - hr * row_items;  // this thread's first (row, item)
+                    const uint32_t chan0 = (uint32_t)cc << p.gc_log2;
+                    while (hr < rows) {
+                        const int par = (p.npar == 1) ? 0 : hr / p.rows_h;
+                        const int ly = hr - par * p.rows_h;
+                        const int lx = t >> p.gc_log2, g = t & (p.Gc - 1);
+                        int iy, ix;
+                        if (p.npar == 1) {
+                            iy = oy0 - 1 + ly, ix = ox0 - 1 + lx;
+                        } else {
+                            iy = 2 * (oy0 - 1 + ly) + (par >> 1), ix = 2 * (ox0 - 1 + lx) + (par & 1);
+                        }
+                        const bool ok = iy >= 0 && iy < p.h && ix >= 0 && ix < p.wd;
+                        const __nv_bfloat16* src = ok ? ximg + ((size_t)iy * p.wd + ix) * p.xpitch + (chan0 + g) * 8 : p.x;
+                        cp_async16(a_dst + g * p.ps + (par * p.hq + ly * p.wl + lx) * 16, src, ok);
+                        t += dr, hr += dq;
+                        if (t >= row_items) t -= row_items, ++hr;
                     }
-                    ok = ok && iy >= 0 && iy < p.h && ix >= 0 && ix < p.wd;
-                    const __nv_bfloat16* src = ok ? ximg + ((size_t)iy * p.wd + ix) * p.xpitch + (cc * p.Gc + g) * 8 : p.x;
-                    cp_async16(a_dst + g * p.ps + qq * 16, src, ok);
+                    // the few pixels past the last halo row that junk GEMM rows may touch: keep them finite (zero)
+                    for (int i = pt; i < p.npar * p.tail_px * p.Gc; i += NP) {
+                        const int g = i & (p.Gc - 1), q = i >> p.gc_log2;
+                        const int par = q / p.tail_px, e = q - par * p.tail_px;
+                        cp_async16(a_dst + g * p.ps + (par * p.hq + p.rows_h * p.wl + e) * 16, p.x, false);
+                    }
                 }
                 // ---- weights
                 if (!p.b_resident || first) {
@@ -206,7 +225,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
         const int ty = row / p.wl, tx = row - ty * p.wl;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aphase = (it >> 1) & 1;
+            const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int img = mt / per_img, t = mt % per_img;
             const int oy = (t / p.tiles_x) * p.th + ty, ox = (t % p.tiles_x) * p.tw + tx;
@@ -338,8 +357,12 @@ int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl
     p.n_tiles = cdiv(y->c, 256);
     p.npad = ((cdiv(y->c, p.n_tiles) + 15) / 16) * 16;
     p.n_tiles = cdiv(y->c, p.npad);
+    // accumulator ring in TMEM: as many buffers as fit (<= MAX_ACC); two are not enough to hide the MMA -> epilogue ->
+    // MMA latency chain when tiles are small
+    p.nacc = 512 / p.npad;
+    if (p.nacc > MAX_ACC) p.nacc = MAX_ACC;
     int cols = 32;
-    while (cols < 2 * p.npad) cols <<= 1;
+    while (cols < p.nacc * p.npad) cols <<= 1;
     p.tmem_cols = cols;
     p.npar = stride == 1 ? 1 : 4;
     const int extra = stride == 1 ? 2 : 1;  // halo columns / rows beyond the tile
@@ -359,6 +382,7 @@ int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl
     p.m_tiles = p.n * p.tiles_x * p.tiles_y;
     p.hq = (p.th + extra) * p.wl + extra;
     p.halo_px = p.npar * p.hq;
+    p.rows_h = p.th + extra, p.tail_px = extra;
     // ---- tap offsets, sorted ascending (the 8-channel path pairs neighbours in this order)
     int off[9], tap[9];
     for (int t = 0; t < 9; ++t) {
@@ -380,12 +404,13 @@ int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl
     for (int t = 0; t < 9; ++t) p.off[t] = off[t], p.tap[t] = tap[t];
     const int need_px = (p.halo_px > 128 + off[8] + 2) ? p.halo_px : 128 + off[8] + 2;
     // ---- channel chunking and stages
-    const size_t fixed = 256 + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * C3_MAX_STAGES + 4) * 8 + 16;
-    int gc = p.G > 8 ? 8 : p.G;
-    while (p.G % gc) --gc;
+    const size_t fixed = 256 + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * C3_MAX_STAGES + 2 * MAX_ACC) * 8 + 16 + 36 * 2 * 8;
+    int gc = 8;
+    while (p.G % gc) gc >>= 1;  // largest power of two <= 8 dividing the plane count
     for (;; gc >>= 1) {
-        DBL_REQUIRE(gc >= 1 && (gc == 1 || gc % 2 == 0), DBL_E_UNSUPPORTED, "conv3x3_tc3: cannot chunk %d channels", x->c);
+        DBL_REQUIRE(gc >= 1 && (gc >= 2 || p.G == 1), DBL_E_UNSUPPORTED, "conv3x3_tc3: cannot chunk %d channels", x->c);
         p.Gc = gc, p.ncc = p.G / gc;
+        p.gc_log2 = gc == 8 ? 3 : (gc == 4 ? 2 : (gc == 2 ? 1 : 0));
         p.ps = plane_units(need_px, gc) * 16;
         p.psb = plane_units(p.npad, gc) * 16;
         p.a_bytes = (gc * p.ps + 127) & ~127;
