@@ -68,6 +68,10 @@ int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_
  * w f32 [cout][3][3][3], y bf16 NHWC, SiLU applied. */
 int dbl_stem_conv(const float* x_nchw, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
                   int stride, dbl_stream_t stream);
+/* Same for the image sources of the reference: x is uint8 NCHW 0..255 and the `/ 255` of BasePredictor.preprocess
+ * (engine/predictor.py:131-133) happens in the loader of the kernel, so only one byte per sample crosses PCIe. */
+int dbl_stem_conv_u8(const uint8_t* x_nchw, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
+                     int stride, dbl_stream_t stream);
 
 /* ---- depthwise convolution ---------------------------------------------------------------------------------------
  * DSConv.dw (conv.py:96-99), DWConv (conv.py:128-133), LSKblock.conv0 / conv_spatial (LSKA.py:31-32).

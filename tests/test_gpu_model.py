@@ -131,3 +131,24 @@ def test_backend_api_surface_and_facade():
     res = YOLO("yolov13n_DBL.yaml", nc=3).predict(x.cuda(), conf=0.05)
     assert len(res) == 2 and res[0].boxes.data.shape[1] == 6 and res[0].orig_shape == (64, 96)
     assert bool((res[0].boxes.conf[:-1] >= res[0].boxes.conf[1:]).all()) if len(res[0]) > 1 else True
+
+
+def test_uint8_input_and_pipelined_stream_match_float_path():
+    m = DBLBackend.synthetic("n", 3, seed=0, device="cuda:0")
+    xs = [(synth_images(2, 96, 128, 20 + i) * 255).round().to(torch.uint8) for i in range(3)]
+    # uint8 (0..255, scaled inside the stem kernel) == float(x)/255 up to one fp32 rounding of the input
+    y_f, _ = m(xs[0].float() / 255.0)
+    y_u, _ = m(xs[0].pin_memory())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y_u, y_f, rtol=1e-3, atol=2e-2)
+    # one call per batch from pinned host memory ...
+    want = []
+    for x in xs:
+        rows, counts = m.detect(x.pin_memory(), conf=0.1, iou=0.7)
+        want.append((rows.clone(), counts.clone()))
+    # ... equals the pipelined generator (copy of batch i+1 overlaps compute of batch i) bit for bit
+    got = [(r.clone(), c.clone()) for r, c in m.detect_stream([x.pin_memory() for x in xs], conf=0.1, iou=0.7)]
+    assert len(got) == 3
+    for (r, c), (wr, wc) in zip(got, want):
+        assert torch.equal(c, wc) and torch.equal(r, wr)
+    assert int(sum(int(c.sum()) for _, c in got)) > 0

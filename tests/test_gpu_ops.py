@@ -133,9 +133,10 @@ def test_stem_conv():
 
 @pytest.mark.parametrize("k,s,d,act,bias", [(3, 1, 1, L.ACT_NONE, False), (3, 2, 1, L.ACT_NONE, False), (7, 1, 1, L.ACT_NONE, False),
                                             (5, 1, 1, L.ACT_NONE, True), (7, 1, 3, L.ACT_NONE, True), (3, 1, 1, L.ACT_SILU, True)])
-def test_dwconv(k, s, d, act, bias):
+@pytest.mark.parametrize("geom", [(2, 64, 20, 28), (1, 24, 10, 30), (3, 128, 6, 6)])
+def test_dwconv(k, s, d, act, bias, geom):
     g = torch.Generator().manual_seed(2)
-    n, c, h, w = 2, 64, 20, 28
+    n, c, h, w = geom
     x = bf16_round(torch.randn(n, c, h, w, generator=g))
     wt = torch.randn(c, 1, k, k, generator=g) / k
     b = torch.randn(c, generator=g) if bias else None

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "dbl_launch_count": (C.c_int64, []),
     "dbl_conv2d": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_stem_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
+    "dbl_stem_conv_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
     "dbl_dwconv2d": (C.c_int, [_TP, _P, _P, _TP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_avgpool2": (C.c_int, [_TP, _TP, _P]),
     "dbl_upsample2_nearest": (C.c_int, [_TP, _TP, _P]),

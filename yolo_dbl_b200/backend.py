@@ -116,7 +116,9 @@ class DBLBackend(nn.Module):
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected BCHW input with 3 channels, got {tuple(x.shape)}")
         L.require_device()  # no GPU / wrong GPU -> DblError, never a silent fallback
-        return x.to(self._device, torch.float32, non_blocking=True)
+        if x.dtype != torch.uint8 and x.dtype != torch.float32:
+            x = x.float()
+        return x  # host or device: the engine copies it straight into its static input buffer
 
     def forward(self, x, augment=False, visualize=False, embed=None):
         if augment or visualize or embed is not None:
@@ -134,6 +136,48 @@ class DBLBackend(nn.Module):
         rows, counts, _ = self.engine(x.shape[0], x.shape[2], x.shape[3]).detect(
             x, conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms)
         return rows, counts
+
+    def detect_stream(self, batches, **nms):
+        """Generator over an iterable of host (pinned) or device batches: yields (rows, counts) per batch while the
+        host->device copy of the NEXT batch runs on a second stream (the analogue of predict(..., stream=True),
+        reference engine/predictor.py:219-304).  Yielded tensors are engine-owned: consume them before advancing."""
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        nxt = self._prep(nxt)
+        eng = self.engine(nxt.shape[0], nxt.shape[2], nxt.shape[3])
+        with torch.cuda.device(self._device):
+            copy_stream = torch.cuda.Stream(device=self._device)
+            staging = [torch.empty(nxt.shape, dtype=nxt.dtype, device=self._device) for _ in range(2)]
+            ready = [None, None]
+            done = [None, None]
+
+            def stage(x, slot):
+                if staging[slot].dtype != x.dtype:
+                    staging[slot] = torch.empty(x.shape, dtype=x.dtype, device=self._device)
+                with torch.cuda.stream(copy_stream):
+                    if done[slot] is not None:
+                        copy_stream.wait_event(done[slot])  # the compute that read this slot has finished
+                    staging[slot].copy_(x, non_blocking=True)
+                    ready[slot] = torch.cuda.Event()
+                    ready[slot].record(copy_stream)
+
+            stage(nxt, 0)
+            i = 0
+            while nxt is not None:
+                slot = i & 1
+                nxt = next(it, None)
+                if nxt is not None:
+                    nxt = self._prep(nxt)
+                    stage(nxt, slot ^ 1)
+                cur = torch.cuda.current_stream(self._device)
+                cur.wait_event(ready[slot])
+                rows, counts, _ = eng.detect(staging[slot], **{{"agnostic_nms": "agnostic"}.get(k, k): v for k, v in nms.items()})
+                done[slot] = torch.cuda.Event()
+                done[slot].record(cur)
+                yield rows, counts
+                i += 1
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -15,8 +15,11 @@ bool conv3x3_tc3_preferred(const dbl_tensor* x, const dbl_tensor* y, int stride)
 // ------------------------------------------------------------------------------------------------------------------
 // stem: x f32 NCHW (n,3,h,w) -> y bf16 NHWC (n,ho,wo,COUT), 3x3, pad 1, SiLU
 // ------------------------------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__device__ __forceinline__ float stem_load(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float stem_load(const uint8_t* p) { return (float)__ldg(p) * (1.0f / 255.0f); }
+
+template <int COUT, typename TIN>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const TIN* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                         int n, int h, int wd, int ho, int wo, int stride, int ypitch) {
     __shared__ __align__(16) float sw[27 * COUT];  // [ci][ky][kx][co]
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     const int iy0 = oy * stride - 1, ix0 = ox * stride - 1;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
-        const float* xp = x + ((size_t)b * 3 + ci) * h * wd;
+        const TIN* xp = x + ((size_t)b * 3 + ci) * h * wd;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int iy = iy0 + ky;
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
             for (int kx = 0; kx < 3; ++kx) {
                 const int ix = ix0 + kx;
                 if (ix < 0 || ix >= wd) continue;
-                const float v = __ldg(xp + (size_t)iy * wd + ix);
+                const float v = stem_load(xp + (size_t)iy * wd + ix);
                 const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * COUT);
 #pragma unroll
                 for (int c4 = 0; c4 < COUT / 4; ++c4) {
@@ -207,12 +210,94 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __rest
     stg8(y + (((size_t)b * ho + oy) * wo + ox) * ypitch + g * 8, pack8(acc));
 }
 
+// depthwise conv, register-blocked: one thread = R consecutive output pixels of one row x 8 channels.  Each input row
+// contributes (R-1)*S + K 16-byte loads that feed all R outputs (K=7, R=8: 12 loads per output instead of 49), the
+// filter lives in shared memory.  Dilation 1 only.
+template <int K, int S, int R>
+__global__ void __launch_bounds__(128) dwconv_strip_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n,
+                                                           int h, int wd, int c, int xpitch, int ho, int wo, int ypitch, int act) {
+    extern __shared__ __align__(16) float sw[];  // [K*K][c]
+    for (int i = threadIdx.x; i < K * K * c; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int cg = c / 8;
+    const int strips = (wo + R - 1) / R;
+    const long long total = (long long)n * ho * strips * cg;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int g = (int)(idx % cg);
+    long long rest = idx / cg;
+    const int sx = (int)(rest % strips);
+    rest /= strips;
+    const int oy = (int)(rest % ho), b = (int)(rest / ho);
+    const int ox0 = sx * R;
+    constexpr int PAD = (K - 1) / 2;
+    constexpr int WIN = (R - 1) * S + K;
+    float acc[R][8];
+    {
+        float b8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + g * 8 + 4));
+            b8[0] = b0.x, b8[1] = b0.y, b8[2] = b0.z, b8[3] = b0.w, b8[4] = b1.x, b8[5] = b1.y, b8[6] = b1.z, b8[7] = b1.w;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = b8[i];
+    }
+    const int ix0 = ox0 * S - PAD;
+#pragma unroll 1
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - PAD + ky;
+        if (iy < 0 || iy >= h) continue;
+        const __nv_bfloat16* xrow = x + ((size_t)b * h + iy) * wd * xpitch + g * 8;
+        float wk[K][8];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * c + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * c + g * 8 + 4);
+            wk[kx][0] = w0.x, wk[kx][1] = w0.y, wk[kx][2] = w0.z, wk[kx][3] = w0.w;
+            wk[kx][4] = w1.x, wk[kx][5] = w1.y, wk[kx][6] = w1.z, wk[kx][7] = w1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < WIN; ++j) {
+            const int ix = ix0 + j;
+            float xv[8];
+            if (ix >= 0 && ix < wd) {
+                unpack8(ldg8(xrow + (size_t)ix * xpitch), xv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xv[i] = 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int kx = j - r * S;  // compile-time after unrolling
+                if (kx >= 0 && kx < K) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(xv[i], wk[kx][i], acc[r][i]);
+                }
+            }
+        }
+    }
+    __nv_bfloat16* yrow = y + (((size_t)b * ho + oy) * wo) * ypitch + g * 8;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (ox0 + r < wo) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = apply_act(acc[r][i], act);
+            stg8(yrow + (size_t)(ox0 + r) * ypitch, pack8(acc[r]));
+        }
+    }
+}
+
 }  // namespace dbl
 
 using namespace dbl;
 
-extern "C" int dbl_stem_conv(const float* x, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
-                             int stride, dbl_stream_t stream) {
+template <typename TIN>
+static int stem_launch(const TIN* x, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y, int stride,
+                       dbl_stream_t stream) {
     DBL_REQUIRE(x && w && valid_tensor(y), DBL_E_ARG, "dbl_stem_conv: null/invalid argument");
     DBL_REQUIRE(stride == 1 || stride == 2, DBL_E_ARG, "dbl_stem_conv: stride %d", stride);
     const int ho = (h + 2 - 3) / stride + 1, wo = (w_ + 2 - 3) / stride + 1;
@@ -222,13 +307,23 @@ extern "C" int dbl_stem_conv(const float* x, int n, int h, int w_, const float* 
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
     cudaStream_t st = as_stream(stream);
     switch (y->c) {
-        case 8: stem_conv_kernel<8><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
-        case 16: stem_conv_kernel<16><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
-        case 32: stem_conv_kernel<32><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 8: stem_conv_kernel<8, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 16: stem_conv_kernel<16, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 32: stem_conv_kernel<32, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
         default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_stem_conv: cout %d not in {8,16,32}", y->c);
     }
     count_launch();
     return check_launch("dbl_stem_conv");
+}
+
+extern "C" int dbl_stem_conv(const float* x, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
+                             int stride, dbl_stream_t stream) {
+    return stem_launch<float>(x, n, h, w_, w, bias, y, stride, stream);
+}
+
+extern "C" int dbl_stem_conv_u8(const uint8_t* x, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
+                                int stride, dbl_stream_t stream) {
+    return stem_launch<uint8_t>(x, n, h, w_, w, bias, y, stride, stream);
 }
 
 extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
@@ -285,6 +380,25 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
     auto* xp = reinterpret_cast<const __nv_bfloat16*>(x->data);
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
     cudaStream_t st = as_stream(stream);
+    if (dil == 1 && (stride == 1 || stride == 2) && (size_t)k * k * x->c * 4 <= 48 * 1024) {
+        // register-blocked strips along W
+        const int R = 4;
+        const long long tot = (long long)x->n * ho * ((wo + R - 1) / R) * (x->c / 8);
+        const unsigned gs = (unsigned)((tot + 127) / 128);
+        const size_t sm = (size_t)k * k * x->c * 4;
+#define DBL_DWS(K, S) dwconv_strip_kernel<K, S, 4><<<gs, 128, sm, st>>>(xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act)
+        bool done = true;
+        if (k == 3 && stride == 1) DBL_DWS(3, 1);
+        else if (k == 3 && stride == 2) DBL_DWS(3, 2);
+        else if (k == 5 && stride == 1) DBL_DWS(5, 1);
+        else if (k == 7 && stride == 1) DBL_DWS(7, 1);
+        else done = false;
+#undef DBL_DWS
+        if (done) {
+            count_launch();
+            return check_launch("dbl_dwconv2d(strip)");
+        }
+    }
 #define DBL_DW(K) dwconv_kernel<K><<<grid, 256, 0, st>>>(xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, stride, dil, act)
     switch (k) {
         case 3: DBL_DW(3); break;

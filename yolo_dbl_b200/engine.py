@@ -81,6 +81,8 @@ class DBLEngine:
         self._post_bufs: Dict[tuple, dict] = {}
         with torch.cuda.device(self.dev):
             self.x_in = torch.zeros(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.dev)
+            self.x_in_u8 = torch.zeros(self.B, 3, self.H, self.W, dtype=torch.uint8, device=self.dev)  # image sources (0..255)
+            self._u8 = False
             self._build()
         if not keep_layers:
             self.sd = None
@@ -328,6 +330,7 @@ class DBLEngine:
                 wd, bd = self._dev(w, torch.float32), self._dev(b, torch.float32)
                 self._emit(self.lib.dbl_stem_conv, (self.x_in.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s),
                            p + ".stem", "stem_conv", 2.0 * 27 * y.c * self.B * y.h * y.w)
+                self._stem_u8 = (self.x_in_u8.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s)
             elif Lx.kind == "Conv":
                 self._conv_bn(ins[0], p, y, s=Lx.s)
             elif Lx.kind == "DSConv":
@@ -381,7 +384,9 @@ class DBLEngine:
 
     # ------------------------------------------------------------------------------------------------ execution
     def _launch_forward(self, stream: int):
-        for fn, args, what in self.ops:
+        for i, (fn, args, what) in enumerate(self.ops):
+            if i == 0 and self._u8:  # uint8 input: same stem, the /255 happens in its loader
+                fn, args = self.lib.dbl_stem_conv_u8, self._stem_u8
             rc = fn(*args, stream)
             if rc:
                 raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
@@ -421,7 +426,7 @@ class DBLEngine:
 
     def _run(self, key: Optional[tuple], want_y: bool):
         """Launch forward (+decode) (+post-process) on the current stream, through a cached CUDA graph when enabled."""
-        gkey = (key, want_y)
+        gkey = (key, want_y, self._u8)
         if not self.use_graph:
             s = L.current_stream()
             self._launch_forward(s)
@@ -460,9 +465,12 @@ class DBLEngine:
                 int(max_nms), float(max_wh))
 
     def set_input(self, im: torch.Tensor):
+        """Stage one batch: float BCHW in 0..1 (LoadTensor sources) or uint8 BCHW in 0..255 (image sources); `im` may
+        live in (pinned) host memory, in which case this is the step's host->device copy."""
         if tuple(im.shape) != tuple(self.x_in.shape):
             raise ValueError(f"engine was built for input {tuple(self.x_in.shape)}, got {tuple(im.shape)}")
-        self.x_in.copy_(im, non_blocking=True)
+        self._u8 = im.dtype == torch.uint8
+        (self.x_in_u8 if self._u8 else self.x_in).copy_(im, non_blocking=True)
 
     def forward(self, im: torch.Tensor):
         """(y [B,4+nc,A] fp32, feats list of [B,64+nc,h,w] fp32 views) like DetectionModel.forward in eval mode."""
