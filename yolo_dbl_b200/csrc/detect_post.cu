@@ -184,9 +184,24 @@ __global__ void __launch_bounds__(256) filter_kernel(const float* __restrict__ p
     }
 }
 
+// IoU(p, q) > thr, evaluated exactly like torchvision's CPU kernel (strict fp32, no FMA contraction).  Pairs that do
+// not intersect are by far the most common; for them inter == 0, so ovr is 0 (or NaN when both boxes are empty) and the
+// comparison is false for every thr >= 0 -- the IEEE division is skipped without changing any result.
+__device__ __forceinline__ bool iou_exceeds(const float4& pb, float pa, const float4& q, float qa, float thr) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(pb.z, q.z), fmaxf(pb.x, q.x)));
+    if (!(w > 0.f)) return false;
+    const float h = fmaxf(0.f, __fsub_rn(fminf(pb.w, q.w), fmaxf(pb.y, q.y)));
+    if (!(h > 0.f)) return false;
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(pa, qa), inter)) > thr;
+}
+
 // ---- sort + NMS ---------------------------------------------------------------------------------------------------
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_FLAG_CAP = 40960;  // candidates per image the suppression flags can hold (smem bytes)
+constexpr int NMS_SMEM_SORT = 8192;  // slow path: lists up to this many keys (12 bytes each) are sorted in shared memory
+constexpr int NMS_FAST_N = 1024;     // images with at most this many candidates are handled entirely in shared memory
+constexpr int NMS_SMEM = NMS_FAST_N * (8 + 16 + 4 + 32 * 4);  // keys | boxes | slots | suppression bit-matrix (> NMS_FLAG_CAP)
 
 __host__ __device__ inline size_t next_pow2(size_t v) {
     size_t p = 32;
@@ -198,11 +213,104 @@ __host__ __device__ inline size_t next_pow2(size_t v) {
 __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd, float iou_thr, float cls_scale, int max_nms, int max_det,
                                                                uint64_t* __restrict__ scratch, size_t per_image, float* __restrict__ out_rows,
                                                                int32_t* __restrict__ out_pos, int32_t* __restrict__ out_count) {
-    __shared__ unsigned char dead[NMS_FLAG_CAP];
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    unsigned char* dead = nms_smem;  // slow path: one flag per candidate (NMS_FLAG_CAP bytes), overlays the fast-path area
     __shared__ int s_pivot;
     __shared__ int s_keep[1024];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = min(cd.count[b], cd.cap);
+    if (n <= NMS_FAST_N) {
+        // ---------------- fast path (the usual case): everything stays in shared memory --------------------------------
+        // stable sort -> class-offset boxes -> full suppression bit-matrix in parallel -> one warp walks it greedily.
+        uint64_t* fkeys = reinterpret_cast<uint64_t*>(nms_smem);                       // [1024]
+        float4* fbox = reinterpret_cast<float4*>(nms_smem + NMS_FAST_N * 8);           // [1024]
+        uint32_t* fslot = reinterpret_cast<uint32_t*>(nms_smem + NMS_FAST_N * 24);     // [1024]
+        uint32_t* fmask = reinterpret_cast<uint32_t*>(nms_smem + NMS_FAST_N * 28);     // [1024][32]
+        const size_t cb = (size_t)b * cd.cap;
+        int P = 32;
+        while (P < n) P <<= 1;
+        for (int i = tid; i < P; i += NMS_THREADS) {
+            if (i < n) {
+                fkeys[i] = ((uint64_t)(~__float_as_uint(cd.score[cb + i])) << 32) | (uint32_t)cd.pos[cb + i];
+                fslot[i] = (uint32_t)i;
+            } else {
+                fkeys[i] = ~0ull;
+                fslot[i] = 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < P / 2; t += NMS_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const uint64_t ki = fkeys[i], kl = fkeys[l];
+                    if ((ki > kl) == ((i & k) == 0)) {
+                        fkeys[i] = kl, fkeys[l] = ki;
+                        const uint32_t si = fslot[i];
+                        fslot[i] = fslot[l], fslot[l] = si;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int m = min(n, max_nms);
+        for (int i = tid; i < m; i += NMS_THREADS) {
+            const size_t sidx = cb + fslot[i];
+            const float4 bx = reinterpret_cast<const float4*>(cd.box)[sidx];
+            const float off = __fmul_rn((float)cd.cls[sidx], cls_scale);
+            fbox[i] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+        }
+        __syncthreads();
+        const int W = (m + 31) >> 5;
+        for (int item = tid; item < m * W; item += NMS_THREADS) {
+            const int i = item / W, wq = item - i * W;
+            uint32_t word = 0;
+            if (32 * wq + 31 > i) {
+                const float4 pb = fbox[i];
+                const float pa = __fmul_rn(__fsub_rn(pb.z, pb.x), __fsub_rn(pb.w, pb.y));
+                for (int bit = 0; bit < 32; ++bit) {
+                    const int j = 32 * wq + bit;
+                    if (j > i && j < m) {
+                        const float4 q = fbox[j];
+                        const float qa = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+                        if (iou_exceeds(pb, pa, q, qa, iou_thr)) word |= 1u << bit;
+                    }
+                }
+            }
+            fmask[i * 32 + wq] = word;
+        }
+        __syncthreads();
+        int kept = 0;
+        if (tid < 32) {  // lane l owns the "removed" bits of candidates [32l, 32l+32)
+            uint32_t removed = 0;
+            for (int i = 0; i < m && kept < max_det; ++i) {
+                const uint32_t r = __shfl_sync(0xffffffffu, removed, i >> 5);
+                if (!((r >> (i & 31)) & 1u)) {
+                    if (tid == 0) s_keep[kept] = i;
+                    ++kept;
+                    if (tid < W) removed |= fmask[i * 32 + tid];
+                }
+            }
+            if (tid == 0) s_pivot = kept;
+        }
+        __syncthreads();
+        kept = s_pivot;
+        for (int k = tid; k < max_det; k += NMS_THREADS) {
+            float* ro = out_rows + ((size_t)b * max_det + k) * 6;
+            if (k < kept) {
+                const size_t sidx = cb + fslot[s_keep[k]];
+                const float4 bx = reinterpret_cast<const float4*>(cd.box)[sidx];
+                ro[0] = bx.x, ro[1] = bx.y, ro[2] = bx.z, ro[3] = bx.w, ro[4] = cd.score[sidx], ro[5] = (float)cd.cls[sidx];
+                out_pos[(size_t)b * max_det + k] = cd.pos[sidx];
+            } else {
+                ro[0] = ro[1] = ro[2] = ro[3] = ro[4] = ro[5] = 0.f;
+                out_pos[(size_t)b * max_det + k] = -1;
+            }
+        }
+        if (tid == 0) out_count[b] = kept;
+        return;
+    }
     const size_t P = next_pow2((size_t)(n > 0 ? n : 1));
     uint64_t* keys = scratch + (size_t)b * per_image;
     const size_t Pcap = next_pow2((size_t)cd.cap);
@@ -222,21 +330,48 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
         }
     }
     __syncthreads();
-    // 2. bitonic sort (keys are unique, so the result equals a stable sort by score)
-    for (size_t k = 2; k <= P; k <<= 1) {
-        for (size_t j = k >> 1; j > 0; j >>= 1) {
-            for (size_t t = tid; t < P / 2; t += NMS_THREADS) {
-                const size_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const size_t l = i | j;
-                const uint64_t ki = keys[i], kl = keys[l];
-                const bool up = (i & k) == 0;
-                if ((ki > kl) == up) {
-                    keys[i] = kl, keys[l] = ki;
-                    const uint32_t si = slot_of[i];
-                    slot_of[i] = slot_of[l], slot_of[l] = si;
+    // 2. bitonic sort (keys are unique, so the result equals a stable sort by score).  Up to NMS_SMEM_SORT keys are
+    //    sorted in shared memory (the flags that later live there are not needed yet) and written back; larger lists
+    //    sort in place in global memory.
+    if (P <= (size_t)NMS_SMEM_SORT) {
+        uint64_t* skeys = reinterpret_cast<uint64_t*>(nms_smem);
+        uint32_t* sslot = reinterpret_cast<uint32_t*>(nms_smem + NMS_SMEM_SORT * 8);
+        const int Pi = (int)P;
+        for (int i = tid; i < Pi; i += NMS_THREADS) skeys[i] = keys[i], sslot[i] = slot_of[i];
+        __syncthreads();
+        for (int k = 2; k <= Pi; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < Pi / 2; t += NMS_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const uint64_t ki = skeys[i], kl = skeys[l];
+                    if ((ki > kl) == ((i & k) == 0)) {
+                        skeys[i] = kl, skeys[l] = ki;
+                        const uint32_t si = sslot[i];
+                        sslot[i] = sslot[l], sslot[l] = si;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
+        }
+        for (int i = tid; i < Pi; i += NMS_THREADS) slot_of[i] = sslot[i];
+        __syncthreads();
+    } else {
+        for (size_t k = 2; k <= P; k <<= 1) {
+            for (size_t j = k >> 1; j > 0; j >>= 1) {
+                for (size_t t = tid; t < P / 2; t += NMS_THREADS) {
+                    const size_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const size_t l = i | j;
+                    const uint64_t ki = keys[i], kl = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((ki > kl) == up) {
+                        keys[i] = kl, keys[l] = ki;
+                        const uint32_t si = slot_of[i];
+                        slot_of[i] = slot_of[l], slot_of[l] = si;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     // 3. class-offset boxes in sorted order (ops.py:289-295), truncated to max_nms (ops.py:285-286)
@@ -249,50 +384,64 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
         sbox[i] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
         dead[i] = 0;
     }
-    if (tid == 0) s_pivot = 0;
+    __shared__ float4 s_pbox[32];
+    __shared__ unsigned s_kmask;
     __syncthreads();
-    // 4. greedy suppression: at most max_det pivots, each one parallel pass over the tail.  `kept` and `cursor` are
-    //    uniform across the block (every thread follows the same pivots).
+    // 4. greedy suppression, 32 candidates per round: warp 0 resolves the chunk sequentially (exactly the reference's
+    //    order), then the whole block applies the chunk's kept boxes to the tail in one pass.  `kept` / `cursor` are
+    //    block-uniform.
     int cursor = 0, kept = 0;
-    while (kept < max_det) {
-        if (tid < 32) {  // warp 0 finds the next live candidate at or after cursor
-            int c = cursor, found = -1;
-            while (c < m) {
-                const int idx = c + tid;
-                const unsigned live = __ballot_sync(0xffffffffu, idx < m && !dead[idx]);
-                if (live) {
-                    found = c + __ffs(live) - 1;
-                    break;
+    while (kept < max_det && cursor < m) {
+        if (tid < 32) {
+            const int c = cursor + tid;
+            const bool alive = c < m && !dead[c];
+            const float4 bx = c < m ? sbox[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+            unsigned sup = 0;  // later chunk members this lane's box would suppress
+            for (int j = 0; j < 32; ++j) {
+                const float qx = __shfl_sync(0xffffffffu, bx.x, j), qy = __shfl_sync(0xffffffffu, bx.y, j);
+                const float qz = __shfl_sync(0xffffffffu, bx.z, j), qw = __shfl_sync(0xffffffffu, bx.w, j);
+                const float qa = __shfl_sync(0xffffffffu, ar, j);
+                if (j > tid && iou_exceeds(bx, ar, make_float4(qx, qy, qz, qw), qa, iou_thr)) sup |= 1u << j;
+            }
+            unsigned live = __ballot_sync(0xffffffffu, alive), kmask = 0;
+            int k2 = kept;
+            for (int l = 0; l < 32 && k2 < max_det; ++l) {
+                const unsigned sl = __shfl_sync(0xffffffffu, sup, l);
+                if ((live >> l) & 1u) {
+                    kmask |= 1u << l;
+                    live &= ~sl;
+                    if (tid == 0) s_keep[k2] = cursor + l;
+                    ++k2;
                 }
-                c += 32;
             }
-            if (tid == 0) {
-                s_pivot = found;
-                if (found >= 0) s_keep[kept] = found;
-            }
+            s_pbox[tid] = bx;
+            if (tid == 0) s_kmask = kmask;
         }
         __syncthreads();
-        const int pv = s_pivot;
-        if (pv < 0) break;
-        ++kept;
-        if (kept < max_det) {
-            const float4 pb = sbox[pv];
-            const float pa = __fmul_rn(__fsub_rn(pb.z, pb.x), __fsub_rn(pb.w, pb.y));
-            for (int j = pv + 1 + tid; j < m; j += NMS_THREADS) {
+        const unsigned kmask = s_kmask;
+        kept += __popc(kmask);
+        if (kept < max_det && kmask) {
+            for (int j = cursor + 32 + tid; j < m; j += NMS_THREADS) {
                 if (dead[j]) continue;
                 const float4 q = sbox[j];
                 const float qa = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
-                const float w = fmaxf(0.f, __fsub_rn(fminf(pb.z, q.z), fmaxf(pb.x, q.x)));
-                const float h = fmaxf(0.f, __fsub_rn(fminf(pb.w, q.w), fmaxf(pb.y, q.y)));
-                const float inter = __fmul_rn(w, h);
-                const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(pa, qa), inter));
-                if (ovr > iou_thr) dead[j] = 1;
+                unsigned km = kmask;
+                while (km) {
+                    const int l = __ffs(km) - 1;
+                    km &= km - 1;
+                    const float4 pb = s_pbox[l];
+                    const float pa = __fmul_rn(__fsub_rn(pb.z, pb.x), __fsub_rn(pb.w, pb.y));
+                    if (iou_exceeds(pb, pa, q, qa, iou_thr)) {
+                        dead[j] = 1;
+                        break;
+                    }
+                }
             }
         }
-        cursor = pv + 1;
-        __syncthreads();  // also orders this round's s_pivot reads before the next round's write
+        cursor += 32;
+        __syncthreads();
     }
-    __syncthreads();
     // 5. emit rows in keep order: x1,y1,x2,y2 (no class offset), conf, cls
     for (int k = tid; k < max_det; k += NMS_THREADS) {
         float* ro = out_rows + ((size_t)b * max_det + k) * 6;
@@ -372,7 +521,13 @@ extern "C" int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic
     DBL_REQUIRE(std::min(cand->cap, max_nms) <= NMS_FLAG_CAP, DBL_E_UNSUPPORTED,
                 "dbl_nms: min(cap,max_nms)=%d exceeds the %d candidates one image may hold", std::min(cand->cap, max_nms), NMS_FLAG_CAP);
     DBL_REQUIRE((reinterpret_cast<uintptr_t>(sort_keys) & 15) == 0, DBL_E_ARG, "dbl_nms: scratch must be 16-byte aligned");
-    sort_nms_kernel<<<cand->batch, NMS_THREADS, 0, as_stream(stream)>>>(*cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
+    static bool smem_ok = false;
+    if (!smem_ok) {
+        cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM);
+        DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_nms: shared memory opt-in failed: %s", cudaGetErrorString(e));
+        smem_ok = true;
+    }
+    sort_nms_kernel<<<cand->batch, NMS_THREADS, NMS_SMEM, as_stream(stream)>>>(*cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
                                                                         sort_keys, dbl_nms_sort_capacity(cand->cap), out_rows, out_pos,
                                                                         out_count);
     count_launch();

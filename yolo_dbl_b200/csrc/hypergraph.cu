@@ -6,7 +6,8 @@
 //   A = softmax over the N tokens;  He = A^T X;  He2 = GELU(He We^T + be)
 //   y[n] = GELU(sum_e A[n,e] Q[e] + bn) + X[n],   Q = He2 Wn^T
 // so the per-token work is two E-term dot products and no D x D GEMM ever touches the token matrix.
-// Five small launches: context partials -> prototypes -> logits (+softmax partials) -> edges -> nodes.
+// Six small launches: context partials -> prototypes -> logits (+softmax partials) -> edge partials -> edge finalise
+// -> nodes.
 #include "dbl_common.cuh"
 
 namespace dbl {
@@ -16,7 +17,7 @@ constexpr int HG_CTX_SPLIT = 32;   // token splits for the mean/max context
 constexpr int HG_TOK_BLOCK = 128;  // tokens per block in the per-token kernels
 
 struct HgLayout {  // float offsets into the caller's workspace
-    size_t ctx_part, P, cvec, logits, stat_part, stats, Q, total;
+    size_t ctx_part, P, cvec, logits, stat_part, stats, Q, He, total;
     int nblk;
 };
 static HgLayout hg_layout(int B, int N, int D, int E) {
@@ -30,6 +31,7 @@ static HgLayout hg_layout(int B, int N, int D, int E) {
     L.stat_part = o, o += (size_t)B * L.nblk * E * 2;
     L.stats = o, o += (size_t)B * E * 2;
     L.Q = o, o += (size_t)B * E * D;
+    L.He = o, o += (size_t)B * E * D;
     L.total = o;
     return L;
 }
@@ -158,16 +160,15 @@ __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_logits_kernel(const __nv_bflo
     }
 }
 
-// K4: softmax normalisation in place, He = A^T X, He2 = GELU(He We^T + be), Q = He2 Wn^T.  grid (B), block 256.
-__global__ void __launch_bounds__(256) hg_edges_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ logits,
-                                                       const float* __restrict__ stat_part, dbl_hypergraph_weights wt,
-                                                       float* __restrict__ Q, int N, int D, int nblk, int pitch) {
-    extern __shared__ float sm[];  // mstat[2*E] | he[E*D] | he2[E*D] | red[R*E*D] (aliases he2 region onward)
-    const int b = blockIdx.x, E = wt.num_edges;
+// K4a: softmax normalisation in place + partial He = A^T X over a token slice.  grid (HG_EDGE_SPLIT, B), block 256.
+constexpr int HG_EDGE_SPLIT = 8;
+__global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ logits,
+                                                               const float* __restrict__ stat_part, float* __restrict__ He, int N, int D,
+                                                               int E, int nblk, int pitch) {
+    extern __shared__ float sm[];  // mstat[2*HG_MAX_E] | red[R*E*D]
+    const int b = blockIdx.y;
     float* mstat = sm;
-    float* he = sm + 2 * HG_MAX_E;
-    float* he2 = he + E * D;
-    float* red = he2 + E * D;
+    float* red = sm + 2 * HG_MAX_E;
     if (threadIdx.x < E) {
         const int e = threadIdx.x;
         float m = -INFINITY;
@@ -181,38 +182,45 @@ __global__ void __launch_bounds__(256) hg_edges_kernel(const __nv_bfloat16* __re
         mstat[HG_MAX_E + e] = 1.0f / s;
     }
     __syncthreads();
+    const int per = (N + HG_EDGE_SPLIT - 1) / HG_EDGE_SPLIT;
+    const int n0 = blockIdx.x * per, n1 = min(N, n0 + per);
     float* lg = logits + (size_t)b * N * E;
-    for (int i = threadIdx.x; i < N * E; i += blockDim.x) {  // A[n,e] in place
+    for (int i = n0 * E + threadIdx.x; i < n1 * E; i += blockDim.x) {  // A[n,e] in place
         const int e = i % E;
         lg[i] = __expf(lg[i] - mstat[e]) * mstat[HG_MAX_E + e];
     }
     __syncthreads();
-    // He[e,d] = sum_n A[n,e] X[n,d]; thread = (row group r, channel d)
-    const int R = blockDim.x / D > 0 ? blockDim.x / D : 1;
-    const int dpt = (D + blockDim.x - 1) / blockDim.x;  // channels per thread when D > blockDim (not used for D <= 256)
-    (void)dpt;
+    const int R = blockDim.x / D;
     const int d = threadIdx.x % D, r = threadIdx.x / D;
     float acc[HG_MAX_E];
 #pragma unroll
     for (int e = 0; e < HG_MAX_E; ++e) acc[e] = 0.f;
-    if (r < R) {
-        for (int n = r; n < N; n += R) {
-            const float xv = __bfloat162float(x[((size_t)b * N + n) * pitch + d]);
-            const float* a = lg + (size_t)n * E;
+    for (int n = n0 + r; n < n1; n += R) {
+        const float xv = __bfloat162float(x[((size_t)b * N + n) * pitch + d]);
+        const float* a = lg + (size_t)n * E;
 #pragma unroll
-            for (int e = 0; e < HG_MAX_E; ++e) {
-                if (e >= E) break;
-                acc[e] = fmaf(a[e], xv, acc[e]);
-            }
+        for (int e = 0; e < HG_MAX_E; ++e) {
+            if (e >= E) break;
+            acc[e] = fmaf(a[e], xv, acc[e]);
         }
-        for (int e = 0; e < E; ++e) red[((size_t)r * E + e) * D + d] = acc[e];
     }
+    for (int e = 0; e < E; ++e) red[((size_t)r * E + e) * D + d] = acc[e];
     __syncthreads();
     for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
         float s = 0.f;
         for (int rr = 0; rr < R; ++rr) s += red[(size_t)rr * E * D + i];
-        he[i] = s;
+        atomicAdd(He + (size_t)b * E * D + i, s);
     }
+}
+
+// K4b: He2 = GELU(He We^T + be), Q = He2 Wn^T.  grid (B), block 256.
+__global__ void __launch_bounds__(256) hg_edges_final_kernel(const float* __restrict__ He, dbl_hypergraph_weights wt, float* __restrict__ Q,
+                                                             int D) {
+    extern __shared__ float sm[];  // he[E*D] | he2[E*D]
+    const int b = blockIdx.x, E = wt.num_edges;
+    float* he = sm;
+    float* he2 = sm + E * D;
+    for (int i = threadIdx.x; i < E * D; i += blockDim.x) he[i] = He[(size_t)b * E * D + i];
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x & 31, nwarp = blockDim.x / 32;
     for (int row = warp; row < E * D; row += nwarp) {  // He2[e,j] = GELU(sum_d He[e,d] We[j,d] + be[j])
@@ -300,14 +308,13 @@ extern "C" int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights*
     hg_logits_kernel<<<dim3(L.nblk, B), HG_TOK_BLOCK, sm3, st>>>(xp, f + L.P, f + L.cvec, f + L.logits, f + L.stat_part, N, D, E,
                                                                  x->pitch);
     const int R = 256 / D;
-    const size_t sm4 = (2 * HG_MAX_E + (size_t)2 * E * D + (size_t)R * E * D) * sizeof(float);
-    if (sm4 > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(hg_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
-        DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_hypergraph: smem opt-in failed: %s", cudaGetErrorString(e));
-    }
-    hg_edges_kernel<<<B, 256, sm4, st>>>(xp, f + L.logits, f + L.stat_part, *wt, f + L.Q, N, D, L.nblk, x->pitch);
+    const size_t sm4 = (2 * HG_MAX_E + (size_t)R * E * D) * sizeof(float);
+    cudaError_t me = cudaMemsetAsync(f + L.He, 0, (size_t)B * E * D * sizeof(float), st);
+    DBL_REQUIRE(me == cudaSuccess, DBL_E_CUDA, "dbl_hypergraph: memset failed: %s", cudaGetErrorString(me));
+    hg_edges_partial_kernel<<<dim3(HG_EDGE_SPLIT, B), 256, sm4, st>>>(xp, f + L.logits, f + L.stat_part, f + L.He, N, D, E, L.nblk, x->pitch);
+    hg_edges_final_kernel<<<B, 256, (size_t)2 * E * D * sizeof(float), st>>>(f + L.He, *wt, f + L.Q, D);
     hg_nodes_kernel<<<dim3(L.nblk, B), HG_TOK_BLOCK, ((size_t)E * D + D) * sizeof(float), st>>>(
         xp, f + L.logits, f + L.Q, wt->node_b, yp, N, D, E, x->pitch, y->pitch);
-    count_launch(5);
+    count_launch(6);
     return check_launch("dbl_hypergraph");
 }
