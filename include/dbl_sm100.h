@@ -73,6 +73,31 @@ int dbl_stem_conv(const float* x_nchw, int n, int h, int w_, const float* w, con
 int dbl_stem_conv_u8(const uint8_t* x_nchw, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
                      int stride, dbl_stream_t stream);
 
+/* ---- thin high-resolution layers: warp-level MMA kernels (csrc/conv_mma.cu) --------------------------------------
+ * Layers whose arithmetic intensity is far below the B200 ridge (3..64 channels at 640^2..80^2) are HBM-bound; these
+ * entry points fuse neighbouring reference modules so every activation crosses HBM once.
+ * Weights are consumed in MMA B-fragment order; dbl_mma_pack_weights produces that layout ONCE from the dbl_conv2d
+ * layout (bf16 [cout][taps][cin], BatchNorm folded) into caller-owned memory of dbl_mma_packed_bytes() bytes.
+ * cin must be 8 or a multiple of 16, cout a multiple of 8. */
+size_t dbl_mma_packed_bytes(int cout, int cin, int taps);
+int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, void* packed, dbl_stream_t stream);
+/* Bottleneck.forward (nn/modules/block.py:344-357) with e=0.5, k=(3,3): y = x + SiLU(cv2(SiLU(cv1(x)))) in one
+ * kernel; cv1: C -> C/2, cv2: C/2 -> C, C in {16,32,64}; the hidden tensor stays in shared memory.  shortcut = 0 drops
+ * the residual.  x and y must not alias. */
+int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                      int shortcut, const dbl_tensor* y, dbl_stream_t stream);
+/* One thin 3x3 Conv (pad 1, stride 1|2), act in {NONE, SILU}, optional residual; (cin,cout,stride) from the set the
+ * kernel is instantiated for (else DBL_E_UNSUPPORTED): the stride-2 down-samplers 8->16, 16->32, 32->64 and the
+ * stride-1 pairs 16<->8, 32<->16, 64<->32. */
+int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
+                    int stride, int act, int epi, dbl_stream_t stream);
+/* Layers 0 and 1 of the graph fused (cfg/models/v13/yolov13_DBL.yaml:9-10: Conv [c0,3,1] then Conv [c1,3,2]) together
+ * with the input cast / scale of BasePredictor.preprocess (engine/predictor.py:116-134).  x: NCHW (n,3,h,w), f32 in 0..1
+ * (x_is_u8 = 0) or uint8 0..255 (x_is_u8 = 1; the /255 is folded into layer 0's weights).  w0: f32 [c0][3][3][3], w1:
+ * packed (c1, c0, 9 taps).  y: bf16 NHWC (n, h/2, w/2, c1).  (c0,c1) in {(8,16), (16,32)}. */
+int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int w, const float* w0, const float* b0, int c0,
+                  const void* w1_packed, const float* b1, const dbl_tensor* y, dbl_stream_t stream);
+
 /* ---- depthwise convolution ---------------------------------------------------------------------------------------
  * DSConv.dw (conv.py:96-99), DWConv (conv.py:128-133), LSKblock.conv0 / conv_spatial (LSKA.py:31-32).
  *   w: f32 [k*k][c]   bias: f32 [c] or NULL   pad = dil*(k-1)/2 */

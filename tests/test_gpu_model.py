@@ -136,11 +136,13 @@ def test_backend_api_surface_and_facade():
 def test_uint8_input_and_pipelined_stream_match_float_path():
     m = DBLBackend.synthetic("n", 3, seed=0, device="cuda:0")
     xs = [(synth_images(2, 96, 128, 20 + i) * 255).round().to(torch.uint8) for i in range(3)]
-    # uint8 (0..255, scaled inside the stem kernel) == float(x)/255 up to one fp32 rounding of the input
+    # uint8 (0..255 exact in bf16, the /255 folded into layer 0's weights) vs float(x)/255 (pixels rounded to bf16 by the
+    # stem): the two differ by one bf16 rounding of layer 0's operands -> boxes within 0.25 px, scores within 5e-3
     y_f, _ = m(xs[0].float() / 255.0)
     y_u, _ = m(xs[0].pin_memory())
     torch.cuda.synchronize()
-    torch.testing.assert_close(y_u, y_f, rtol=1e-3, atol=2e-2)
+    d = (y_u - y_f).abs()
+    assert float(d[:, :4].max()) <= 0.25 and float(d[:, 4:].max()) <= 5e-3, (float(d[:, :4].max()), float(d[:, 4:].max()))
     # one call per batch from pinned host memory ...
     want = []
     for x in xs:
@@ -152,3 +154,26 @@ def test_uint8_input_and_pipelined_stream_match_float_path():
     for (r, c), (wr, wc) in zip(got, want):
         assert torch.equal(c, wc) and torch.equal(r, wr)
     assert int(sum(int(c.sum()) for _, c in got)) > 0
+
+
+def test_fused_stem_engine_matches_layerwise_engine():
+    """The production engine fuses layers 0+1 (dbl_stem_pair); the layer-wise engine used by the parity tests does not."""
+    spec = resolve(None, "n", 3)
+    sd = synth_state_dict(param_shapes(spec), 0)
+    x = synth_images(2, 128, 160, 4)
+    e_layer = DBLEngine(spec, sd, 2, 128, 160, use_graph=False, keep_layers=True)
+    e_fused = DBLEngine(spec, sd, 2, 128, 160, use_graph=False)
+    assert not e_layer.fuse_stem and e_fused.fuse_stem
+    assert any(m["kern"] == "stem_pair" for m in e_fused.op_meta) and any(m["kern"] == "bottleneck_mma" for m in e_fused.op_meta)
+    y_ref, _ = O.forward(sd, x, "n")
+    for name, inp in (("f32", x.cuda()), ("u8", (x * 255).round().to(torch.uint8).cuda())):
+        y1 = e_layer.forward(inp)[0].clone()
+        y2 = e_fused.forward(inp)[0].clone()
+        torch.cuda.synchronize()
+        d12 = (y1 - y2).abs()
+        dref = (y2.cpu() - y_ref).abs()
+        print(f"[{name}] fused vs layer-wise: box max {float(d12[:, :4].max()):.3f} px, score max {float(d12[:, 4:].max()):.4f}; "
+              f"fused vs oracle: box p99 {float(dref[:, :4].flatten().quantile(0.99)):.3f} px")
+        assert float(d12[:, :4].flatten().quantile(0.99)) <= 1.5 and float(d12[:, 4:].max()) <= 5e-2
+        if name == "f32":
+            assert float(dref[:, :4].flatten().quantile(0.99)) <= 1.5 and float(dref[:, 4:].flatten().quantile(0.99)) <= 1e-2

@@ -276,3 +276,106 @@ def test_argument_errors_are_reported_not_thrown():
     w = torch.zeros(16 * 9 * 16, dtype=torch.bfloat16, device=dev())
     assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(bad), 3, 1, 1, 1, 0, 0, 0, stream()) == 1
     assert lib.dbl_conv2d(C.byref(xv), w.data_ptr(), None, None, C.byref(yv), 3, 1, 2, 2, 0, 0, L.IMPL_TCGEN05, stream()) == 2  # unsupported
+
+
+# ---- warp-MMA kernels for the thin high-resolution layers (csrc/conv_mma.cu) -----------------------------------------
+def _pack_mma(wt):
+    """[Cout,Cin,3,3] fp32 -> device buffer in B-fragment order"""
+    lib = L.require_device()
+    cout, cin = wt.shape[:2]
+    wd = pack_w(wt)
+    nbytes = lib.dbl_mma_packed_bytes(cout, cin, 9)
+    assert nbytes > 0
+    out = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev())
+    assert lib.dbl_mma_pack_weights(wd.data_ptr(), cout, cin, 9, out.data_ptr(), stream()) == 0
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("c,n,h,w,xpad,ypad", [(16, 2, 40, 72, 0, 0), (16, 1, 33, 50, 16, 8), (32, 2, 48, 64, 0, 32), (32, 1, 17, 35, 0, 0),
+                                               (64, 2, 24, 40, 64, 0), (64, 1, 9, 33, 0, 0), (16, 3, 320, 320, 0, 0)])
+def test_bottleneck3x3_fused(c, n, h, w, xpad, ypad):
+    g = torch.Generator().manual_seed(c + h)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    w1 = bf16_round(torch.randn(c // 2, c, 3, 3, generator=g) / (9 * c) ** 0.5)
+    w2 = bf16_round(torch.randn(c, c // 2, 3, 3, generator=g) / (4.5 * c) ** 0.5)
+    b1, b2 = torch.randn(c // 2, generator=g) * 0.3, torch.randn(c, generator=g) * 0.3
+    hid = bf16_round(F.silu(F.conv2d(x, w1, b1, 1, 1)))  # the hidden tensor is held as bf16 in shared memory
+    ref = x + F.silu(F.conv2d(hid, w2, b2, 1, 1))
+    xbuf, xv = to_nhwc(x, pad_c=xpad, c_off=xpad // 2 // 8 * 8)
+    ybuf, yv = empty_nhwc(n, h, w, c, pad_c=ypad, c_off=ypad // 2 // 8 * 8)
+    w1p, w2p, b1d, b2d = _pack_mma(w1), _pack_mma(w2), b1.to(dev()), b2.to(dev())
+    lib = L.require_device()
+    rc = lib.dbl_bottleneck3x3(C.byref(xv), w1p.data_ptr(), b1d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), 1, C.byref(yv), stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    off = (yv.data - ybuf.data_ptr()) // 2
+    assert_close_bf16(from_nhwc(ybuf, off, c), ref, f"bottleneck c={c} {h}x{w}", abs_=3e-2)
+    if ypad:
+        mask = torch.ones(ybuf.shape[-1], dtype=torch.bool)
+        mask[off:off + c] = False
+        assert bool((ybuf[..., mask.to(dev())].float() == -3.0).all()), "kernel wrote outside its channel slice"
+    # shortcut = 0
+    rc = lib.dbl_bottleneck3x3(C.byref(xv), w1p.data_ptr(), b1d.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), 0, C.byref(yv), stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    assert_close_bf16(from_nhwc(ybuf, off, c), ref - x, f"bottleneck (no shortcut) c={c}", abs_=3e-2)
+    # unsupported widths and aliasing fail loudly
+    assert lib.dbl_bottleneck3x3(C.byref(xv), w1p.data_ptr(), None, w2p.data_ptr(), None, 1, C.byref(xv), stream()) == 1
+
+
+@pytest.mark.parametrize("cin,cout,s,n,h,w,epi", [(8, 16, 2, 2, 64, 96, L.EPI_NONE), (16, 32, 2, 2, 40, 72, L.EPI_NONE), (32, 64, 2, 1, 34, 38, L.EPI_NONE),
+                                                  (16, 8, 1, 1, 33, 50, L.EPI_NONE), (8, 16, 1, 2, 24, 40, L.EPI_ADD), (32, 16, 1, 1, 40, 40, L.EPI_NONE),
+                                                  (16, 32, 1, 1, 18, 70, L.EPI_MUL), (64, 32, 1, 1, 20, 36, L.EPI_NONE), (32, 64, 1, 2, 20, 20, L.EPI_ADD),
+                                                  (16, 32, 2, 4, 160, 160, L.EPI_NONE)])
+def test_conv3x3_mma(cin, cout, s, n, h, w, epi):
+    g = torch.Generator().manual_seed(cin * 3 + cout)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.5
+    ref = F.silu(F.conv2d(x, wt, b, s, 1))
+    r = bf16_round(torch.randn(ref.shape, generator=g)) if epi else None
+    if epi == L.EPI_ADD:
+        ref = ref + r
+    elif epi == L.EPI_MUL:
+        ref = ref * r
+    xbuf, xv = to_nhwc(x, pad_c=8, c_off=8)
+    ybuf, yv = empty_nhwc(n, ref.shape[2], ref.shape[3], cout, pad_c=8)
+    rv = None
+    if epi:
+        rbuf, rv = to_nhwc(r)
+    wp, bd = _pack_mma(wt), b.to(dev())
+    rc = L.require_device().dbl_conv3x3_mma(C.byref(xv), wp.data_ptr(), bd.data_ptr(), None if rv is None else C.byref(rv), C.byref(yv), s,
+                                            L.ACT_SILU, epi, stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(ybuf, 0, cout), ref, f"conv3x3_mma {cin}->{cout} s{s}")
+    assert bool((ybuf[..., cout:].float() == -3.0).all())
+
+
+@pytest.mark.parametrize("c0,c1", [(8, 16), (16, 32)])
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("n,h,w", [(2, 64, 96), (1, 160, 224), (1, 34, 70)])
+def test_stem_pair(c0, c1, u8, n, h, w):
+    g = torch.Generator().manual_seed(c0 + h + int(u8))
+    if u8:
+        xi = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
+        x = xi.float() / 255.0
+    else:
+        x = torch.rand(n, 3, h, w, generator=g)
+    w0 = torch.randn(c0, 3, 3, 3, generator=g) / 27 ** 0.5
+    b0 = torch.randn(c0, generator=g) * 0.3
+    w1 = bf16_round(torch.randn(c1, c0, 3, 3, generator=g) / (9 * c0) ** 0.5)
+    b1 = torch.randn(c1, generator=g) * 0.3
+    l0 = bf16_round(F.silu(F.conv2d(x, w0, b0, 1, 1)))  # layer 0's output is held as bf16 in shared memory
+    ref = F.silu(F.conv2d(l0, w1, b1, 2, 1))
+    ybuf, yv = empty_nhwc(n, h // 2, w // 2, c1, pad_c=8)
+    xd = (xi if u8 else x).to(dev())
+    w0d, b0d, b1d, w1p = w0.to(dev()), b0.to(dev()), b1.to(dev()), _pack_mma(w1)
+    rc = L.require_device().dbl_stem_pair(xd.data_ptr(), int(u8), n, h, w, w0d.data_ptr(), b0d.data_ptr(), c0, w1p.data_ptr(), b1d.data_ptr(),
+                                          C.byref(yv), stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    # layer 0 runs on bf16-rounded pixels / weights here (fp32 in the reference): one extra 2^-9 rounding per operand
+    assert_close_bf16(from_nhwc(ybuf, 0, c1), ref, f"stem_pair {c0}->{c1} u8={u8}", rel=2.0 ** -6, abs_=4e-2)
+    assert bool((ybuf[..., c1:].float() == -3.0).all())

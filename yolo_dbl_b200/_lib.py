@@ -54,6 +54,11 @@ _SIGNATURES = {
     "dbl_conv2d": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_stem_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
     "dbl_stem_conv_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
+    "dbl_mma_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dbl_mma_pack_weights": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "dbl_bottleneck3x3": (C.c_int, [_TP, _P, _P, _P, _P, C.c_int, _TP, _P]),
+    "dbl_conv3x3_mma": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, _P]),
+    "dbl_stem_pair": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _TP, _P]),
     "dbl_dwconv2d": (C.c_int, [_TP, _P, _P, _TP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_avgpool2": (C.c_int, [_TP, _TP, _P]),
     "dbl_upsample2_nearest": (C.c_int, [_TP, _TP, _P]),

@@ -1,0 +1,845 @@
+// Thin, high-resolution 3x3 convolutions on warp-level tensor-core MMA (mma.sync m16n8k16 bf16, fp32 accumulate).
+//
+// Layers 0-6 of YOLO-DBL run at 640^2..80^2 with 3..64 channels: their arithmetic intensity is far below the B200 ridge,
+// so they are HBM-bound and what matters is (a) touching every activation once and (b) spending few instructions per
+// pixel.  tcgen05's 128-row, single-issuer, TMEM-epilogue machinery costs thousands of instructions per 128-pixel tile
+// on such layers (ncu: issue-bound at 19% of HBM peak), so these layers get their own kernels:
+//
+//   * bottleneck_mma_kernel : Bottleneck.forward (block.py:344-357) = x + cv2(cv1(x)) in ONE kernel.  The input tile
+//     (+2 pixel halo) is fetched once with cp.async into a planar shared-memory layout, cv1's output (+1 pixel halo,
+//     recomputed) stays in shared memory as bf16, cv2 reads it from there, the residual comes from the input tile.
+//     HBM traffic = read x once + write y once.
+//   * stem_pair_kernel      : layer 0 (3 -> C0, stride 1, on the raw f32/uint8 NCHW image) + layer 1 (C0 -> C1, stride 2)
+//     fused; the C0 x 640 x 640 intermediate never leaves shared memory.
+//   * conv3x3_mma_kernel    : single 3x3 conv (stride 1 or 2) for thin layers (the stride-2 down-samplers).
+//
+// Shared-memory operand layout ("planar"): plane g holds channels [8g, 8g+8) of every tile pixel, 16 bytes per pixel,
+// pixels linearised with the INPUT tile's row pitch.  With that pitch shared by producer and consumer tiles, the A
+// operand of filter tap (ky,kx) for 16 consecutive GEMM rows is the same buffer advanced by (ky*pitch + kx) pixels: one
+// ldmatrix.x4 per (16 pixels x 16 k) fragment, conflict-free, no im2col.  GEMM rows that fall on the 2 (or 4) halo
+// columns of each tile row are junk and never stored.  8-channel inputs pair two taps per k-step.  Stride-2 convs keep
+// four parity sub-tiles (row parity x column parity) so taps are unit-stride again.
+// Weights are pre-packed once (dbl_mma_pack_weights) in B-fragment order: one 8-byte load per lane per (k-step, n-block).
+// Output channels are permuted inside the packed weights so that every thread owns 2*NB CONTIGUOUS channels of its
+// pixels -> 8/16-byte global stores without any shuffle.
+#include "tc_ptx.cuh"
+
+namespace dbl {
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- packed-weight geometry (shared by the pack kernel and the consumers) -------------------------------------------
+// k-steps: cin >= 16: tap-major, 16 channels per step;  cin == 8: two taps per step (an odd tap count pads with zeros)
+__host__ __device__ constexpr int mma_ksteps(int cin, int taps) { return cin == 8 ? (taps + 1) / 2 : taps * (cin / 16); }
+// GEMM column n (0..7) of n-block j  ->  output channel: thread t = n/2 owns channels [t*2NB, (t+1)*2NB)
+__host__ __device__ constexpr int mma_chan(int nb_total, int j, int n) { return (n >> 1) * 2 * nb_total + 2 * j + (n & 1); }
+
+__global__ void mma_pack_kernel(const __nv_bfloat16* __restrict__ w, int cout, int cin, int taps, uint2* __restrict__ out) {
+    const int nb = cout / 8, ks_n = mma_ksteps(cin, taps);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ks_n * nb * 32) return;
+    const int lane = i & 31, j = (i >> 5) % nb, ks = (i >> 5) / nb;
+    const int ch = mma_chan(nb, j, lane >> 2), t = lane & 3;
+    uint32_t v[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // k = 2t, 2t+1 (half 0) and 2t+8, 2t+9 (half 1) of this k-step
+        int tap, c;
+        if (cin == 8) {
+            tap = 2 * ks + half, c = 2 * t;
+        } else {
+            const int cp = cin / 16;
+            tap = ks / cp, c = (ks % cp) * 16 + half * 8 + 2 * t;
+        }
+        uint32_t pair = 0;
+        if (tap < taps) pair = *reinterpret_cast<const uint32_t*>(w + ((size_t)ch * taps + tap) * cin + c);
+        v[half] = pair;
+    }
+    out[i] = make_uint2(v[0], v[1]);
+}
+
+// ---- tap offsets (bytes) inside a planar tile ---------------------------------------------------------------------
+template <int PITCH>
+struct OffS1 {  // stride 1: tile pixels linearised with row pitch PITCH
+    static __device__ __forceinline__ constexpr uint32_t at(int tap) { return (uint32_t)(((tap / 3) * PITCH + tap % 3) * 16); }
+};
+template <int PITCH, int PARB>
+struct OffS2 {  // stride 2: four parity sub-tiles of PARB bytes each, sub-tile pixels linearised with row pitch PITCH
+    static __device__ __forceinline__ constexpr uint32_t at(int tap) {
+        const int ky = tap / 3, kx = tap % 3;
+        return (uint32_t)(((ky & 1) * 2 + (kx & 1)) * PARB + ((ky >> 1) * PITCH + (kx >> 1)) * 16);
+    }
+};
+
+// One conv "phase": acc[mb][j] += A(tile rows m0*16.. , taps) x B for MB consecutive 16-row blocks.
+//   a_addr: shared byte address of GEMM row (lane&7)+8*((lane>>3)&1) of the first block, tap 0, plane (CIN>8 ? lane>>4 : 0)
+//   b_addr: shared byte address of this lane's slot in the packed weights
+template <int CIN, int NB, int MB, int PS, class Off>
+__device__ __forceinline__ void conv_phase(float (&acc)[MB][NB][4], uint32_t a_addr, uint32_t b_addr, bool hi) {
+    constexpr int KS = mma_ksteps(CIN, 9);
+    // software pipeline (everything is unrolled): A fragments one k-step ahead, B fragment one n-block ahead
+    auto a_off = [&](int ks) -> uint32_t {
+        if (CIN == 8) return hi ? Off::at(2 * ks + 1 < 9 ? 2 * ks + 1 : 8) : Off::at(2 * ks);
+        return Off::at(ks / (CIN >= 16 ? CIN / 16 : 1)) + (uint32_t)(2 * (ks % (CIN >= 16 ? CIN / 16 : 1)) * PS);
+    };
+    uint32_t a[2][MB][4];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) ldsm_x4(a_addr + a_off(0) + mb * 256, a[0][mb]);
+    uint2 b_next = lds64(b_addr);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        if (ks + 1 < KS) {
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) ldsm_x4(a_addr + a_off(ks + 1) + mb * 256, a[(ks + 1) & 1][mb]);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            const uint2 b = b_next;
+            if (ks * NB + j + 1 < KS * NB) b_next = lds64(b_addr + (uint32_t)((ks * NB + j + 1) * 256));
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) mma16816(acc[mb][j], a[ks & 1][mb], b.x, b.y);
+        }
+    }
+}
+
+// plane stride (in pixels) >= need, chosen so the 16-byte cp.async stores of one quarter-warp (G consecutive planes of
+// the same pixel, then the next pixel) spread over all banks
+__host__ __device__ constexpr int plane_px(int need, int g) {
+    const int gg = g > 8 ? 8 : g;
+    const int want = gg <= 1 ? 0 : (8 / gg) % 8;
+    int v = need;
+    if (gg > 1)
+        while (v % 8 != want) ++v;
+    return v;
+}
+__host__ __device__ constexpr int round16(int v) { return (v + 15) / 16 * 16; }
+
+// store 2*NB contiguous bf16 channels (thread t's share of one pixel) into a planar tile / read them back
+template <int NB>
+__device__ __forceinline__ void planar_store(uint32_t tile, int ps_bytes, int pix, int t, const uint32_t* v) {
+    if (NB == 1) sts32(tile + pix * 16 + t * 4, v[0]);
+    else if (NB == 2) sts64(tile + (t >> 1) * ps_bytes + pix * 16 + (t & 1) * 8, make_uint2(v[0], v[1]));
+    else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q)
+            sts128(tile + (t * (NB / 4) + q) * ps_bytes + pix * 16, make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    }
+}
+template <int NB>
+__device__ __forceinline__ void planar_load(uint32_t tile, int ps_bytes, int pix, int t, uint32_t* v) {
+    if (NB == 1) v[0] = lds32(tile + pix * 16 + t * 4);
+    else if (NB == 2) {
+        const uint2 u = lds64(tile + (t >> 1) * ps_bytes + pix * 16 + (t & 1) * 8);
+        v[0] = u.x, v[1] = u.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q) {
+            const uint4 u = lds128(tile + (t * (NB / 4) + q) * ps_bytes + pix * 16);
+            v[4 * q] = u.x, v[4 * q + 1] = u.y, v[4 * q + 2] = u.z, v[4 * q + 3] = u.w;
+        }
+    }
+}
+// 2*NB contiguous bf16 channels to / from global memory (p is 4*NB-byte aligned)
+template <int NB>
+__device__ __forceinline__ void global_store(__nv_bfloat16* p, const uint32_t* v) {
+    if (NB == 1) *reinterpret_cast<uint32_t*>(p) = v[0];
+    else if (NB == 2) *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+    else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q) reinterpret_cast<uint4*>(p)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+template <int NB>
+__device__ __forceinline__ void global_load(const __nv_bfloat16* p, uint32_t* v) {
+    if (NB == 1) v[0] = *reinterpret_cast<const uint32_t*>(p);
+    else if (NB == 2) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        v[0] = u.x, v[1] = u.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q) {
+            const uint4 u = reinterpret_cast<const uint4*>(p)[q];
+            v[4 * q] = u.x, v[4 * q + 1] = u.y, v[4 * q + 2] = u.z, v[4 * q + 3] = u.w;
+        }
+    }
+}
+
+// =====================================================================================================================
+// fused Bottleneck: y = x + SiLU(cv2(SiLU(cv1(x))))          x, y: bf16 NHWC with C channels; hidden = C/2 channels
+// =====================================================================================================================
+struct BnParams {
+    const __nv_bfloat16* x;
+    __nv_bfloat16* y;
+    const uint2* w1;  // packed [ks][nb][lane]
+    const uint2* w2;
+    const float* b1;
+    const float* b2;
+    int n, h, w, xpitch, ypitch, add;
+    int tiles_x, tiles_y, ntiles;
+};
+
+template <int C, int TH, int TW>
+struct BnCfg {
+    static constexpr int H = C / 2;
+    static constexpr int WI = TW + 4;                       // row pitch of every tile (pixels)
+    static constexpr int M1 = round16((TH + 2) * WI) / 16;  // cv1 m-blocks (hidden tile incl. halo, pitch WI)
+    static constexpr int M2 = round16(TH * WI) / 16;        // cv2 m-blocks
+    static constexpr int IN_NEED = M1 * 16 + 2 * WI + 2;    // pixels a cv1 fragment load may touch
+    static constexpr int GI = C / 8, GH = H / 8;
+    static constexpr int PSI = plane_px(IN_NEED > (TH + 4) * WI ? IN_NEED : (TH + 4) * WI, GI) * 16;  // bytes
+    static constexpr int HID_NEED = (M1 * 16 > M2 * 16 + 2 * WI + 2) ? M1 * 16 : M2 * 16 + 2 * WI + 2;
+    static constexpr int PSH = plane_px(HID_NEED, GH) * 16;
+    static constexpr int NB1 = H / 8, NB2 = C / 8;
+    static constexpr int KS1 = mma_ksteps(C, 9), KS2 = mma_ksteps(H, 9);
+    static constexpr int W1B = KS1 * NB1 * 256, W2B = KS2 * NB2 * 256;
+    static constexpr int IN_BYTES = GI * PSI, HID_BYTES = GH * PSH;
+    static constexpr int SMEM = 2 * IN_BYTES + HID_BYTES + W1B + W2B + (H + C) * 4 + 128;
+    static_assert(SMEM <= 227 * 1024, "bottleneck tile does not fit shared memory");
+};
+
+template <int C, int TH, int TW, int NWARPS, int MB>
+__global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnParams p) {
+    using K = BnCfg<C, TH, TW>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const uint32_t sIn = smem_u32(smem);
+    const uint32_t sHid = sIn + 2 * K::IN_BYTES;
+    const uint32_t sW1 = sHid + K::HID_BYTES;
+    const uint32_t sW2 = sW1 + K::W1B;
+    float* sB1 = reinterpret_cast<float*>(smem + 2 * K::IN_BYTES + K::HID_BYTES + K::W1B + K::W2B);
+    float* sB2 = sB1 + K::H;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = NWARPS * 32;
+
+    auto prefetch = [&](int tile, int buf) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        const __nv_bfloat16* ximg = p.x + (size_t)img * p.h * p.w * p.xpitch;
+        const uint32_t dst0 = sIn + buf * K::IN_BYTES;
+        constexpr int ITEMS = (TH + 4) * K::WI * K::GI;
+        for (int i = tid; i < ITEMS; i += NT) {
+            const int gi = i % K::GI, pix = i / K::GI;
+            const int ly = pix / K::WI, lx = pix - ly * K::WI;
+            const int gy = oy0 - 2 + ly, gx = ox0 - 2 + lx;
+            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+            const __nv_bfloat16* src = ok ? ximg + ((size_t)gy * p.w + gx) * p.xpitch + gi * 8 : p.x;
+            cp_async16(dst0 + gi * K::PSI + pix * 16, src, ok);
+        }
+    };
+
+    // weights + biases: once per CTA
+    for (int i = tid; i < K::W1B / 16; i += NT) cp_async16(sW1 + i * 16, reinterpret_cast<const uint8_t*>(p.w1) + i * 16, true);
+    for (int i = tid; i < K::W2B / 16; i += NT) cp_async16(sW2 + i * 16, reinterpret_cast<const uint8_t*>(p.w2) + i * 16, true);
+    for (int i = tid; i < K::H; i += NT) sB1[i] = p.b1 ? p.b1[i] : 0.f;
+    for (int i = tid; i < C; i += NT) sB2[i] = p.b2 ? p.b2[i] : 0.f;
+    int tile = blockIdx.x, buf = 0;
+    if (tile < p.ntiles) prefetch(tile, 0);
+    cp_async_commit();
+
+    // lane constants of the ldmatrix row addresses
+    const uint32_t row16 = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
+    const bool hi = lane >= 16;
+    const uint32_t a1_lane = row16 + (C > 8 && hi ? K::PSI : 0);
+    const uint32_t a2_lane = row16 + (K::H > 8 && hi ? K::PSH : 0);
+
+    for (; tile < p.ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < p.ntiles) prefetch(next, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        const uint32_t in = sIn + buf * K::IN_BYTES;
+
+        // ---------------- cv1: hidden tile (TH+2 rows, pitch WI) ----------------
+        for (int m0 = warp * MB; m0 < K::M1; m0 += NWARPS * MB) {
+            float acc[MB][K::NB1][4];
+#pragma unroll
+            for (int j = 0; j < K::NB1; ++j) {
+                const float2 bb = *reinterpret_cast<const float2*>(sB1 + t * 2 * K::NB1 + 2 * j);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
+            }
+            conv_phase<C, K::NB1, MB, K::PSI, OffS1<K::WI>>(acc, in + a1_lane + m0 * 256, sW1 + lane * 8, hi);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                if (m0 + mb >= K::M1) break;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int q = (m0 + mb) * 16 + g + 8 * rh;
+                    const int hy = q / K::WI, hx = q - hy * K::WI;
+                    const int gy = oy0 - 1 + hy, gx = ox0 - 1 + hx;
+                    const bool inside = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;  // cv2 zero-pads cv1's OUTPUT
+                    uint32_t v[K::NB1];
+#pragma unroll
+                    for (int j = 0; j < K::NB1; ++j)
+                        v[j] = inside ? pack2(silu_fast(acc[mb][j][2 * rh]), silu_fast(acc[mb][j][2 * rh + 1])) : 0u;
+                    planar_store<K::NB1>(sHid, K::PSH, q, t, v);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- cv2 + residual -> global ----------------
+        for (int m0 = warp * MB; m0 < K::M2; m0 += NWARPS * MB) {
+            float acc[MB][K::NB2][4];
+#pragma unroll
+            for (int j = 0; j < K::NB2; ++j) {
+                const float2 bb = *reinterpret_cast<const float2*>(sB2 + t * 2 * K::NB2 + 2 * j);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
+            }
+            conv_phase<K::H, K::NB2, MB, K::PSH, OffS1<K::WI>>(acc, sHid + a2_lane + m0 * 256, sW2 + lane * 8, hi);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                if (m0 + mb >= K::M2) break;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int o = (m0 + mb) * 16 + g + 8 * rh;
+                    const int oy = o / K::WI, ox = o - oy * K::WI;
+                    const int gy = oy0 + oy, gx = ox0 + ox;
+                    if (ox >= TW || gy >= p.h || gx >= p.w) continue;
+                    uint32_t res[K::NB2];
+                    if (p.add) planar_load<K::NB2>(in, K::PSI, o + 2 * K::WI + 2, t, res);
+                    uint32_t v[K::NB2];
+#pragma unroll
+                    for (int j = 0; j < K::NB2; ++j) {
+                        float a = silu_fast(acc[mb][j][2 * rh]), b = silu_fast(acc[mb][j][2 * rh + 1]);
+                        if (p.add) {
+                            float r0, r1;
+                            unpack2(res[j], r0, r1);
+                            a += r0, b += r1;
+                        }
+                        v[j] = pack2(a, b);
+                    }
+                    global_store<K::NB2>(p.y + (((size_t)img * p.h + gy) * p.w + gx) * p.ypitch + t * 2 * K::NB2, v);
+                }
+            }
+        }
+        __syncthreads();  // the next iteration's prefetch overwrites this buffer's twin; cv1 overwrites the hidden tile
+    }
+    cp_async_wait<0>();
+}
+
+// =====================================================================================================================
+// single thin 3x3 conv, stride 1 or 2, SiLU / none, optional residual (add / mul) read from global
+// =====================================================================================================================
+struct CmParams {
+    const __nv_bfloat16* x;
+    __nv_bfloat16* y;
+    const __nv_bfloat16* r;
+    const uint2* w;
+    const float* b;
+    int n, h, wd, ho, wo, xpitch, ypitch, rpitch, act, epi;
+    int tiles_x, tiles_y, ntiles;
+};
+
+template <int CIN, int COUT, int S, int TH, int TW>
+struct CmCfg {
+    static constexpr int E = S == 1 ? 2 : 1;           // extra rows / columns per (sub-)tile
+    static constexpr int WP = TW + E;                   // row pitch of a (sub-)tile
+    static constexpr int M = round16(TH * WP) / 16;
+    static constexpr int NPAR = S == 1 ? 1 : 4;
+    static constexpr int SUB_NEED = M * 16 + E * WP + E;  // pixels per (sub-)tile a fragment load may touch
+    static constexpr int SUB_PX = SUB_NEED > (TH + E) * WP ? SUB_NEED : (TH + E) * WP;
+    static constexpr int GI = CIN / 8;
+    static constexpr int PARB = SUB_PX * 16;                       // bytes of one parity sub-tile within a plane
+    static constexpr int PS = plane_px(NPAR * SUB_PX, GI) * 16;    // plane stride (bytes)
+    static constexpr int NB = COUT / 8;
+    static constexpr int KS = mma_ksteps(CIN, 9);
+    static constexpr int WB = KS * NB * 256;
+    static constexpr int IN_BYTES = GI * PS;
+    static constexpr int SMEM = 2 * IN_BYTES + WB + COUT * 4 + 128;
+    static_assert(SMEM <= 227 * 1024, "conv tile does not fit shared memory");
+};
+
+template <int CIN, int COUT, int S, int TH, int TW, int NWARPS, int MB>
+__global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams p) {
+    using K = CmCfg<CIN, COUT, S, TH, TW>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const uint32_t sIn = smem_u32(smem);
+    const uint32_t sW = sIn + 2 * K::IN_BYTES;
+    float* sB = reinterpret_cast<float*>(smem + 2 * K::IN_BYTES + K::WB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = NWARPS * 32;
+
+    auto prefetch = [&](int tile, int buf) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        const __nv_bfloat16* ximg = p.x + (size_t)img * p.h * p.wd * p.xpitch;
+        const uint32_t dst0 = sIn + buf * K::IN_BYTES;
+        constexpr int ROWS = S * TH + (S == 1 ? 2 : 1), COLS = S * TW + (S == 1 ? 2 : 1);  // input footprint of the tile
+        constexpr int ITEMS = ROWS * COLS * K::GI;
+        for (int i = tid; i < ITEMS; i += NT) {
+            const int gi = i % K::GI, pix = i / K::GI;
+            const int ly = pix / COLS, lx = pix - ly * COLS;
+            const int gy = S * oy0 - 1 + ly, gx = S * ox0 - 1 + lx;
+            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.wd;
+            const __nv_bfloat16* src = ok ? ximg + ((size_t)gy * p.wd + gx) * p.xpitch + gi * 8 : p.x;
+            uint32_t d;
+            if (S == 1) d = (uint32_t)((ly * K::WP + lx) * 16);
+            else d = (uint32_t)(((ly & 1) * 2 + (lx & 1)) * K::PARB + ((ly >> 1) * K::WP + (lx >> 1)) * 16);
+            cp_async16(dst0 + gi * K::PS + d, src, ok);
+        }
+    };
+
+    for (int i = tid; i < K::WB / 16; i += NT) cp_async16(sW + i * 16, reinterpret_cast<const uint8_t*>(p.w) + i * 16, true);
+    for (int i = tid; i < COUT; i += NT) sB[i] = p.b ? p.b[i] : 0.f;
+    int tile = blockIdx.x, buf = 0;
+    if (tile < p.ntiles) prefetch(tile, 0);
+    cp_async_commit();
+    const uint32_t row16 = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
+    const bool hi = lane >= 16;
+    const uint32_t a_lane = row16 + (CIN > 8 && hi ? K::PS : 0);
+
+    for (; tile < p.ntiles; tile += gridDim.x, buf ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < p.ntiles) prefetch(next, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        const uint32_t in = sIn + buf * K::IN_BYTES;
+        for (int m0 = warp * MB; m0 < K::M; m0 += NWARPS * MB) {
+            float acc[MB][K::NB][4];
+#pragma unroll
+            for (int j = 0; j < K::NB; ++j) {
+                const float2 bb = *reinterpret_cast<const float2*>(sB + t * 2 * K::NB + 2 * j);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
+            }
+            if (S == 1) conv_phase<CIN, K::NB, MB, K::PS, OffS1<K::WP>>(acc, in + a_lane + m0 * 256, sW + lane * 8, hi);
+            else conv_phase<CIN, K::NB, MB, K::PS, OffS2<K::WP, K::PARB>>(acc, in + a_lane + m0 * 256, sW + lane * 8, hi);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                if (m0 + mb >= K::M) break;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int o = (m0 + mb) * 16 + g + 8 * rh;
+                    const int oy = o / K::WP, ox = o - oy * K::WP;
+                    const int gy = oy0 + oy, gx = ox0 + ox;
+                    if (ox >= TW || oy >= TH || gy >= p.ho || gx >= p.wo) continue;
+                    const size_t opix = ((size_t)img * p.ho + gy) * p.wo + gx;
+                    uint32_t res[K::NB];
+                    if (p.epi != DBL_EPI_NONE) global_load<K::NB>(p.r + opix * p.rpitch + t * 2 * K::NB, res);
+                    uint32_t v[K::NB];
+#pragma unroll
+                    for (int j = 0; j < K::NB; ++j) {
+                        float a = acc[mb][j][2 * rh], b = acc[mb][j][2 * rh + 1];
+                        if (p.act == DBL_ACT_SILU) a = silu_fast(a), b = silu_fast(b);
+                        if (p.epi != DBL_EPI_NONE) {
+                            float r0, r1;
+                            unpack2(res[j], r0, r1);
+                            if (p.epi == DBL_EPI_ADD) a += r0, b += r1;
+                            else a *= r0, b *= r1;
+                        }
+                        v[j] = pack2(a, b);
+                    }
+                    global_store<K::NB>(p.y + opix * p.ypitch + t * 2 * K::NB, v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+// =====================================================================================================================
+// fused stem: layer 0 (3 -> C0, 3x3 s1, SiLU) on the raw NCHW image + layer 1 (C0 -> C1, 3x3 s2, SiLU)
+// =====================================================================================================================
+struct StemParams {
+    const void* x;      // f32 or u8 NCHW (n,3,h,w)
+    const float* w0;    // f32 [C0][3][3][3]
+    const float* b0;
+    const uint2* w1;    // packed
+    const float* b1;
+    __nv_bfloat16* y;   // (n, h/2, w/2, C1)
+    int n, h, w, ho, wo, ypitch;
+    float in_scale;     // 1 (f32 input in 0..1) or 1/255 (u8), folded into layer 0's weights
+    int tiles_x, tiles_y;
+};
+
+template <int C0, int C1, int TH, int TW>
+struct StemCfg {
+    static constexpr int R0 = 2 * TH + 1, W0 = 2 * TW + 1;  // layer-0 outputs layer 1 needs (rows, cols)
+    static constexpr int RI = R0 + 2;                        // input rows
+    static constexpr int PI = 2 * TW + 4;                    // input row pitch (pixels of 8 bytes: 4 x bf16, RGB0)
+    static constexpr int M0 = round16(R0 * PI) / 16;         // layer-0 m-blocks (pitch PI -> tap shift = address offset)
+    static constexpr int IN_PX = M0 * 16 + 2 * PI + 8;
+    static constexpr int IN_BYTES = ((IN_PX > RI * PI ? IN_PX : RI * PI) * 8 + 127) / 128 * 128;
+    static constexpr int WP = TW + 1;                        // layer-0 parity sub-tile pitch
+    static constexpr int M1 = round16(TH * WP) / 16;
+    static constexpr int SUB_NEED = M1 * 16 + WP + 2;
+    static constexpr int SUB_PX = SUB_NEED > (TH + 1) * WP ? SUB_NEED : (TH + 1) * WP;
+    static constexpr int PARB = SUB_PX * 16;
+    static constexpr int G0 = C0 / 8;
+    static constexpr int PS0 = plane_px(4 * SUB_PX, G0) * 16;
+    static constexpr int L0_BYTES = G0 * PS0;
+    static constexpr int NB0 = C0 / 8, NB1 = C1 / 8;
+    static constexpr int KS1 = mma_ksteps(C0, 9);
+    static constexpr int W0B = 3 * NB0 * 256, W1B = KS1 * NB1 * 256;
+    static constexpr int SMEM = IN_BYTES + L0_BYTES + W0B + W1B + (C0 + C1) * 4 + 128;
+    static_assert(SMEM <= 227 * 1024, "stem tile does not fit shared memory");
+};
+
+template <int C0, int C1, int TH, int TW, int NWARPS, typename TIN>
+__global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams p) {
+    using K = StemCfg<C0, C1, TH, TW>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const uint32_t sIn = smem_u32(smem);
+    const uint32_t sL0 = sIn + K::IN_BYTES;
+    const uint32_t sW0 = sL0 + K::L0_BYTES;
+    const uint32_t sW1 = sW0 + K::W0B;
+    float* sB0 = reinterpret_cast<float*>(smem + K::IN_BYTES + K::L0_BYTES + K::W0B + K::W1B);
+    float* sB1 = sB0 + C0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int NT = NWARPS * 32;
+
+    const int img = blockIdx.z, oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+
+    // ---- weights: layer 1 packed (async copy); layer 0 packed here from f32 [C0][ci][ky][kx]: k-step = ky, k = kx*4 + ci
+    for (int i = tid; i < K::W1B / 16; i += NT) cp_async16(sW1 + i * 16, reinterpret_cast<const uint8_t*>(p.w1) + i * 16, true);
+    cp_async_commit();
+    for (int i = tid; i < 3 * K::NB0 * 32; i += NT) {
+        const int ln = i & 31, j = (i >> 5) % K::NB0, ky = (i >> 5) / K::NB0;
+        const int ch = mma_chan(K::NB0, j, ln >> 2), tt = ln & 3;
+        uint32_t v[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float f[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * tt + 8 * half + e, kx = k >> 2, ci = k & 3;
+                f[e] = (kx < 3 && ci < 3) ? p.w0[((ch * 3 + ci) * 3 + ky) * 3 + kx] * p.in_scale : 0.f;
+            }
+            v[half] = pack2(f[0], f[1]);
+        }
+        sts64(sW0 + i * 8, make_uint2(v[0], v[1]));
+    }
+    for (int i = tid; i < C0; i += NT) sB0[i] = p.b0 ? p.b0[i] : 0.f;
+    for (int i = tid; i < C1; i += NT) sB1[i] = p.b1 ? p.b1[i] : 0.f;
+
+    // ---- stage the input tile: rows 2*oy0-2 .., cols 2*ox0-2 ..; pixel = {R,G,B,0} bf16 (8 bytes); zero outside the image
+    {
+        const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)img * 3 * p.h * p.w;
+        const size_t plane = (size_t)p.h * p.w;
+        for (int i = tid; i < K::RI * K::PI; i += NT) {
+            const int ly = i / K::PI, lx = i - ly * K::PI;
+            const int gy = 2 * oy0 - 2 + ly, gx = 2 * ox0 - 2 + lx;
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
+                const TIN* s = xin + (size_t)gy * p.w + gx;
+                c0 = (float)__ldg(s), c1 = (float)__ldg(s + plane), c2 = (float)__ldg(s + 2 * plane);
+            }
+            sts64(sIn + i * 8, make_uint2(pack2(c0, c1), pack2(c2, 0.f)));
+        }
+        // the few pixels past the last row that junk GEMM rows touch: keep them finite
+        for (int i = K::RI * K::PI + tid; i < K::IN_BYTES / 8; i += NT) sts64(sIn + i * 8, make_uint2(0u, 0u));
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- layer 0: GEMM rows q = ly*PI + lx over the layer-0 tile; k-step ky reads 32 contiguous bytes of input row ly+ky
+    {
+        uint2 bw[3][K::NB0];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int j = 0; j < K::NB0; ++j) bw[ky][j] = lds64(sW0 + ((ky * K::NB0 + j) * 32 + lane) * 8);
+        float2 bias[K::NB0];
+#pragma unroll
+        for (int j = 0; j < K::NB0; ++j) bias[j] = *reinterpret_cast<const float2*>(sB0 + t * 2 * K::NB0 + 2 * j);
+        constexpr int MB = 2;
+        for (int m0 = warp * MB; m0 < K::M0; m0 += NWARPS * MB) {
+            float acc[MB][K::NB0][4];
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int j = 0; j < K::NB0; ++j)
+                    acc[mb][j][0] = acc[mb][j][2] = bias[j].x, acc[mb][j][1] = acc[mb][j][3] = bias[j].y;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t base = sIn + (uint32_t)((((m0 + mb) * 16 + g) + ky * K::PI) * 8 + t * 4);
+                    uint32_t a[4];
+                    a[0] = lds32(base), a[1] = lds32(base + 64), a[2] = lds32(base + 16), a[3] = lds32(base + 80);
+#pragma unroll
+                    for (int j = 0; j < K::NB0; ++j) mma16816(acc[mb][j], a, bw[ky][j].x, bw[ky][j].y);
+                }
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                if (m0 + mb >= K::M0) break;
+#pragma unroll
+                for (int rh = 0; rh < 2; ++rh) {
+                    const int q = (m0 + mb) * 16 + g + 8 * rh;
+                    const int ly = q / K::PI, lx = q - ly * K::PI;
+                    if (ly >= K::R0 || lx >= K::W0) continue;
+                    const int gy = 2 * oy0 - 1 + ly, gx = 2 * ox0 - 1 + lx;
+                    const bool inside = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;  // layer 1 zero-pads layer 0's OUTPUT
+                    uint32_t v[K::NB0];
+#pragma unroll
+                    for (int j = 0; j < K::NB0; ++j)
+                        v[j] = inside ? pack2(silu_fast(acc[mb][j][2 * rh]), silu_fast(acc[mb][j][2 * rh + 1])) : 0u;
+                    const int sub = ((ly & 1) * 2 + (lx & 1)) * K::SUB_PX + (ly >> 1) * K::WP + (lx >> 1);
+                    planar_store<K::NB0>(sL0, K::PS0, sub, t, v);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- layer 1: stride 2 over the parity sub-tiles
+    {
+        const uint32_t row16 = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
+        const bool hi = lane >= 16;
+        const uint32_t a_lane = row16 + (C0 > 8 && hi ? K::PS0 : 0);
+        constexpr int MB = 1;
+        for (int m0 = warp * MB; m0 < K::M1; m0 += NWARPS * MB) {
+            float acc[MB][K::NB1][4];
+#pragma unroll
+            for (int j = 0; j < K::NB1; ++j) {
+                const float2 bb = *reinterpret_cast<const float2*>(sB1 + t * 2 * K::NB1 + 2 * j);
+                acc[0][j][0] = acc[0][j][2] = bb.x, acc[0][j][1] = acc[0][j][3] = bb.y;
+            }
+            conv_phase<C0, K::NB1, MB, K::PS0, OffS2<K::WP, K::PARB>>(acc, sL0 + a_lane + m0 * 256, sW1 + lane * 8, hi);
+#pragma unroll
+            for (int rh = 0; rh < 2; ++rh) {
+                const int o = m0 * 16 + g + 8 * rh;
+                const int oy = o / K::WP, ox = o - oy * K::WP;
+                const int gy = oy0 + oy, gx = ox0 + ox;
+                if (ox >= TW || oy >= TH || gy >= p.ho || gx >= p.wo) continue;
+                uint32_t v[K::NB1];
+#pragma unroll
+                for (int j = 0; j < K::NB1; ++j) v[j] = pack2(silu_fast(acc[0][j][2 * rh]), silu_fast(acc[0][j][2 * rh + 1]));
+                global_store<K::NB1>(p.y + (((size_t)img * p.ho + gy) * p.wo + gx) * p.ypitch + t * 2 * K::NB1, v);
+            }
+        }
+    }
+}
+
+static int g_sms = 0;
+static int sm_count() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sms;
+}
+
+template <class Kern>
+static int launch_persistent(Kern kern, size_t smem, int threads, int ntiles, cudaStream_t st, const char* what, int* grid_out) {
+    static thread_local const void* configured[32];
+    static thread_local int blocks_per_sm[32];
+    static thread_local int nconf = 0;
+    int occ = 0;
+    for (int i = 0; i < nconf; ++i)
+        if (configured[i] == reinterpret_cast<const void*>(kern)) occ = blocks_per_sm[i];
+    if (!occ) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            set_error("%s: cannot configure kernel (%zu bytes of shared memory): %s", what, smem, cudaGetErrorString(e));
+            return DBL_E_CUDA;
+        }
+        if (nconf < 32) configured[nconf] = reinterpret_cast<const void*>(kern), blocks_per_sm[nconf] = occ, ++nconf;
+    }
+    const int cap = sm_count() * occ;
+    *grid_out = ntiles < cap ? ntiles : cap;
+    return DBL_OK;
+}
+
+template <int C, int TH, int TW, int NWARPS, int MB>
+static int launch_bottleneck(const dbl_tensor* x, const void* w1p, const float* b1, const void* w2p, const float* b2, int add,
+                             const dbl_tensor* y, cudaStream_t st) {
+    using K = BnCfg<C, TH, TW>;
+    BnParams p;
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x->data), p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
+    p.w1 = reinterpret_cast<const uint2*>(w1p), p.w2 = reinterpret_cast<const uint2*>(w2p), p.b1 = b1, p.b2 = b2;
+    p.n = x->n, p.h = x->h, p.w = x->w, p.xpitch = x->pitch, p.ypitch = y->pitch, p.add = add;
+    p.tiles_x = cdiv(x->w, TW), p.tiles_y = cdiv(x->h, TH), p.ntiles = x->n * p.tiles_x * p.tiles_y;
+    auto kern = bottleneck_mma_kernel<C, TH, TW, NWARPS, MB>;
+    int grid = 0;
+    const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_bottleneck3x3", &grid);
+    if (rc) return rc;
+    kern<<<grid, NWARPS * 32, K::SMEM, st>>>(p);
+    count_launch();
+    return check_launch("dbl_bottleneck3x3");
+}
+
+template <int CIN, int COUT, int S, int TH, int TW, int NWARPS, int MB>
+static int launch_conv_mma(const dbl_tensor* x, const void* wp, const float* b, const dbl_tensor* r, const dbl_tensor* y, int act, int epi,
+                           cudaStream_t st) {
+    using K = CmCfg<CIN, COUT, S, TH, TW>;
+    CmParams p;
+    p.x = reinterpret_cast<const __nv_bfloat16*>(x->data), p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
+    p.r = r ? reinterpret_cast<const __nv_bfloat16*>(r->data) : nullptr;
+    p.w = reinterpret_cast<const uint2*>(wp), p.b = b;
+    p.n = x->n, p.h = x->h, p.wd = x->w, p.ho = y->h, p.wo = y->w, p.xpitch = x->pitch, p.ypitch = y->pitch, p.rpitch = r ? r->pitch : 0;
+    p.act = act, p.epi = r ? epi : DBL_EPI_NONE;
+    p.tiles_x = cdiv(y->w, TW), p.tiles_y = cdiv(y->h, TH), p.ntiles = x->n * p.tiles_x * p.tiles_y;
+    auto kern = conv3x3_mma_kernel<CIN, COUT, S, TH, TW, NWARPS, MB>;
+    int grid = 0;
+    const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_conv3x3_mma", &grid);
+    if (rc) return rc;
+    kern<<<grid, NWARPS * 32, K::SMEM, st>>>(p);
+    count_launch();
+    return check_launch("dbl_conv3x3_mma");
+}
+
+template <int C0, int C1, typename TIN>
+static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0, const float* b0, const void* w1p, const float* b1,
+                            const dbl_tensor* y, float scale, cudaStream_t st) {
+    constexpr int TH = 16, TW = 32, NWARPS = 8;
+    using K = StemCfg<C0, C1, TH, TW>;
+    StemParams p;
+    p.x = x, p.w0 = w0, p.b0 = b0, p.w1 = reinterpret_cast<const uint2*>(w1p), p.b1 = b1;
+    p.y = reinterpret_cast<__nv_bfloat16*>(y->data);
+    p.n = n, p.h = h, p.w = w, p.ho = y->h, p.wo = y->w, p.ypitch = y->pitch, p.in_scale = scale;
+    p.tiles_x = cdiv(y->w, TW), p.tiles_y = cdiv(y->h, TH);
+    auto kern = stem_pair_kernel<C0, C1, TH, TW, NWARPS, TIN>;
+    static thread_local bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("dbl_stem_pair: cannot opt in to %d bytes of shared memory: %s", (int)K::SMEM, cudaGetErrorString(e));
+            return DBL_E_CUDA;
+        }
+        configured = true;
+    }
+    DBL_REQUIRE(n <= 65535 && p.tiles_y <= 65535, DBL_E_UNSUPPORTED, "dbl_stem_pair: grid too large");
+    kern<<<dim3(p.tiles_x, p.tiles_y, n), NWARPS * 32, K::SMEM, st>>>(p);
+    count_launch();
+    return check_launch("dbl_stem_pair");
+}
+
+}  // namespace dbl
+
+using namespace dbl;
+
+extern "C" size_t dbl_mma_packed_bytes(int cout, int cin, int taps) {
+    if (cout <= 0 || cout % 8 || (cin != 8 && (cin <= 0 || cin % 16)) || taps <= 0) return 0;
+    return (size_t)mma_ksteps(cin, taps) * (cout / 8) * 256;
+}
+
+extern "C" int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, void* packed, dbl_stream_t stream) {
+    DBL_REQUIRE(w && packed, DBL_E_ARG, "dbl_mma_pack_weights: null pointer");
+    DBL_REQUIRE(dbl_mma_packed_bytes(cout, cin, taps) > 0, DBL_E_UNSUPPORTED, "dbl_mma_pack_weights: cout %d (need %%8), cin %d (need 8 or %%16)", cout, cin);
+    DBL_REQUIRE((reinterpret_cast<uintptr_t>(w) & 3) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0, DBL_E_ARG,
+                "dbl_mma_pack_weights: misaligned pointer");
+    const int total = mma_ksteps(cin, taps) * (cout / 8) * 32;
+    mma_pack_kernel<<<cdiv(total, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(w), cout, cin, taps,
+                                                                      reinterpret_cast<uint2*>(packed));
+    count_launch();
+    return check_launch("dbl_mma_pack_weights");
+}
+
+extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                                 int shortcut, const dbl_tensor* y, dbl_stream_t stream) {
+    DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w1_packed && w2_packed, DBL_E_ARG, "dbl_bottleneck3x3: null/invalid argument");
+    DBL_REQUIRE(vec8_ok(x) && vec8_ok(y) && same_shape(x, y), DBL_E_ARG, "dbl_bottleneck3x3: x and y must be bf16 NHWC of equal shape, 16-byte aligned");
+    DBL_REQUIRE(x->data != y->data, DBL_E_ARG, "dbl_bottleneck3x3: in-place operation is not supported (tiles read their neighbours' halo)");
+    DBL_REQUIRE(((reinterpret_cast<uintptr_t>(w1_packed) | reinterpret_cast<uintptr_t>(w2_packed)) & 15) == 0, DBL_E_ARG,
+                "dbl_bottleneck3x3: packed weights must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    switch (x->c) {
+        case 16: return launch_bottleneck<16, 16, 32, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 32: return launch_bottleneck<32, 16, 32, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 64: return launch_bottleneck<64, 8, 32, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        default: break;
+    }
+    set_error("dbl_bottleneck3x3: %d channels not in {16,32,64}", x->c);
+    return DBL_E_UNSUPPORTED;
+}
+
+extern "C" int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
+                               int stride, int act, int epi, dbl_stream_t stream) {
+    DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w_packed, DBL_E_ARG, "dbl_conv3x3_mma: null/invalid argument");
+    DBL_REQUIRE(vec8_ok(x) && vec8_ok(y), DBL_E_ARG, "dbl_conv3x3_mma: x and y must be bf16 NHWC, 16-byte aligned");
+    DBL_REQUIRE(stride == 1 || stride == 2, DBL_E_ARG, "dbl_conv3x3_mma: stride %d", stride);
+    DBL_REQUIRE(act == DBL_ACT_NONE || act == DBL_ACT_SILU, DBL_E_UNSUPPORTED, "dbl_conv3x3_mma: activation %d", act);
+    const int ho = (x->h - 1) / stride + 1, wo = (x->w - 1) / stride + 1;
+    DBL_REQUIRE(y->n == x->n && y->h == ho && y->w == wo, DBL_E_ARG, "dbl_conv3x3_mma: output shape mismatch");
+    if (epi != DBL_EPI_NONE) DBL_REQUIRE(valid_tensor(r) && same_shape(r, y) && vec8_ok(r), DBL_E_ARG, "dbl_conv3x3_mma: residual mismatch");
+    DBL_REQUIRE(x->data != y->data, DBL_E_ARG, "dbl_conv3x3_mma: in-place operation is not supported");
+    cudaStream_t st = as_stream(stream);
+    const dbl_tensor* rr = epi != DBL_EPI_NONE ? r : nullptr;
+#define DBL_CM(CI, CO, S, TH) \
+    if (x->c == CI && y->c == CO && stride == S) return launch_conv_mma<CI, CO, S, TH, 32, 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
+    DBL_CM(8, 16, 2, 8);
+    DBL_CM(16, 32, 2, 8);
+    DBL_CM(32, 64, 2, 8);
+    DBL_CM(16, 8, 1, 16);
+    DBL_CM(8, 16, 1, 16);
+    DBL_CM(32, 16, 1, 16);
+    DBL_CM(16, 32, 1, 16);
+    DBL_CM(64, 32, 1, 8);
+    DBL_CM(32, 64, 1, 8);
+#undef DBL_CM
+    set_error("dbl_conv3x3_mma: no instantiation for cin %d cout %d stride %d", x->c, y->c, stride);
+    return DBL_E_UNSUPPORTED;
+}
+
+extern "C" int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int w, const float* w0, const float* b0, int c0,
+                             const void* w1_packed, const float* b1, const dbl_tensor* y, dbl_stream_t stream) {
+    DBL_REQUIRE(x_nchw && w0 && w1_packed && valid_tensor(y), DBL_E_ARG, "dbl_stem_pair: null/invalid argument");
+    DBL_REQUIRE(h % 2 == 0 && w % 2 == 0 && y->n == n && y->h == h / 2 && y->w == w / 2, DBL_E_ARG, "dbl_stem_pair: output shape mismatch");
+    DBL_REQUIRE(vec8_ok(y), DBL_E_ARG, "dbl_stem_pair: y must be bf16 NHWC, 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const float scale = x_is_u8 ? 1.0f / 255.0f : 1.0f;
+#define DBL_SP(A, B)                                                                                             \
+    if (c0 == A && y->c == B)                                                                                    \
+        return x_is_u8 ? launch_stem_pair<A, B, uint8_t>(x_nchw, n, h, w, w0, b0, w1_packed, b1, y, scale, st) \
+                       : launch_stem_pair<A, B, float>(x_nchw, n, h, w, w0, b0, w1_packed, b1, y, scale, st)
+    DBL_SP(8, 16);
+    DBL_SP(16, 32);
+#undef DBL_SP
+    set_error("dbl_stem_pair: channels (%d, %d) not in {(8,16), (16,32)}", c0, y->c);
+    return DBL_E_UNSUPPORTED;
+}

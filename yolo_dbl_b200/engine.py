@@ -63,13 +63,17 @@ def _fold(w: torch.Tensor, sd, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
 class DBLEngine:
     def __init__(self, spec: GraphSpec, state_dict: Dict[str, torch.Tensor], batch: int, height: int, width: int,
                  device: torch.device | str = "cuda", conv_impl: int = L.IMPL_AUTO, use_graph: bool = True,
-                 keep_layers: bool = False):
+                 keep_layers: bool = False, fuse_thin: Optional[bool] = None):
         self.lib = L.require_device()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(height), int(width)
         if self.H % 32 or self.W % 32:
             raise ValueError("input height/width must be multiples of 32 (reference data/loaders.py:516-584)")
         self.dev = torch.device(device)
         self.conv_impl = conv_impl
+        # warp-MMA kernels for the thin high-resolution layers (fused stem pair, fused Bottleneck, thin stride-2 convs);
+        # off when a specific conv implementation is forced or every top-level layer output must exist (parity tests)
+        self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
+        self.fuse_stem = self.fuse_thin and not keep_layers
         self.use_graph = use_graph
         self.sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[object] = []        # weights, ctypes structs, scratch: everything launches point at
@@ -128,6 +132,32 @@ class DBLEngine:
         tc = self.conv_impl != L.IMPL_DIRECT and x.c % 16 == 0 and k in (1, 3)
         self._emit(self.lib.dbl_conv2d, args, what, "conv_tc" if tc else "conv_direct", 2.0 * npix * y.c * x.c * k * k, nbytes)
 
+    def _pack_mma(self, w: torch.Tensor) -> torch.Tensor:
+        """[Cout,Cin,3,3] f32 -> device buffer in MMA B-fragment order (dbl_mma_pack_weights)"""
+        cout, cin, kh, kw = w.shape
+        wd = self._pack_w(w)
+        nbytes = self.lib.dbl_mma_packed_bytes(cout, cin, kh * kw)
+        if not nbytes:
+            raise L.DblError(f"no warp-MMA packing for cout={cout} cin={cin}")
+        out = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.dev)
+        L.check(self.lib.dbl_mma_pack_weights(L.ptr(wd), cout, cin, kh * kw, L.ptr(out), L.current_stream()), "dbl_mma_pack_weights")
+        torch.cuda.synchronize(self.dev)
+        self._keep.append(out)
+        return out
+
+    THIN_S2 = {(8, 16), (16, 32), (32, 64)}
+
+    def _conv_bn_thin(self, x: Act, p: str, y: Act, s: int) -> bool:
+        """3x3 Conv module on the warp-MMA kernel when an instantiation exists; False -> caller uses dbl_conv2d"""
+        w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
+        if not (self.fuse_thin and w.shape[-1] == 3 and s == 2 and (x.c, y.c) in self.THIN_S2 and x.buf.data_ptr() != y.buf.data_ptr()):
+            return False
+        wp, bd = self._pack_mma(w), self._dev(b, torch.float32)
+        npix = self.B * y.h * y.w
+        self._emit(self.lib.dbl_conv3x3_mma, (C.byref(x.desc), L.ptr(wp), L.ptr(bd), None, C.byref(y.desc), s, L.ACT_SILU, L.EPI_NONE), p,
+                   "conv_mma", 2.0 * npix * y.c * x.c * 9, 2 * self.B * x.h * x.w * x.c + 2 * npix * y.c + 2 * w.numel() + 4 * y.c)
+        return True
+
     def _conv_bn(self, x: Act, p: str, y: Act, s: int = 1, act: int = L.ACT_SILU, epi=L.EPI_NONE, r=None):
         """Conv module: conv(bias=False)+BN+SiLU (nn/modules/conv.py:39-63)"""
         w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
@@ -163,9 +193,19 @@ class DBLEngine:
     def _lower_bottleneck(self, x: Act, p: str, y: Act, shortcut: bool):
         """Bottleneck.forward (block.py:344-357)"""
         c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
+        add = shortcut and x.c == y.c
+        if self.fuse_thin and add and x.c in (16, 32, 64) and c_ * 2 == x.c and x.buf.data_ptr() != y.buf.data_ptr() \
+                and self.sd[p + ".cv1.conv.weight"].shape[-1] == 3 and self.sd[p + ".cv2.conv.weight"].shape[-1] == 3:
+            # cv1 -> cv2 -> +x in one kernel, hidden tensor in shared memory (csrc/conv_mma.cu)
+            w1, b1 = _fold(self.sd[p + ".cv1.conv.weight"], self.sd, p + ".cv1.bn")
+            w2, b2 = _fold(self.sd[p + ".cv2.conv.weight"], self.sd, p + ".cv2.bn")
+            npix = self.B * y.h * y.w
+            self._emit(self.lib.dbl_bottleneck3x3, (C.byref(x.desc), L.ptr(self._pack_mma(w1)), L.ptr(self._dev(b1, torch.float32)),
+                                                    L.ptr(self._pack_mma(w2)), L.ptr(self._dev(b2, torch.float32)), 1, C.byref(y.desc)),
+                       p, "bottleneck_mma", 2.0 * npix * 9 * 2 * x.c * c_, 2 * npix * (x.c + y.c) + 2 * (w1.numel() + w2.numel()) + 4 * (c_ + y.c))
+            return
         t = self._alloc(x.h, x.w, c_)
         self._conv_bn(x, p + ".cv1", t)
-        add = shortcut and x.c == y.c
         self._conv_bn(t, p + ".cv2", y, epi=L.EPI_ADD if add else L.EPI_NONE, r=x if add else None)
 
     def _lower_dsbottleneck_inplace(self, x: Act, p: str):
@@ -284,6 +324,34 @@ class DBLEngine:
                 self._conv_bn(d, q + ".1", cur)
             self._conv_bias(cur, f"{p}.cv3.{i}.2", hd.slice(64, nc))
 
+    # ------------------------------------------------------------------------------------------------ stem
+    def _stem_pair_ok(self) -> bool:
+        """layers 0 and 1 = Conv(3->c0, k3, s1) then Conv(c0->c1, k3, s2) with (c0,c1) the fused kernel is built for,
+        and nobody else reads layer 0"""
+        if not self.fuse_stem or len(self.spec.layers) < 3:
+            return False
+        l0, l1 = self.spec.layers[0], self.spec.layers[1]
+        if not (l0.kind == "Conv" and l0.k == 3 and l0.s == 1 and l1.kind == "Conv" and l1.k == 3 and l1.s == 2):
+            return False
+        if (l0.c2, l1.c2) not in ((8, 16), (16, 32)) or list(l1.src) not in ([-1], [0]):
+            return False
+        return not any(0 in [j for j in Lx.src if j >= 0] for Lx in self.spec.layers[2:])
+
+    def _lower_stem_pair(self, y: Act):
+        """Conv(3->c0,s1) + Conv(c0->c1,s2) + the input cast/scale of BasePredictor.preprocess in one kernel"""
+        sd = self.sd
+        w0, b0 = _fold(sd["model.0.conv.weight"], sd, "model.0.bn")
+        w1, b1 = _fold(sd["model.1.conv.weight"], sd, "model.1.bn")
+        w0d, b0d, b1d = self._dev(w0, torch.float32), self._dev(b0, torch.float32), self._dev(b1, torch.float32)
+        w1p = self._pack_mma(w1)
+        c0 = w0.shape[0]
+        npix0, npix1 = self.B * self.H * self.W, self.B * y.h * y.w
+        tail = (self.B, self.H, self.W, L.ptr(w0d), L.ptr(b0d), c0, L.ptr(w1p), L.ptr(b1d), C.byref(y.desc))
+        self._emit(self.lib.dbl_stem_pair, (self.x_in.data_ptr(), 0) + tail, "model.0+1.stem_pair", "stem_pair",
+                   2.0 * 27 * c0 * npix0 + 2.0 * 9 * c0 * y.c * npix1, self.x_in.numel() * 4 + 2 * npix1 * y.c)
+        self._stem_u8 = (self.x_in_u8.data_ptr(), 1) + tail
+        self._stem_fn_u8 = self.lib.dbl_stem_pair
+
     # ------------------------------------------------------------------------------------------------ graph
     def _build(self):
         spec, sd = self.spec, self.sd
@@ -322,8 +390,13 @@ class DBLEngine:
                 outs.append(None)
                 self.layer_ops[-1] = (self.layer_ops[-1][0], len(self.ops))
                 continue
+            if Lx.i == 0 and self._stem_pair_ok():
+                outs.append(None)  # layer 0's output never exists: it is consumed inside the fused stem kernel
+                continue
             y = out_act(Lx)
-            if Lx.i == 0:
+            if Lx.i == 1 and outs[0] is None:
+                self._lower_stem_pair(y)
+            elif Lx.i == 0:
                 if not (Lx.kind == "Conv" and Lx.k == 3):
                     raise NotImplementedError("layer 0 must be a 3x3 Conv")
                 w, b = _fold(sd[p + ".conv.weight"], sd, p + ".bn")
@@ -331,8 +404,10 @@ class DBLEngine:
                 self._emit(self.lib.dbl_stem_conv, (self.x_in.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s),
                            p + ".stem", "stem_conv", 2.0 * 27 * y.c * self.B * y.h * y.w)
                 self._stem_u8 = (self.x_in_u8.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s)
+                self._stem_fn_u8 = self.lib.dbl_stem_conv_u8
             elif Lx.kind == "Conv":
-                self._conv_bn(ins[0], p, y, s=Lx.s)
+                if not self._conv_bn_thin(ins[0], p, y, Lx.s):
+                    self._conv_bn(ins[0], p, y, s=Lx.s)
             elif Lx.kind == "DSConv":
                 self._dsconv(ins[0], p, y, s=Lx.s)
             elif Lx.kind == "Bottleneck":
@@ -386,7 +461,7 @@ class DBLEngine:
     def _launch_forward(self, stream: int):
         for i, (fn, args, what) in enumerate(self.ops):
             if i == 0 and self._u8:  # uint8 input: same stem, the /255 happens in its loader
-                fn, args = self.lib.dbl_stem_conv_u8, self._stem_u8
+                fn, args = self._stem_fn_u8, self._stem_u8
             rc = fn(*args, stream)
             if rc:
                 raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
