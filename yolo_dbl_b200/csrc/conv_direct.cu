@@ -1,6 +1,6 @@
 // CUDA-core convolutions: the fp32 NCHW -> bf16 NHWC stem, a generic direct convolution (used where the tensor-core
 // implicit GEMM does not apply: Cin % 16 != 0, dilation, forced by the caller) and the depthwise convolution.
-#include "dbl_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace dbl {
 int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int k,
@@ -291,6 +291,142 @@ __global__ void __launch_bounds__(128) dwconv_strip_kernel(const __nv_bfloat16* 
     }
 }
 
+
+// depthwise conv, shared-memory tiled.  One CTA = one (image, spatial tile, block of G 8-channel groups).  The input tile
+// (+halo, zero-filled outside the image = the convolution's padding) is copied once with 16-byte cp.async in its natural
+// [row][col][channel-chunk] order and the filter block sits next to it as f32 [tap][G*8].  A thread owns one output
+// column x one channel group and R consecutive output rows: every 16-byte input chunk it reads feeds up to R outputs, the
+// K filter taps of the current filter column live in registers.  Lanes run over (channel group, column), so a warp's
+// shared-memory reads are contiguous 16-byte chunks (conflict free) and its global stores are full 128-byte lines.
+template <int K, int S, int D, int R>
+__global__ void __launch_bounds__(512) dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int h, int wd,
+                                                          int c, int xpitch, int ho, int wo, int ypitch, int act, int G, int tw, int ty,
+                                                          int tiles_x) {
+    extern __shared__ __align__(16) uint8_t dw_smem[];
+    constexpr int PAD = D * (K - 1) / 2;
+    constexpr int ROWS_T = (R - 1) * S + (K - 1) * D + 1;  // input rows one thread walks
+    const int th = ty * R;
+    const int ir = (th - 1) * S + (K - 1) * D + 1, ic = (tw - 1) * S + (K - 1) * D + 1;
+    const int img = blockIdx.z, cb = blockIdx.y;
+    const int oy0 = (blockIdx.x / tiles_x) * th, ox0 = (blockIdx.x % tiles_x) * tw;
+    const int c0 = cb * G * 8;
+    const int g_here = min(G, c / 8 - cb * G);  // channel groups of this block (the last block may be short)
+    float* sw = reinterpret_cast<float*>(dw_smem);                      // [K*K][G*8]
+    const uint32_t sx = smem_u32(dw_smem) + (uint32_t)(K * K * G * 32);  // [ir][ic][G] x 16 bytes
+    const int nt = blockDim.x;
+    for (int i = threadIdx.x; i < K * K * G * 8; i += nt) {
+        const int tap = i / (G * 8), cc = i - tap * (G * 8);
+        sw[i] = (cc < g_here * 8) ? w[(size_t)tap * c + c0 + cc] : 0.f;
+    }
+    {
+        const __nv_bfloat16* ximg = x + (size_t)img * h * wd * xpitch + c0;
+        const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+        const int items = ir * ic * G;
+        for (int i = threadIdx.x; i < items; i += nt) {
+            const int g = i % G, pix = i / G;
+            const int ly = pix / ic, lx = pix - ly * ic;
+            const int gy = iy0 + ly, gx = ix0 + lx;
+            const bool ok = g < g_here && gy >= 0 && gy < h && gx >= 0 && gx < wd;
+            cp_async16(sx + (uint32_t)i * 16, ok ? ximg + ((size_t)gy * wd + gx) * xpitch + g * 8 : x, ok);
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int g = threadIdx.x % G, xi = (threadIdx.x / G) % tw, ys = threadIdx.x / (G * tw);
+    if (ys >= ty || g >= g_here) return;
+    const int ox = ox0 + xi, oyb = oy0 + ys * R;
+    if (ox >= wo || oyb >= ho) return;
+    float acc[R][8];
+    {
+        float b8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4));
+            b8[0] = b0.x, b8[1] = b0.y, b8[2] = b0.z, b8[3] = b0.w, b8[4] = b1.x, b8[5] = b1.y, b8[6] = b1.z, b8[7] = b1.w;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = b8[i];
+    }
+    const uint32_t xbase = sx + (uint32_t)(((ys * R * S) * ic + xi * S) * G + g) * 16;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+        float wk[K][8];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * G * 8 + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * G * 8 + g * 8 + 4);
+            wk[ky][0] = w0.x, wk[ky][1] = w0.y, wk[ky][2] = w0.z, wk[ky][3] = w0.w;
+            wk[ky][4] = w1.x, wk[ky][5] = w1.y, wk[ky][6] = w1.z, wk[ky][7] = w1.w;
+        }
+#pragma unroll
+        for (int iy = 0; iy < ROWS_T; ++iy) {
+            bool used = false;  // compile-time: does any of the R outputs read input row iy?
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int d = iy - r * S;
+                if (d >= 0 && d % D == 0 && d / D < K) used = true;
+            }
+            if (!used) continue;
+            bf16x8 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.u.x), "=r"(v.u.y), "=r"(v.u.z), "=r"(v.u.w)
+                         : "r"(xbase + (uint32_t)((iy * ic + kx * D) * G) * 16));
+            float xv[8];
+            unpack8(v, xv);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int d = iy - r * S;
+                if (d >= 0 && d % D == 0 && d / D < K) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(xv[i], wk[d / D][i], acc[r][i]);
+                }
+            }
+        }
+    }
+    __nv_bfloat16* yp = y + (((size_t)img * ho + oyb) * wo + ox) * ypitch + c0 + g * 8;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (oyb + r < ho) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[r][i] = act == DBL_ACT_SILU ? silu_fast(acc[r][i]) : apply_act(acc[r][i], act);
+            stg8(yp + (size_t)r * wo * ypitch, pack8(acc[r]));
+        }
+    }
+}
+
+// host-side tile choice for dwconv_tile_kernel; returns false when no tile fits
+static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int* G_, int* tw_, int* ty_, size_t* smem_) {
+    const int cg = c / 8;
+    long long best = -1;
+    for (int G = 1; G <= 8; G <<= 1) {
+        if (G > cg && G != 1) {
+            if (G / 2 >= cg) continue;
+        }
+        for (int tw = 4; tw <= 40; ++tw) {
+            if (tw > wo && tw != 4) break;
+            for (int ty = 1; ty <= 8; ++ty) {
+                const int threads = G * tw * ty;
+                if (threads > 512 || threads < 64) continue;
+                const int th = ty * R;
+                if (th > ho + R - 1 && ty > 1) continue;
+                const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
+                const size_t smem = (size_t)k * k * G * 32 + (size_t)ir * ic * G * 16;
+                if (smem > 100 * 1024) continue;
+                const long long tiles = (long long)cdiv(wo, tw) * cdiv(ho, th) * cdiv(cg, G);
+                // cost model: shared-memory fill (halo included) + padded compute, per CTA a fixed cost
+                const long long fill = (long long)ir * ic * G;
+                const long long comp = (long long)((threads + 31) / 32 * 32) * R * k * k / 4;
+                const long long cost = tiles * (fill + comp + 1500);
+                if (best < 0 || cost < best) best = cost, *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = smem;
+            }
+        }
+    }
+    return best >= 0;
+}
+
 }  // namespace dbl
 
 using namespace dbl;
@@ -380,6 +516,37 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
     auto* xp = reinterpret_cast<const __nv_bfloat16*>(x->data);
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
     cudaStream_t st = as_stream(stream);
+    {
+        // shared-memory tiled kernel for every (k, stride, dilation) the graph uses
+        constexpr int R = 4;
+        int G = 0, tw = 0, ty = 0;
+        size_t smem = 0;
+        void (*kern)(const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, int, int, int, int, int, int, int, int, int, int, int,
+                     int) = nullptr;
+        if (k == 3 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<3, 1, 1, R>;
+        else if (k == 3 && stride == 2 && dil == 1) kern = dwconv_tile_kernel<3, 2, 1, R>;
+        else if (k == 5 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<5, 1, 1, R>;
+        else if (k == 7 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<7, 1, 1, R>;
+        else if (k == 7 && stride == 1 && dil == 3) kern = dwconv_tile_kernel<7, 1, 3, R>;
+        if (kern && x->n <= 65535 && dw_pick_tile(k, stride, dil, R, x->c, ho, wo, &G, &tw, &ty, &smem)) {
+            static thread_local const void* configured[8];
+            static thread_local int nconf = 0;
+            bool have = false;
+            for (int i = 0; i < nconf; ++i) have = have || configured[i] == reinterpret_cast<const void*>(kern);
+            if (!have) {
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
+                    set_error("dbl_dwconv2d: cannot opt in to 100 KB of shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+                    return DBL_E_CUDA;
+                }
+                if (nconf < 8) configured[nconf++] = reinterpret_cast<const void*>(kern);
+            }
+            const int tiles_x = cdiv(wo, tw), tiles_y = cdiv(ho, ty * R);
+            dim3 grid(tiles_x * tiles_y, cdiv(x->c / 8, G), x->n);
+            kern<<<grid, G * tw * ty, smem, st>>>(xp, w, bias, yp, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act, G, tw, ty, tiles_x);
+            count_launch();
+            return check_launch("dbl_dwconv2d(tile)");
+        }
+    }
     if (dil == 1 && (stride == 1 || stride == 2) && (size_t)k * k * x->c * 4 <= 48 * 1024) {
         // register-blocked strips along W
         const int R = 4;

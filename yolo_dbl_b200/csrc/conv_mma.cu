@@ -507,7 +507,7 @@ struct StemCfg {
     static constexpr int M0 = round16(R0 * PI) / 16;         // layer-0 m-blocks (pitch PI -> tap shift = address offset)
     static constexpr int IN_PX = M0 * 16 + 2 * PI + 8;
     static constexpr int IN_BYTES = ((IN_PX > RI * PI ? IN_PX : RI * PI) * 8 + 127) / 128 * 128;
-    static constexpr int WP = TW + 1;                        // layer-0 parity sub-tile pitch
+    static constexpr int WP = PI / 2;                        // layer-0 parity sub-tile pitch (junk columns keep their own slots)
     static constexpr int M1 = round16(TH * WP) / 16;
     static constexpr int SUB_NEED = M1 * 16 + WP + 2;
     static constexpr int SUB_PX = SUB_NEED > (TH + 1) * WP ? SUB_NEED : (TH + 1) * WP;
@@ -735,7 +735,7 @@ static int launch_conv_mma(const dbl_tensor* x, const void* wp, const float* b, 
 template <int C0, int C1, typename TIN>
 static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0, const float* b0, const void* w1p, const float* b1,
                             const dbl_tensor* y, float scale, cudaStream_t st) {
-    constexpr int TH = 16, TW = 32, NWARPS = 8;
+    constexpr int TH = 16, TW = 30, NWARPS = 8;  // input row pitch 64 pixels, layer-0 sub-tile pitch 32: index math = shifts
     using K = StemCfg<C0, C1, TH, TW>;
     StemParams p;
     p.x = x, p.w0 = w0, p.b0 = b0, p.w1 = reinterpret_cast<const uint2*>(w1p), p.b1 = b1;
@@ -789,9 +789,11 @@ extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, con
                 "dbl_bottleneck3x3: packed weights must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     switch (x->c) {
-        case 16: return launch_bottleneck<16, 16, 32, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-        case 32: return launch_bottleneck<32, 16, 32, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-        case 64: return launch_bottleneck<64, 8, 32, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        // tile width 28 -> row pitch 32: every 16-row GEMM block is half a tile row (index math = shifts) and the
+        // m-block counts of both phases divide evenly over the warps
+        case 16: return launch_bottleneck<16, 30, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 32: return launch_bottleneck<32, 14, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 64: return launch_bottleneck<64, 10, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
         default: break;
     }
     set_error("dbl_bottleneck3x3: %d channels not in {16,32,64}", x->c);
@@ -810,8 +812,8 @@ extern "C" int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const 
     DBL_REQUIRE(x->data != y->data, DBL_E_ARG, "dbl_conv3x3_mma: in-place operation is not supported");
     cudaStream_t st = as_stream(stream);
     const dbl_tensor* rr = epi != DBL_EPI_NONE ? r : nullptr;
-#define DBL_CM(CI, CO, S, TH) \
-    if (x->c == CI && y->c == CO && stride == S) return launch_conv_mma<CI, CO, S, TH, 32, 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
+#define DBL_CM(CI, CO, S, TH) /* tile width 30 (stride 1) / 31 (stride 2) -> (sub-)tile row pitch 32 */ \
+    if (x->c == CI && y->c == CO && stride == S) return launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
     DBL_CM(8, 16, 2, 8);
     DBL_CM(16, 32, 2, 8);
     DBL_CM(32, 64, 2, 8);
