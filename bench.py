@@ -221,9 +221,14 @@ def main():
     out_cnt = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
     x_u8 = [(x_host * 255.0).round().to(torch.uint8).pin_memory() for _ in range(2)]
 
+    from yolo_dbl_b200.parallel import gather_detections
+
     def e2e_run(k, src):
         n = 0
         for rows, counts in model.detect_stream((src[i & 1] for i in range(k)), **NMS):
+            if world > 1:  # the path's one collective: final gather of the fixed-capacity detections (NCCL all-gather)
+                g_rows, g_cnt = gather_detections(rows, counts, args.batch * world)
+                rows, counts = g_rows[rank * args.batch:(rank + 1) * args.batch], g_cnt[rank * args.batch:(rank + 1) * args.batch]
             out_rows.copy_(rows, non_blocking=True)
             out_cnt.copy_(counts, non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the caller reads the result on the host every step

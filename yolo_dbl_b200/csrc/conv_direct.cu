@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128) dwconv_strip_kernel(const __nv_bfloat16* 
 // K filter taps of the current filter column live in registers.  Lanes run over (channel group, column), so a warp's
 // shared-memory reads are contiguous 16-byte chunks (conflict free) and its global stores are full 128-byte lines.
 template <int K, int S, int D, int R>
-__global__ void __launch_bounds__(512) dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int h, int wd,
                                                           int c, int xpitch, int ho, int wo, int ypitch, int act, int G, int tw, int ty,
                                                           int tiles_x) {
@@ -409,12 +409,12 @@ static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int*
             if (tw > wo && tw != 4) break;
             for (int ty = 1; ty <= 8; ++ty) {
                 const int threads = G * tw * ty;
-                if (threads > 512 || threads < 64) continue;
+                if (threads > 256 || threads < 64) continue;  // small CTAs: several per SM, so one CTA's fill overlaps another's math
                 const int th = ty * R;
                 if (th > ho + R - 1 && ty > 1) continue;
                 const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
                 const size_t smem = (size_t)k * k * G * 32 + (size_t)ir * ic * G * 16;
-                if (smem > 100 * 1024) continue;
+                if (smem > 64 * 1024) continue;
                 const long long tiles = (long long)cdiv(wo, tw) * cdiv(ho, th) * cdiv(cg, G);
                 // cost model: shared-memory fill (halo included) + padded compute, per CTA a fixed cost
                 const long long fill = (long long)ir * ic * G;
