@@ -63,7 +63,7 @@ def _fold(w: torch.Tensor, sd, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
 class DBLEngine:
     def __init__(self, spec: GraphSpec, state_dict: Dict[str, torch.Tensor], batch: int, height: int, width: int,
                  device: torch.device | str = "cuda", conv_impl: int = L.IMPL_AUTO, use_graph: bool = True,
-                 keep_layers: bool = False, fuse_thin: Optional[bool] = None):
+                 keep_layers: bool = False, fuse_thin: Optional[bool] = None, lanes: int = 8):
         self.lib = L.require_device()
         self.spec, self.B, self.H, self.W = spec, int(batch), int(height), int(width)
         if self.H % 32 or self.W % 32:
@@ -75,9 +75,13 @@ class DBLEngine:
         self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
         self.fuse_stem = self.fuse_thin and not keep_layers
         self.use_graph = use_graph
+        # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
+        # run on `lanes` streams: inside a captured CUDA graph they become parallel branches, so small kernels overlap
+        self.n_lanes = max(1, int(lanes)) if use_graph else 1
         self.sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[object] = []        # weights, ctypes structs, scratch: everything launches point at
         self.ops: List[Tuple[Callable, tuple, str]] = []
+        self.op_rw: List[Tuple[list, list]] = []
         self.op_meta: List[dict] = []
         self.kernels_per_step: Dict[tuple, int] = {}
         self.layer_out: List[Optional[Act]] = []
@@ -88,6 +92,7 @@ class DBLEngine:
             self.x_in_u8 = torch.zeros(self.B, 3, self.H, self.W, dtype=torch.uint8, device=self.dev)  # image sources (0..255)
             self._u8 = False
             self._build()
+            self._plan_lanes()
         if not keep_layers:
             self.sd = None
 
@@ -107,6 +112,14 @@ class DBLEngine:
         declared input and output tensor counted once, weights once; halo re-reads and scratch are not counted."""
         self._keep.append(args)
         self.ops.append((fn, args, what))
+        # memory regions of the tensor arguments, for the dependency analysis of _plan_lanes: by convention of the C ABI
+        # the LAST dbl_tensor argument is the output (dbl_gated_add: both tensors after the gate), the others are inputs
+        views = [(i, a._obj) for i, a in enumerate(args) if isinstance(getattr(a, "_obj", None), L.Tensor)]
+        n_out = 1
+        if fn is self.lib.dbl_gated_add:
+            n_out = len([1 for i, _ in views if i >= 3])
+        regs = [self._region(t) for _, t in views]
+        self.op_rw.append((regs[:len(regs) - n_out], regs[len(regs) - n_out:]))
         if not nbytes:  # bandwidth-bound glue: every tensor view in the argument list, once
             for a in args:
                 t = getattr(a, "_obj", None)
@@ -457,14 +470,102 @@ class DBLEngine:
         self.levels = lv
         self.y = torch.zeros(self.B, 4 + spec.nc, self.A, dtype=torch.float32, device=self.dev)
 
+    # ------------------------------------------------------------------------------------------------ lanes
+    @staticmethod
+    def _region(t: "L.Tensor"):
+        es = 2 if t.dtype == L.DBL_BF16 else 4
+        stride = t.pitch * es
+        return (t.data, t.data + ((t.n * t.h * t.w - 1) * t.pitch + t.c) * es, stride, t.c * es)
+
+    @staticmethod
+    def _overlap(a, b) -> bool:
+        if a[1] <= b[0] or b[1] <= a[0]:
+            return False
+        if a[2] != b[2]:
+            return True  # different pixel pitch over the same memory: be conservative
+        d = (b[0] - a[0]) % a[2]
+        return d < a[3] or d + b[3] > a[2]
+
+    def _plan_lanes(self):
+        """Dependency DAG of the launch list (RAW, WAW and WAR hazards on the channel-sliced buffers) and a greedy
+        assignment of every launch to one of `n_lanes` streams.  self.plan[i] = (lane, [ops whose completion event this
+        launch must wait for because they run on another lane])."""
+        n = len(self.ops)
+        deps: List[set] = [set() for _ in range(n)]
+        anc = [0] * n  # ancestor bitsets
+        for j in range(n):
+            rj, wj = self.op_rw[j]
+            for i in range(j - 1, -1, -1):
+                if (anc[j] >> i) & 1:
+                    continue  # already ordered through another dependency
+                ri, wi = self.op_rw[i]
+                if any(self._overlap(w, r) for w in wi for r in rj) or any(self._overlap(w, w2) for w in wi for w2 in wj) \
+                        or any(self._overlap(r, w) for r in ri for w in wj):
+                    deps[j].add(i)
+                    anc[j] |= anc[i] | (1 << i)
+        lane_tail = [-1] * self.n_lanes
+        self.plan: List[Tuple[int, List[int]]] = []
+        lane_of = [0] * n
+        for j in range(n):
+            lane = None
+            if self.n_lanes > 1:
+                for i in sorted(deps[j], reverse=True):  # continue the chain of the most recent predecessor if it is a tail
+                    if lane_tail[lane_of[i]] == i:
+                        lane = lane_of[i]
+                        break
+                if lane is None:  # a lane whose tail is an ancestor anyway (no false dependency), else the least recently used
+                    cands = [l for l in range(self.n_lanes) if lane_tail[l] < 0 or (anc[j] >> lane_tail[l]) & 1]
+                    lane = cands[0] if cands else min(range(self.n_lanes), key=lambda l: lane_tail[l])
+            else:
+                lane = 0
+            if j == 0:
+                lane = 0
+            lane_of[j] = lane
+            lane_tail[lane] = j
+            self.plan.append((lane, sorted(i for i in deps[j] if lane_of[i] != lane)))
+        self._signals = set(i for _, w in self.plan for i in w)  # launches that need a completion event
+        self._side_streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes - 1)]
+
     # ------------------------------------------------------------------------------------------------ execution
-    def _launch_forward(self, stream: int):
+    def _launch_forward(self, stream: int, lanes: bool = False):
+        if lanes and self.n_lanes > 1:
+            return self._launch_forward_lanes()
         for i, (fn, args, what) in enumerate(self.ops):
             if i == 0 and self._u8:  # uint8 input: same stem, the /255 happens in its loader
                 fn, args = self._stem_fn_u8, self._stem_u8
             rc = fn(*args, stream)
             if rc:
                 raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
+
+    def _launch_forward_lanes(self):
+        """Same launches, spread over the planned lanes (lane 0 = the current stream).  Cross-lane dependencies are CUDA
+        events; under stream capture they become edges of the graph.  All lanes are joined back before returning."""
+        main = torch.cuda.current_stream(self.dev)
+        streams = [main] + self._side_streams
+        started = [True] + [False] * (self.n_lanes - 1)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        done: Dict[int, torch.cuda.Event] = {}
+        for i, (fn, args, what) in enumerate(self.ops):
+            if i == 0 and self._u8:
+                fn, args = self._stem_fn_u8, self._stem_u8
+            lane, waits = self.plan[i]
+            st = streams[lane]
+            if not started[lane]:
+                st.wait_event(fork)
+                started[lane] = True
+            for d in waits:
+                st.wait_event(done[d])
+            rc = fn(*args, st.cuda_stream)
+            if rc:
+                raise L.DblError(f"{what}: code {rc}: {self.lib.dbl_last_error().decode()}")
+            if i in self._signals:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done[i] = ev
+        for lane in range(1, self.n_lanes):
+            if started[lane]:
+                main.wait_stream(streams[lane])
 
     def _launch_decode(self, stream: int):
         L.check(self.lib.dbl_detect_decode(C.byref(self.levels), self.y.data_ptr(), stream), "dbl_detect_decode")
@@ -516,7 +617,7 @@ class DBLEngine:
             s.wait_stream(torch.cuda.current_stream(self.dev))
             n0 = self.lib.dbl_launch_count()
             with torch.cuda.stream(s):  # warm-up outside capture: one-time attribute / descriptor setup happens here
-                self._launch_forward(s.cuda_stream)
+                self._launch_forward(s.cuda_stream, lanes=True)
                 if want_y:
                     self._launch_decode(s.cuda_stream)
                 if key is not None:
@@ -526,7 +627,7 @@ class DBLEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=s):
                 cs = L.current_stream()
-                self._launch_forward(cs)
+                self._launch_forward(cs, lanes=True)
                 if want_y:
                     self._launch_decode(cs)
                 if key is not None:
