@@ -49,6 +49,9 @@ const char* dbl_last_error(void);
 int dbl_version(void);
 /* 1 if the current CUDA device can run this library (compute capability 10.x), else 0. */
 int dbl_device_ok(void);
+/* Programmatic dependent launch (on by default): kernels are launched so that the prologue of kernel i+1 overlaps the
+ * tail of kernel i on the same stream / graph branch.  Returns the previous setting. */
+int dbl_set_pdl(int enabled);
 /* number of kernels this library has launched from the calling process (bench.py reports it as gpu_launches) */
 int64_t dbl_launch_count(void);
 

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "dbl_last_error": (C.c_char_p, []),
     "dbl_version": (C.c_int, []),
     "dbl_device_ok": (C.c_int, []),
+    "dbl_set_pdl": (C.c_int, [C.c_int]),
     "dbl_launch_count": (C.c_int64, []),
     "dbl_conv2d": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_stem_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
@@ -92,6 +93,8 @@ def load() -> C.CDLL:
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
+        if os.environ.get("DBL_PDL", "1") == "0":  # A/B switch for programmatic dependent launch
+            lib.dbl_set_pdl(0)
         _lib = lib
     return _lib
 

@@ -9,6 +9,7 @@ namespace dbl {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+int g_pdl_enabled = 1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -50,6 +51,12 @@ int dbl_device_ok(void) {
     }
     if (major != 10) dbl::set_error("libdbl_sm100 needs compute capability 10.x, found %d.x", major);
     return major == 10;
+}
+
+int dbl_set_pdl(int enabled) {
+    const int old = dbl::g_pdl_enabled;
+    dbl::g_pdl_enabled = enabled ? 1 : 0;
+    return old;
 }
 
 int64_t dbl_launch_count(void) { return dbl::g_launches.load(std::memory_order_relaxed); }

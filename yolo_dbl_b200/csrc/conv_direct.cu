@@ -1,5 +1,7 @@
 // CUDA-core convolutions: the fp32 NCHW -> bf16 NHWC stem, a generic direct convolution (used where the tensor-core
 // implicit GEMM does not apply: Cin % 16 != 0, dilation, forced by the caller) and the depthwise convolution.
+#include <cstdlib>
+
 #include "tc_ptx.cuh"
 
 namespace dbl {
@@ -22,6 +24,8 @@ template <int COUT, typename TIN>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const TIN* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                         int n, int h, int wd, int ho, int wo, int stride, int ypitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) float sw[27 * COUT];  // [ci][ky][kx][co]
     __shared__ float sb[COUT];
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) {
@@ -82,6 +86,8 @@ __global__ void __launch_bounds__(DC_THREADS) conv_direct_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
     const __nv_bfloat16* __restrict__ r, void* __restrict__ y, int n, int h, int wd, int cin, int xpitch, int ho, int wo,
     int cout, int ypitch, int ydtype, int rpitch, int k, int stride, int pad, int dil, int act, int epi, int cin_chunk) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float swt[];  // [k*k][cin_chunk][8]
     const int co0 = blockIdx.y * DC_CO;
     const long long total = (long long)n * ho * wo;
@@ -165,6 +171,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const __nv_bfloat16* __rest
                                                      const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n,
                                                      int h, int wd, int c, int xpitch, int ho, int wo, int ypitch,
                                                      int stride, int dil, int act) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const long long total = (long long)n * ho * wo * cg;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,6 +225,8 @@ template <int K, int S, int R>
 __global__ void __launch_bounds__(128) dwconv_strip_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int n,
                                                            int h, int wd, int c, int xpitch, int ho, int wo, int ypitch, int act) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sw[];  // [K*K][c]
     for (int i = threadIdx.x; i < K * K * c; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
@@ -304,6 +314,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
                                                           int c, int xpitch, int ho, int wo, int ypitch, int act, int G, int tw, int ty,
                                                           int tiles_x) {
     extern __shared__ __align__(16) uint8_t dw_smem[];
+    pdl_launch_dependents();
     constexpr int PAD = D * (K - 1) / 2;
     constexpr int ROWS_T = (R - 1) * S + (K - 1) * D + 1;  // input rows one thread walks
     const int th = ty * R;
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
         const int tap = i / (G * 8), cc = i - tap * (G * 8);
         sw[i] = (cc < g_here * 8) ? w[(size_t)tap * c + c0 + cc] : 0.f;
     }
+    pdl_wait();  // the filter block above is constant data; the activations are the previous kernel's output
     {
         const __nv_bfloat16* ximg = x + (size_t)img * h * wd * xpitch + c0;
         const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
@@ -351,7 +363,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
             for (int i = 0; i < 8; ++i) acc[r][i] = b8[i];
     }
     const uint32_t xbase = sx + (uint32_t)(((ys * R * S) * ic + xi * S) * G + g) * 16;
-#pragma unroll
+    // the filter-column loop stays ROLLED: fully unrolled this kernel is 65 KB of straight-line code that every warp runs
+    // exactly once, and ncu showed it stalled on instruction fetch for half of its cycles
+#pragma unroll 1
     for (int kx = 0; kx < K; ++kx) {
         float wk[K][8];
 #pragma unroll
@@ -391,40 +405,41 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
     for (int r = 0; r < R; ++r) {
         if (oyb + r < ho) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[r][i] = act == DBL_ACT_SILU ? silu_fast(acc[r][i]) : apply_act(acc[r][i], act);
+            for (int i = 0; i < 8; ++i) acc[r][i] = act == DBL_ACT_SILU ? silu_fast(acc[r][i]) : acc[r][i];
             stg8(yp + (size_t)r * wo * ypitch, pack8(acc[r]));
         }
     }
 }
 
-// host-side tile choice for dwconv_tile_kernel; returns false when no tile fits
+// host-side tile choice for dwconv_tile_kernel (measured with tools/dw_bench.py): two channel groups per CTA (32-byte
+// chunks = full sectors), rows as wide as the map (<= 40 columns), as many 4-row strips as fit 256 threads; widths and
+// strip counts are picked to minimise the padding of the last tile.  Returns false when no tile fits.
 static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int* G_, int* tw_, int* ty_, size_t* smem_) {
-    const int cg = c / 8;
-    long long best = -1;
-    for (int G = 1; G <= 8; G <<= 1) {
-        if (G > cg && G != 1) {
-            if (G / 2 >= cg) continue;
-        }
-        for (int tw = 4; tw <= 40; ++tw) {
-            if (tw > wo && tw != 4) break;
-            for (int ty = 1; ty <= 8; ++ty) {
-                const int threads = G * tw * ty;
-                if (threads > 256 || threads < 64) continue;  // small CTAs: several per SM, so one CTA's fill overlaps another's math
-                const int th = ty * R;
-                if (th > ho + R - 1 && ty > 1) continue;
-                const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
-                const size_t smem = (size_t)k * k * G * 32 + (size_t)ir * ic * G * 16;
-                if (smem > 64 * 1024) continue;
-                const long long tiles = (long long)cdiv(wo, tw) * cdiv(ho, th) * cdiv(cg, G);
-                // cost model: shared-memory fill (halo included) + padded compute, per CTA a fixed cost
-                const long long fill = (long long)ir * ic * G;
-                const long long comp = (long long)((threads + 31) / 32 * 32) * R * k * k / 4;
-                const long long cost = tiles * (fill + comp + 1500);
-                if (best < 0 || cost < best) best = cost, *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = smem;
-            }
+    const int cg = c / 8, G = cg >= 2 ? 2 : 1;
+    int tw = wo <= 40 ? wo : 40;
+    if (wo > 40) {
+        int best_pad = 1 << 30;
+        for (int t = 40; t >= 20; --t) {
+            const int pad = cdiv(wo, t) * t - wo;
+            if (pad < best_pad) best_pad = pad, tw = t;
         }
     }
-    return best >= 0;
+    if (tw < 4) tw = 4;
+    const int strips = cdiv(ho, R);
+    int ty = 0;
+    int best_pad = 1 << 30;
+    for (int t = 256 / (G * tw); t >= 1; --t) {
+        const int th = t * R;
+        const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
+        if ((size_t)k * k * G * 32 + (size_t)ir * ic * G * 16 > 64 * 1024) continue;
+        const int pad = cdiv(strips, t) * t - strips;
+        if (pad < best_pad) best_pad = pad, ty = t;
+    }
+    if (ty < 1) return false;
+    const int th = ty * R;
+    const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
+    *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = (size_t)k * k * G * 32 + (size_t)ir * ic * G * 16;
+    return true;
 }
 
 }  // namespace dbl
@@ -443,9 +458,9 @@ static int stem_launch(const TIN* x, int n, int h, int w_, const float* w, const
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
     cudaStream_t st = as_stream(stream);
     switch (y->c) {
-        case 8: stem_conv_kernel<8, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
-        case 16: stem_conv_kernel<16, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
-        case 32: stem_conv_kernel<32, TIN><<<grid, block, 0, st>>>(x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 8: launch_k(stem_conv_kernel<8, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 16: launch_k(stem_conv_kernel<16, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
+        case 32: launch_k(stem_conv_kernel<32, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
         default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_stem_conv: cout %d not in {8,16,32}", y->c);
     }
     count_launch();
@@ -493,7 +508,7 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
     const size_t smem = (size_t)k * k * chunk * DC_CO * sizeof(float);
     const long long total = (long long)x->n * ho * wo;
     dim3 grid((unsigned)((total + DC_THREADS - 1) / DC_THREADS), cdiv(y->c, DC_CO));
-    conv_direct_kernel<<<grid, DC_THREADS, smem, st>>>(
+    launch_k(conv_direct_kernel, grid, DC_THREADS, smem, st, 
         reinterpret_cast<const __nv_bfloat16*>(x->data), reinterpret_cast<const __nv_bfloat16*>(w), bias,
         epi ? reinterpret_cast<const __nv_bfloat16*>(r->data) : nullptr, y->data, x->n, x->h, x->w, x->c, x->pitch, ho, wo,
         y->c, y->pitch, y->dtype, epi ? r->pitch : 0, k, stride, pad, dil, act, epi, chunk);
@@ -528,7 +543,17 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
         else if (k == 5 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<5, 1, 1, R>;
         else if (k == 7 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<7, 1, 1, R>;
         else if (k == 7 && stride == 1 && dil == 3) kern = dwconv_tile_kernel<7, 1, 3, R>;
-        if (kern && x->n <= 65535 && dw_pick_tile(k, stride, dil, R, x->c, ho, wo, &G, &tw, &ty, &smem)) {
+        bool have_tile = kern && act != DBL_ACT_GELU && x->n <= 65535 && dw_pick_tile(k, stride, dil, R, x->c, ho, wo, &G, &tw, &ty, &smem);
+        if (have_tile) {
+            static const char* force = getenv("DBL_DW_TILE");  // tuning aid: "G,tw,ty"
+            int fg, ftw, fty;
+            if (force && sscanf(force, "%d,%d,%d", &fg, &ftw, &fty) == 3 && fg * ftw * fty <= 256) {
+                const int ir = (fty * R - 1) * stride + (k - 1) * dil + 1, ic = (ftw - 1) * stride + (k - 1) * dil + 1;
+                const size_t sm = (size_t)k * k * fg * 32 + (size_t)ir * ic * fg * 16;
+                if (sm <= 100 * 1024) G = fg, tw = ftw, ty = fty, smem = sm;
+            }
+        }
+        if (have_tile) {
             static thread_local const void* configured[8];
             static thread_local int nconf = 0;
             bool have = false;
@@ -542,7 +567,7 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
             }
             const int tiles_x = cdiv(wo, tw), tiles_y = cdiv(ho, ty * R);
             dim3 grid(tiles_x * tiles_y, cdiv(x->c / 8, G), x->n);
-            kern<<<grid, G * tw * ty, smem, st>>>(xp, w, bias, yp, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act, G, tw, ty, tiles_x);
+            launch_k(kern, grid, G * tw * ty, smem, st, xp, w, bias, yp, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act, G, tw, ty, tiles_x);
             count_launch();
             return check_launch("dbl_dwconv2d(tile)");
         }
@@ -553,7 +578,7 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
         const long long tot = (long long)x->n * ho * ((wo + R - 1) / R) * (x->c / 8);
         const unsigned gs = (unsigned)((tot + 127) / 128);
         const size_t sm = (size_t)k * k * x->c * 4;
-#define DBL_DWS(K, S) dwconv_strip_kernel<K, S, 4><<<gs, 128, sm, st>>>(xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act)
+#define DBL_DWS(K, S) launch_k(dwconv_strip_kernel<K, S, 4>, gs, 128, sm, st, xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act)
         bool done = true;
         if (k == 3 && stride == 1) DBL_DWS(3, 1);
         else if (k == 3 && stride == 2) DBL_DWS(3, 2);
@@ -566,7 +591,7 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
             return check_launch("dbl_dwconv2d(strip)");
         }
     }
-#define DBL_DW(K) dwconv_kernel<K><<<grid, 256, 0, st>>>(xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, stride, dil, act)
+#define DBL_DW(K) launch_k(dwconv_kernel<K>, grid, 256, 0, st, xp, w, bias, yp, x->n, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, stride, dil, act)
     switch (k) {
         case 3: DBL_DW(3); break;
         case 5: DBL_DW(5); break;

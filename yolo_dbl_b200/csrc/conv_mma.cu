@@ -65,6 +65,8 @@ __host__ __device__ constexpr int mma_ksteps(int cin, int taps) { return cin == 
 __host__ __device__ constexpr int mma_chan(int nb_total, int j, int n) { return (n >> 1) * 2 * nb_total + 2 * j + (n & 1); }
 
 __global__ void mma_pack_kernel(const __nv_bfloat16* __restrict__ w, int cout, int cin, int taps, uint2* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nb = cout / 8, ks_n = mma_ksteps(cin, taps);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ks_n * nb * 32) return;
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     constexpr int NT = NWARPS * 32;
+    pdl_launch_dependents();
 
     auto prefetch = [&](int tile, int buf) {
         const int per_img = p.tiles_x * p.tiles_y;
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
     for (int i = tid; i < K::W2B / 16; i += NT) cp_async16(sW2 + i * 16, reinterpret_cast<const uint8_t*>(p.w2) + i * 16, true);
     for (int i = tid; i < K::H; i += NT) sB1[i] = p.b1 ? p.b1[i] : 0.f;
     for (int i = tid; i < C; i += NT) sB2[i] = p.b2 ? p.b2[i] : 0.f;
+    pdl_wait();  // weights / biases are constant; x is the previous kernel's output
     int tile = blockIdx.x, buf = 0;
     if (tile < p.ntiles) prefetch(tile, 0);
     cp_async_commit();
@@ -399,6 +403,7 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     constexpr int NT = NWARPS * 32;
+    pdl_launch_dependents();
 
     auto prefetch = [&](int tile, int buf) {
         const int per_img = p.tiles_x * p.tiles_y;
@@ -423,6 +428,7 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
 
     for (int i = tid; i < K::WB / 16; i += NT) cp_async16(sW + i * 16, reinterpret_cast<const uint8_t*>(p.w) + i * 16, true);
     for (int i = tid; i < COUT; i += NT) sB[i] = p.b ? p.b[i] : 0.f;
+    pdl_wait();
     int tile = blockIdx.x, buf = 0;
     if (tile < p.ntiles) prefetch(tile, 0);
     cp_async_commit();
@@ -538,6 +544,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
     constexpr int NT = NWARPS * 32;
 
     const int img = blockIdx.z, oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+    pdl_launch_dependents();
 
     // ---- weights: layer 1 packed (async copy); layer 0 packed here from f32 [C0][ci][ky][kx]: k-step = ky, k = kx*4 + ci
     for (int i = tid; i < K::W1B / 16; i += NT) cp_async16(sW1 + i * 16, reinterpret_cast<const uint8_t*>(p.w1) + i * 16, true);
@@ -561,6 +568,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
     for (int i = tid; i < C0; i += NT) sB0[i] = p.b0 ? p.b0[i] : 0.f;
     for (int i = tid; i < C1; i += NT) sB1[i] = p.b1 ? p.b1[i] : 0.f;
 
+    pdl_wait();  // the image batch may have been produced by an earlier kernel / copy of the stream
     // ---- stage the input tile: rows 2*oy0-2 .., cols 2*ox0-2 ..; pixel = {R,G,B,0} bf16 (8 bytes); zero outside the image
     {
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)img * 3 * p.h * p.w;
@@ -707,7 +715,7 @@ static int launch_bottleneck(const dbl_tensor* x, const void* w1p, const float* 
     int grid = 0;
     const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_bottleneck3x3", &grid);
     if (rc) return rc;
-    kern<<<grid, NWARPS * 32, K::SMEM, st>>>(p);
+    launch_k(kern, grid, NWARPS * 32, K::SMEM, st, p);
     count_launch();
     return check_launch("dbl_bottleneck3x3");
 }
@@ -727,7 +735,7 @@ static int launch_conv_mma(const dbl_tensor* x, const void* wp, const float* b, 
     int grid = 0;
     const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_conv3x3_mma", &grid);
     if (rc) return rc;
-    kern<<<grid, NWARPS * 32, K::SMEM, st>>>(p);
+    launch_k(kern, grid, NWARPS * 32, K::SMEM, st, p);
     count_launch();
     return check_launch("dbl_conv3x3_mma");
 }
@@ -754,7 +762,7 @@ static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0,
         configured = true;
     }
     DBL_REQUIRE(n <= 65535 && p.tiles_y <= 65535, DBL_E_UNSUPPORTED, "dbl_stem_pair: grid too large");
-    kern<<<dim3(p.tiles_x, p.tiles_y, n), NWARPS * 32, K::SMEM, st>>>(p);
+    launch_k(kern, dim3(p.tiles_x, p.tiles_y, n), NWARPS * 32, K::SMEM, st, p);
     count_launch();
     return check_launch("dbl_stem_pair");
 }
@@ -774,7 +782,7 @@ extern "C" int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, 
     DBL_REQUIRE((reinterpret_cast<uintptr_t>(w) & 3) == 0 && (reinterpret_cast<uintptr_t>(packed) & 15) == 0, DBL_E_ARG,
                 "dbl_mma_pack_weights: misaligned pointer");
     const int total = mma_ksteps(cin, taps) * (cout / 8) * 32;
-    mma_pack_kernel<<<cdiv(total, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(w), cout, cin, taps,
+    launch_k(mma_pack_kernel, cdiv(total, 128), 128, 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(w), cout, cin, taps,
                                                                       reinterpret_cast<uint2*>(packed));
     count_launch();
     return check_launch("dbl_mma_pack_weights");

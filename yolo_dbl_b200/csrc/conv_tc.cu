@@ -20,7 +20,7 @@
 
 namespace dbl {
 
-constexpr int TC_EPI_WARPS = 8;                      // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
+constexpr int TC_EPI_WARPS = 16;                     // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int TC_MAX_STAGES = 8;
 constexpr int MAX_ACC = 8;
@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents may start only once every CTA of this grid HOLDS its TMEM columns (a dependent CTA that allocated
+    // first and then blocked in its own pdl_wait() would starve us); then wait for our own predecessor
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int kblocks = p.taps * p.nchunks;
@@ -443,11 +447,11 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     if (act == DBL_ACT_SILU)
-        conv_tc_kernel<DBL_ACT_SILU><<<grid, TC_THREADS, smem, st>>>(maps, p);
+        launch_k(conv_tc_kernel<DBL_ACT_SILU>, grid, TC_THREADS, smem, st, maps, p);
     else if (act == DBL_ACT_GELU)
-        conv_tc_kernel<DBL_ACT_GELU><<<grid, TC_THREADS, smem, st>>>(maps, p);
+        launch_k(conv_tc_kernel<DBL_ACT_GELU>, grid, TC_THREADS, smem, st, maps, p);
     else
-        conv_tc_kernel<DBL_ACT_NONE><<<grid, TC_THREADS, smem, st>>>(maps, p);
+        launch_k(conv_tc_kernel<DBL_ACT_NONE>, grid, TC_THREADS, smem, st, maps, p);
     count_launch();
     return check_launch("dbl_conv2d(tcgen05)");
 }

@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: dependents may start only once every CTA of this grid HOLDS its TMEM columns (a dependent CTA that allocated
+    // first and then blocked in its own pdl_wait() would starve us); then wait for our own predecessor
+    pdl_launch_dependents();
+    pdl_wait();
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int per_img = p.tiles_x * p.tiles_y;
 
@@ -438,11 +442,11 @@ int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     if (act == DBL_ACT_SILU)
-        conv3x3_tc_kernel<DBL_ACT_SILU><<<grid, C3_THREADS, smem, st>>>(p);
+        launch_k(conv3x3_tc_kernel<DBL_ACT_SILU>, grid, C3_THREADS, smem, st, p);
     else if (act == DBL_ACT_GELU)
-        conv3x3_tc_kernel<DBL_ACT_GELU><<<grid, C3_THREADS, smem, st>>>(p);
+        launch_k(conv3x3_tc_kernel<DBL_ACT_GELU>, grid, C3_THREADS, smem, st, p);
     else
-        conv3x3_tc_kernel<DBL_ACT_NONE><<<grid, C3_THREADS, smem, st>>>(p);
+        launch_k(conv3x3_tc_kernel<DBL_ACT_NONE>, grid, C3_THREADS, smem, st, p);
     count_launch();
     return check_launch("dbl_conv2d(tcgen05 3x3)");
 }

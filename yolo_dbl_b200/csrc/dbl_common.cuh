@@ -22,6 +22,29 @@ int check_launch(const char* what);  // cudaGetLastError -> DBL_E_CUDA
         }                                 \
     } while (0)
 
+// ---- launches: programmatic dependent launch (PDL) ----------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute: the next kernel of the
+// stream (or the next node of the captured graph) may START -- block scheduling, shared-memory carve-up, barrier / TMEM
+// set-up, weight staging -- while its predecessor is still draining, and blocks in pdl_wait() until the predecessor has
+// completed and its writes are visible.  Rules every kernel follows: pdl_launch_dependents() first; nothing written by
+// an earlier kernel is read, and nothing is written, before pdl_wait(); every kernel executes pdl_wait() (completion is
+// then transitive along the stream).  dbl_set_pdl(0) turns the attribute off (the device-side calls become no-ops).
+extern int g_pdl_enabled;
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = g_pdl_enabled ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through check_launch()
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 static inline cudaStream_t as_stream(dbl_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline bool valid_tensor(const dbl_tensor* t) {

@@ -109,6 +109,8 @@ __device__ __forceinline__ void locate_anchor(const LevelGeom& g, int a, int& lv
 // ---- decode to the reference's y layout ---------------------------------------------------------------------------
 // grid (ceil(A/256), B); thread per anchor.
 __global__ void __launch_bounds__(256) decode_kernel(LevelGeom g, float* __restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (a >= g.A) return;
     int lvl, cell;
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(256) decode_kernel(LevelGeom g, float* __restr
 // ---- fused decode + filter ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) decode_filter_kernel(LevelGeom g, float conf, int multi_label, const int32_t* __restrict__ classes,
                                                             int ncls, dbl_candidates cd) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     const bool live = a < g.A;
     int lvl = 0, cell = 0;
@@ -160,6 +164,8 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(LevelGeom g, float c
 __global__ void __launch_bounds__(256) filter_kernel(const float* __restrict__ pred, int nc, int A, long long sb, long long sc, long long sa,
                                                      float conf, int multi_label, const int32_t* __restrict__ classes, int ncls,
                                                      dbl_candidates cd) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     const bool live = a < A;
     const float* p = pred + (size_t)b * sb + (size_t)(live ? a : 0) * sa;
@@ -213,6 +219,8 @@ __host__ __device__ inline size_t next_pow2(size_t v) {
 __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd, float iou_thr, float cls_scale, int max_nms, int max_det,
                                                                uint64_t* __restrict__ scratch, size_t per_image, float* __restrict__ out_rows,
                                                                int32_t* __restrict__ out_pos, int32_t* __restrict__ out_count) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char nms_smem[];
     unsigned char* dead = nms_smem;  // slow path: one flag per candidate (NMS_FLAG_CAP bytes), overlays the fast-path area
     __shared__ int s_pivot;
@@ -471,7 +479,7 @@ extern "C" int dbl_detect_decode(const dbl_head_levels* lv, float* y, dbl_stream
     LevelGeom g;
     DBL_REQUIRE(make_geom(lv, &g) && y, DBL_E_ARG, "dbl_detect_decode: invalid head description");
     DBL_REQUIRE(g.pitch % 4 == 0, DBL_E_ARG, "dbl_detect_decode: pitch must be a multiple of 4 floats");
-    decode_kernel<<<dim3(cdiv(g.A, 256), lv->batch), 256, 0, as_stream(stream)>>>(g, y);
+    launch_k(decode_kernel, dim3(cdiv(g.A, 256), lv->batch), 256, 0, as_stream(stream), g, y);
     count_launch();
     return check_launch("dbl_detect_decode");
 }
@@ -486,7 +494,7 @@ extern "C" int dbl_decode_filter(const dbl_head_levels* lv, float conf_thres, in
     cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaMemsetAsync(cand->count, 0, sizeof(int32_t) * cand->batch, st);
     DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_decode_filter: memset: %s", cudaGetErrorString(e));
-    decode_filter_kernel<<<dim3(cdiv(g.A, 256), lv->batch), 256, 0, st>>>(g, conf_thres, ml, classes, num_classes_kept, *cand);
+    launch_k(decode_filter_kernel, dim3(cdiv(g.A, 256), lv->batch), 256, 0, st, g, conf_thres, ml, classes, num_classes_kept, *cand);
     count_launch();
     return check_launch("dbl_decode_filter");
 }
@@ -501,7 +509,7 @@ extern "C" int dbl_nms_filter(const float* pred, int batch, int nc, int anchors,
     cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaMemsetAsync(cand->count, 0, sizeof(int32_t) * batch, st);
     DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_nms_filter: memset: %s", cudaGetErrorString(e));
-    filter_kernel<<<dim3(cdiv(anchors, 256), batch), 256, 0, st>>>(pred, nc, anchors, stride_b, stride_c, stride_a, conf_thres, ml, classes,
+    launch_k(filter_kernel, dim3(cdiv(anchors, 256), batch), 256, 0, st, pred, nc, anchors, stride_b, stride_c, stride_a, conf_thres, ml, classes,
                                                                    num_classes_kept, *cand);
     count_launch();
     return check_launch("dbl_nms_filter");
@@ -527,7 +535,7 @@ extern "C" int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic
         DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_nms: shared memory opt-in failed: %s", cudaGetErrorString(e));
         smem_ok = true;
     }
-    sort_nms_kernel<<<cand->batch, NMS_THREADS, NMS_SMEM, as_stream(stream)>>>(*cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
+    launch_k(sort_nms_kernel, cand->batch, NMS_THREADS, NMS_SMEM, as_stream(stream), *cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
                                                                         sort_keys, dbl_nms_sort_capacity(cand->cap), out_rows, out_pos,
                                                                         out_count);
     count_launch();

@@ -8,6 +8,8 @@ namespace dbl {
 template <int MODE>
 __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                        int n, int ho, int wo, int c, int xpitch, int ypitch, int hi, int wi) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const long long total = (long long)n * ho * wo * cg;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) resample_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) gated_add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                                         float gate, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ y2,
                                                         long long npix, int c, int apitch, int bpitch, int ypitch, int y2pitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= npix * cg) return;
@@ -60,6 +64,8 @@ __global__ void __launch_bounds__(256) gated_add_kernel(const __nv_bfloat16* __r
 __global__ void __launch_bounds__(256) dysample_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ off,
                                                        __nv_bfloat16* __restrict__ y, int n, int h, int w, int c, int xpitch,
                                                        int opitch, int ypitch, int groups) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const int ho = 2 * h, wo = 2 * w;
     const long long total = (long long)n * ho * wo * cg;
@@ -94,6 +100,8 @@ __global__ void __launch_bounds__(256) dysample_kernel(const __nv_bfloat16* __re
 // LSK squeeze: one warp per pixel -> (mean, max) over all channels of [attn1|attn2]
 __global__ void __launch_bounds__(256) lsk_squeeze_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ agg,
                                                           long long npix, int c, int apitch, int gpitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long pix = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (pix >= npix) return;
@@ -122,6 +130,8 @@ __global__ void __launch_bounds__(256) lsk_gate_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ wsq, const float* __restrict__ bsq,
                                                        __nv_bfloat16* __restrict__ y, int n, int h, int w, int half, int apitch,
                                                        int gpitch, int ypitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sw[2 * 2 * 49];
     for (int i = threadIdx.x; i < 196; i += blockDim.x) sw[i] = wsq[i];
     __syncthreads();
@@ -165,9 +175,9 @@ static int launch_resample(int mode, const dbl_tensor* x, const dbl_tensor* y, c
     const unsigned grid = (unsigned)((total + 255) / 256);
     auto* xp = reinterpret_cast<const __nv_bfloat16*>(x->data);
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
-    if (mode == 0) resample_kernel<0><<<grid, 256, 0, st>>>(xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
-    if (mode == 1) resample_kernel<1><<<grid, 256, 0, st>>>(xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
-    if (mode == 2) resample_kernel<2><<<grid, 256, 0, st>>>(xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
+    if (mode == 0) launch_k(resample_kernel<0>, grid, 256, 0, st, xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
+    if (mode == 1) launch_k(resample_kernel<1>, grid, 256, 0, st, xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
+    if (mode == 2) launch_k(resample_kernel<2>, grid, 256, 0, st, xp, yp, y->n, y->h, y->w, y->c, x->pitch, y->pitch, x->h, x->w);
     count_launch();
     return check_launch(name);
 }
@@ -195,7 +205,7 @@ extern "C" int dbl_gated_add(const dbl_tensor* a, const dbl_tensor* b, float gat
     if (y2) DBL_REQUIRE(valid_tensor(y2) && vec8_ok(y2) && same_shape(a, y2), DBL_E_ARG, "dbl_gated_add: y2 mismatch");
     const long long npix = (long long)a->n * a->h * a->w;
     const long long total = npix * (a->c / 8);
-    gated_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(
+    launch_k(gated_add_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(s), 
         reinterpret_cast<const __nv_bfloat16*>(a->data), reinterpret_cast<const __nv_bfloat16*>(b->data), gate,
         reinterpret_cast<__nv_bfloat16*>(y->data), y2 ? reinterpret_cast<__nv_bfloat16*>(y2->data) : nullptr, npix, a->c,
         a->pitch, b->pitch, y->pitch, y2 ? y2->pitch : 0);
@@ -212,7 +222,7 @@ extern "C" int dbl_dysample(const dbl_tensor* x, const dbl_tensor* off, const db
     DBL_REQUIRE(groups > 0 && x->c % groups == 0 && (x->c / groups) % 8 == 0, DBL_E_UNSUPPORTED,
                 "dbl_dysample: channels per group must be a multiple of 8");
     const long long total = (long long)y->n * y->h * y->w * (y->c / 8);
-    dysample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(s)>>>(
+    launch_k(dysample_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(s), 
         reinterpret_cast<const __nv_bfloat16*>(x->data), reinterpret_cast<const float*>(off->data),
         reinterpret_cast<__nv_bfloat16*>(y->data), x->n, x->h, x->w, x->c, x->pitch, off->pitch, y->pitch, groups);
     count_launch();
@@ -224,7 +234,7 @@ extern "C" int dbl_lsk_squeeze(const dbl_tensor* attn, const dbl_tensor* agg, db
     DBL_REQUIRE(agg->dtype == DBL_F32 && agg->c == 2 && agg->n == attn->n && agg->h == attn->h && agg->w == attn->w, DBL_E_ARG,
                 "dbl_lsk_squeeze: agg must be f32 (n,h,w,2)");
     const long long npix = (long long)attn->n * attn->h * attn->w;
-    lsk_squeeze_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, as_stream(s)>>>(
+    launch_k(lsk_squeeze_kernel, (unsigned)((npix + 7) / 8), 256, 0, as_stream(s), 
         reinterpret_cast<const __nv_bfloat16*>(attn->data), reinterpret_cast<float*>(agg->data), npix, attn->c, attn->pitch,
         agg->pitch);
     count_launch();
@@ -239,7 +249,7 @@ extern "C" int dbl_lsk_gate(const dbl_tensor* attn, const dbl_tensor* agg, const
     DBL_REQUIRE(attn->n == y->n && attn->h == y->h && attn->w == y->w && agg->n == y->n && agg->h == y->h && agg->w == y->w, DBL_E_ARG,
                 "dbl_lsk_gate: shape mismatch");
     const long long npix = (long long)y->n * y->h * y->w;
-    lsk_gate_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, as_stream(s)>>>(
+    launch_k(lsk_gate_kernel, (unsigned)((npix + 7) / 8), 256, 0, as_stream(s), 
         reinterpret_cast<const __nv_bfloat16*>(attn->data), reinterpret_cast<const float*>(agg->data), w_sq, b_sq,
         reinterpret_cast<__nv_bfloat16*>(y->data), y->n, y->h, y->w, y->c, attn->pitch, agg->pitch, y->pitch);
     count_launch();

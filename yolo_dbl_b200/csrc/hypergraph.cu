@@ -38,6 +38,8 @@ static HgLayout hg_layout(int B, int N, int D, int E) {
 
 // K1: partial sum / max over a token range.  grid (HG_CTX_SPLIT, B), block D threads.
 __global__ void hg_context_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part, int N, int D, int pitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int d = threadIdx.x, s = blockIdx.x, b = blockIdx.y;
     const int per = (N + HG_CTX_SPLIT - 1) / HG_CTX_SPLIT;
     const int n0 = s * per, n1 = min(N, n0 + per);
@@ -55,6 +57,8 @@ __global__ void hg_context_kernel(const __nv_bfloat16* __restrict__ x, float* __
 // K2: prototypes and their folded forms.  grid (B), block 256.
 __global__ void __launch_bounds__(256) hg_proto_kernel(const float* __restrict__ part, dbl_hypergraph_weights wt, float* __restrict__ P,
                                                        float* __restrict__ cvec, int N, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // ctx[2D] | proto[E*D]
     float* ctx = sm;
     float* proto = sm + 2 * D;
@@ -101,6 +105,8 @@ __global__ void __launch_bounds__(256) hg_proto_kernel(const float* __restrict__
 __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_logits_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ P,
                                                                  const float* __restrict__ cvec, float* __restrict__ logits,
                                                                  float* __restrict__ stat_part, int N, int D, int E, int pitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // P[E*D] | red_max[E*NW] | red_sum[E*NW]
     float* sP = sm;
     float* red = sm + E * D;
@@ -165,6 +171,8 @@ constexpr int HG_EDGE_SPLIT = 8;
 __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ logits,
                                                                const float* __restrict__ stat_part, float* __restrict__ He, int N, int D,
                                                                int E, int nblk, int pitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // mstat[2*HG_MAX_E] | red[R*E*D]
     const int b = blockIdx.y;
     float* mstat = sm;
@@ -216,6 +224,8 @@ __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat
 // K4b: He2 = GELU(He We^T + be), Q = He2 Wn^T.  grid (B), block 256.
 __global__ void __launch_bounds__(256) hg_edges_final_kernel(const float* __restrict__ He, dbl_hypergraph_weights wt, float* __restrict__ Q,
                                                              int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // he[E*D] | he2[E*D]
     const int b = blockIdx.x, E = wt.num_edges;
     float* he = sm;
@@ -247,6 +257,8 @@ __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_nodes_kernel(const __nv_bfloa
                                                                 const float* __restrict__ Q, const float* __restrict__ node_b,
                                                                 __nv_bfloat16* y, int N, int D, int E, int xpitch,
                                                                 int ypitch) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // Q[E*D] | bn[D]
     float* sQ = sm;
     float* sb = sm + E * D;
@@ -302,18 +314,18 @@ extern "C" int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights*
     auto* xp = reinterpret_cast<const __nv_bfloat16*>(x->data);
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
 
-    hg_context_kernel<<<dim3(HG_CTX_SPLIT, B), D, 0, st>>>(xp, f + L.ctx_part, N, D, x->pitch);
-    hg_proto_kernel<<<B, 256, (2 * D + E * D) * sizeof(float), st>>>(f + L.ctx_part, *wt, f + L.P, f + L.cvec, N, D);
+    launch_k(hg_context_kernel, dim3(HG_CTX_SPLIT, B), D, 0, st, xp, f + L.ctx_part, N, D, x->pitch);
+    launch_k(hg_proto_kernel, B, 256, (2 * D + E * D) * sizeof(float), st, f + L.ctx_part, *wt, f + L.P, f + L.cvec, N, D);
     const size_t sm3 = ((size_t)E * D + 2 * E * (HG_TOK_BLOCK / 32)) * sizeof(float);
-    hg_logits_kernel<<<dim3(L.nblk, B), HG_TOK_BLOCK, sm3, st>>>(xp, f + L.P, f + L.cvec, f + L.logits, f + L.stat_part, N, D, E,
+    launch_k(hg_logits_kernel, dim3(L.nblk, B), HG_TOK_BLOCK, sm3, st, xp, f + L.P, f + L.cvec, f + L.logits, f + L.stat_part, N, D, E,
                                                                  x->pitch);
     const int R = 256 / D;
     const size_t sm4 = (2 * HG_MAX_E + (size_t)R * E * D) * sizeof(float);
     cudaError_t me = cudaMemsetAsync(f + L.He, 0, (size_t)B * E * D * sizeof(float), st);
     DBL_REQUIRE(me == cudaSuccess, DBL_E_CUDA, "dbl_hypergraph: memset failed: %s", cudaGetErrorString(me));
-    hg_edges_partial_kernel<<<dim3(HG_EDGE_SPLIT, B), 256, sm4, st>>>(xp, f + L.logits, f + L.stat_part, f + L.He, N, D, E, L.nblk, x->pitch);
-    hg_edges_final_kernel<<<B, 256, (size_t)2 * E * D * sizeof(float), st>>>(f + L.He, *wt, f + L.Q, D);
-    hg_nodes_kernel<<<dim3(L.nblk, B), HG_TOK_BLOCK, ((size_t)E * D + D) * sizeof(float), st>>>(
+    launch_k(hg_edges_partial_kernel, dim3(HG_EDGE_SPLIT, B), 256, sm4, st, xp, f + L.logits, f + L.stat_part, f + L.He, N, D, E, L.nblk, x->pitch);
+    launch_k(hg_edges_final_kernel, B, 256, (size_t)2 * E * D * sizeof(float), st, f + L.He, *wt, f + L.Q, D);
+    launch_k(hg_nodes_kernel, dim3(L.nblk, B), HG_TOK_BLOCK, ((size_t)E * D + D) * sizeof(float), st, 
         xp, f + L.logits, f + L.Q, wt->node_b, yp, N, D, E, x->pitch, y->pitch);
     count_launch(6);
     return check_launch("dbl_hypergraph");
