@@ -35,7 +35,8 @@ enum {
     DBL_IMPL_AUTO = 0,
     DBL_IMPL_DIRECT = 1,      /* CUDA-core direct convolution */
     DBL_IMPL_TCGEN05 = 2,     /* tensor cores: halo-reuse kernel for 3x3, TMA kernel for 1x1 */
-    DBL_IMPL_TCGEN05_TMA = 3  /* tensor cores, first-generation kernel (one TMA box per filter tap) */
+    DBL_IMPL_TCGEN05_TMA = 3, /* tensor cores, first-generation kernel (one TMA box per filter tap) */
+    DBL_IMPL_TCGEN05_MULTI = 4 /* tensor cores, 3x3 stride 1: halo reuse + weights streamed once per multi-accumulator super-tile */
 };
 
 typedef struct dbl_tensor {

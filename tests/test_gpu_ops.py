@@ -379,3 +379,24 @@ def test_stem_pair(c0, c1, u8, n, h, w):
     # layer 0 runs on bf16-rounded pixels / weights here (fp32 in the reference): one extra 2^-9 rounding per operand
     assert_close_bf16(from_nhwc(ybuf, 0, c1), ref, f"stem_pair {c0}->{c1} u8={u8}", rel=2.0 ** -6, abs_=4e-2)
     assert bool((ybuf[..., c1:].float() == -3.0).all())
+
+
+# ---- multi-accumulator tcgen05 3x3 kernel (csrc/conv_tc4.cu): large reduction depth --------------------------------
+TC4_CASES = [
+    (2, 40, 40, 384, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 80, 80, 256, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 40, 40, 192, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 64),
+    (2, 20, 20, 256, 64, 3, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 0),
+    (1, 40, 40, 128, 128, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 128, 0),
+    (1, 33, 50, 128, 48, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 20, 20, 160, 80, 3, 1, L.ACT_GELU, L.EPI_MUL, torch.bfloat16, 0, 0),   # 32-channel chunks
+    (1, 24, 24, 144, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),   # 16-channel chunks
+    (1, 20, 20, 256, 256, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (24, 80, 80, 128, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),  # every CTA loops over several super-tiles
+    (3, 40, 40, 64, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC4_CASES)
+def test_conv3x3_multi_accumulator_kernel(case):
+    _run_conv_case(case, L.IMPL_TCGEN05_MULTI, seed=11)

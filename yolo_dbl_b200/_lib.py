@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdbl_sm100.so")
 DBL_BF16, DBL_F32 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 EPI_NONE, EPI_ADD, EPI_MUL = 0, 1, 2
-IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TCGEN05_TMA = 0, 1, 2, 3
+IMPL_AUTO, IMPL_DIRECT, IMPL_TCGEN05, IMPL_TCGEN05_TMA, IMPL_TCGEN05_MULTI = 0, 1, 2, 3, 4
 
 
 class DblError(RuntimeError):

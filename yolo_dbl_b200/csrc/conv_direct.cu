@@ -13,6 +13,9 @@ int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl
                 int epi, cudaStream_t st);
 bool conv3x3_tc3_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil);
 bool conv3x3_tc3_preferred(const dbl_tensor* x, const dbl_tensor* y, int stride);
+int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int act, int epi, cudaStream_t st);
+bool conv3x3_tc4_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil);
+bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y);
 
 // ------------------------------------------------------------------------------------------------------------------
 // stem: x f32 NCHW (n,3,h,w) -> y bf16 NHWC (n,ho,wo,COUT), 3x3, pad 1, SiLU
@@ -493,6 +496,10 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = conv2d_tcgen05_eligible(x, r, y, k, stride, pad, dil);
     const bool tc3_ok = conv3x3_tc3_eligible(x, y, k, stride, pad, dil);
+    const bool tc4_ok = conv3x3_tc4_eligible(x, y, k, stride, pad, dil);
+    if (impl == DBL_IMPL_TCGEN05_MULTI) DBL_REQUIRE(tc4_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the multi-accumulator tcgen05 path");
+    if (tc4_ok && (impl == DBL_IMPL_TCGEN05_MULTI || ((impl == DBL_IMPL_AUTO || impl == DBL_IMPL_TCGEN05) && conv3x3_tc4_preferred(x, y))))
+        return conv3x3_tc4(x, w, bias, epi ? r : nullptr, y, act, epi, st);
     if (impl == DBL_IMPL_TCGEN05) DBL_REQUIRE(tc_ok || tc3_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for a tcgen05 path");
     if (impl == DBL_IMPL_TCGEN05_TMA) DBL_REQUIRE(tc_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the TMA tcgen05 path");
     if (tc3_ok && (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && (!tc_ok || conv3x3_tc3_preferred(x, y, stride)))))
