@@ -126,25 +126,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t row_bytes = (uint32_t)p.cchunk * 2;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-                int img = 0, y0 = 0, x0 = 0;
-                if (!p.flat) {
-                    const int per_img = p.tiles_x * p.tiles_y;
-                    img = mt / per_img;
-                    const int t = mt % per_img;
-                    y0 = (t / p.tiles_x) * p.th;
-                    x0 = (t % p.tiles_x) * p.tw;
-                }
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / p.nchunks, ch = kb % p.nchunks;
-                    mbar_wait(&empty[stage], phase ^ 1);
+        // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            int img = 0, y0 = 0, x0 = 0;
+            if (!p.flat) {
+                const int per_img = p.tiles_x * p.tiles_y;
+                img = mt / per_img;
+                const int t = mt % per_img;
+                y0 = (t / p.tiles_x) * p.th;
+                x0 = (t % p.tiles_x) * p.tw;
+            }
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int tap = kb / p.nchunks, ch = kb % p.nchunks;
+                mbar_wait(&empty[stage], phase ^ 1);
+                void* a_dst = sA + (size_t)stage * p.a_bytes;
+                void* b_dst = sB + (size_t)stage * p.b_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(&full[stage], p.a_tx + p.b_tx);
-                    void* a_dst = sA + (size_t)stage * p.a_bytes;
-                    void* b_dst = sB + (size_t)stage * p.b_bytes;
                     if (p.flat) {
                         tma_load_2d(&maps.a[0], &full[stage], a_dst, ch * p.cchunk, mt * TILE_M);
                     } else if (p.stride == 1) {
@@ -157,33 +157,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         tma_load_4d(&maps.a[ph * 2 + pw], &full[stage], a_dst, ch * p.cchunk, x0 + ox, y0 + oy, img);
                     }
                     tma_load_2d(&maps.b, &full[stage], b_dst, kb * p.cchunk, nt * p.npad);
-                    if (++stage == (uint32_t)p.stages) stage = 0, phase ^= 1;
                 }
+                __syncwarp();
+                if (++stage == (uint32_t)p.stages) stage = 0, phase ^= 1;
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        // instruction descriptor: D=f32, A=B=bf16, both K-major, N = npad, M = 128
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N = npad, M = 128.  Everything the MMA consumes is kept
+        // provably warp-uniform (loops outside the election, TMEM base re-broadcast): otherwise ptxas wraps each UTCHMMA
+        // in an R2UR / ELECT waterfall loop of ~15 instructions, which paces the whole kernel when K is small.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t dtempl = make_kmajor_desc(0, row_bytes);
+        const int ksteps = p.cchunk / 16;
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
-            if (lane == 0) mbar_wait(&tempty[acc], aphase ^ 1);
-            __syncwarp();
+            mbar_wait(&tempty[acc], aphase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.npad;
+            const uint32_t d_tmem = tmem_u + acc * (uint32_t)p.npad;
             for (int kb = 0; kb < kblocks; ++kb) {
-                if (lane == 0) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)stage * p.a_bytes);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)stage * p.b_bytes);
-                    const int ksteps = p.cchunk / 16;
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ad = make_kmajor_desc(a_addr + ks * 32, row_bytes);
-                        const uint64_t bd = make_kmajor_desc(b_addr + ks * 32, row_bytes);
-                        umma_bf16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
-                    }
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint64_t ad0 = dtempl + (uint64_t)(smem_u32(sA + (size_t)stage * p.a_bytes) >> 4);
+                const uint64_t bd0 = dtempl + (uint64_t)(smem_u32(sB + (size_t)stage * p.b_bytes) >> 4);
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps; ++ks) umma_bf16(d_tmem, ad0 + 2 * ks, bd0 + 2 * ks, idesc, (kb | ks) ? 1u : 0u);
                     umma_commit(&empty[stage]);                       // frees the smem slot when these MMAs retire
                     if (kb == kblocks - 1) umma_commit(&tfull[acc]);  // accumulator complete
                 }

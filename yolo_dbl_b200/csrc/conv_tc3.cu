@@ -108,42 +108,42 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
     const int per_img = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
-        // ===================== MMA issuer =====================
-        // One thread issues every MMA, so its instruction count per MMA is the kernel's pace for thin layers.  The
-        // descriptors of a pipeline unit differ from stage to stage only in their start address: build the sequence once
-        // (all 32 lanes, into shared memory) and add the stage base at issue time.
+        // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+        // One thread issues every MMA, so its instruction count per MMA is the kernel's pace for thin layers.  All operands
+        // are kept provably warp-uniform (loops outside the election, descriptors computed from kernel parameters, TMEM base
+        // re-broadcast), so ptxas emits plain uniform-datapath arithmetic + UTCHMMA instead of an R2UR waterfall per MMA.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const int nmma = (p.G == 1) ? 5 : 9 * (p.Gc >> 1);
-        for (int k = lane; k < nmma; k += 32) {
-            uint32_t a_rel, a_lbo, b_rel;
-            if (p.G == 1) {
-                const int o0 = p.off[2 * k], o1 = (2 * k + 1 < 9) ? p.off[2 * k + 1] : o0 + 1;
-                a_rel = o0 * 16, a_lbo = (uint32_t)(o1 - o0) * 16, b_rel = (2 * k) * p.psb;
-            } else {
-                const int pairs = p.Gc >> 1, j = k / pairs, pp = k - j * pairs;
-                a_rel = (2 * pp) * p.ps + p.off[j] * 16, a_lbo = (uint32_t)p.ps, b_rel = (j * p.Gc + 2 * pp) * p.psb;
-            }
-            sDesc[2 * k] = make_noswz_desc(a_rel, a_lbo);
-            sDesc[2 * k + 1] = make_noswz_desc(b_rel, (uint32_t)p.psb);
-        }
-        __syncwarp();
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const int pairs = p.Gc >> 1;
         uint32_t stage = 0, phase = 0, it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
-            if (lane == 0) mbar_wait(&tempty[acc], aphase ^ 1);
-            __syncwarp();
+            mbar_wait(&tempty[acc], aphase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.npad;
+            const uint32_t d_tmem = tmem_u + acc * (uint32_t)p.npad;
             for (int cc = 0; cc < p.ncc; ++cc) {
-                if (lane == 0) {
-                    mbar_wait(&full[stage], phase);
-                    if (!DBL_C3_NO_FENCE) fence_proxy_async();  // cp.async wrote through the generic proxy; tcgen05 reads through the async proxy
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(sRing + (size_t)stage * stage_bytes);
-                    const uint32_t b_base = p.b_resident ? smem_u32(sBres) : a_base + p.a_bytes;
-                    const uint64_t a_add = (uint64_t)(a_base >> 4), b_add = (uint64_t)(b_base >> 4);
-                    umma_bf16(d_tmem, sDesc[0] + a_add, sDesc[1] + b_add, idesc, cc ? 1u : 0u);
-                    for (int k = 1; k < nmma; ++k) umma_bf16(d_tmem, sDesc[2 * k] + a_add, sDesc[2 * k + 1] + b_add, idesc, 1u);
+                mbar_wait(&full[stage], phase);
+                if (!DBL_C3_NO_FENCE) fence_proxy_async();  // cp.async wrote through the generic proxy; tcgen05 reads through the async proxy
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(sRing + (size_t)stage * stage_bytes);
+                const uint32_t b_base = p.b_resident ? smem_u32(sBres) : a_base + p.a_bytes;
+                if (elect_one()) {
+                    if (p.G == 1) {  // 8 input channels: two filter taps per K=16 step, LBO = pixel distance between them
+#pragma unroll 1
+                        for (int k = 0; k < 5; ++k) {
+                            const int o0 = p.off[2 * k], o1 = (2 * k + 1 < 9) ? p.off[2 * k + 1] : o0 + 1;
+                            umma_bf16(d_tmem, make_noswz_desc(a_base + o0 * 16, (uint32_t)(o1 - o0) * 16),
+                                      make_noswz_desc(b_base + (2 * k) * p.psb, (uint32_t)p.psb), idesc, (cc | k) ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 9; ++j) {
+                            const uint32_t a_tap = a_base + p.off[j] * 16, b_tap = b_base + (uint32_t)(j * p.Gc) * p.psb;
+                            for (int pp = 0; pp < pairs; ++pp)
+                                umma_bf16(d_tmem, make_noswz_desc(a_tap + (2 * pp) * p.ps, (uint32_t)p.ps),
+                                          make_noswz_desc(b_tap + (2 * pp) * p.psb, (uint32_t)p.psb), idesc, (cc | j | pp) ? 1u : 0u);
+                        }
+                    }
                     umma_commit(&empty[stage]);
                     if (cc == p.ncc - 1) umma_commit(&tfull[acc]);
                 }

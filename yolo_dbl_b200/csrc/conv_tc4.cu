@@ -67,7 +67,20 @@ __device__ __forceinline__ uint64_t make_sw_desc(uint32_t saddr, uint32_t row_by
     return d;
 }
 
-template <int ACT>
+// tcgen05.mma with the descriptors given as (lo, hi) words: only the low word changes from MMA to MMA (start address)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int ACT, int KSTEPS>
 __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid_constant__ T4Maps maps, const T4Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -82,7 +95,6 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     uint64_t* tfull = bempty + 2;              // [T4_MAX_ACC]
     uint64_t* tempty = tfull + T4_MAX_ACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + T4_MAX_ACC);
-    uint64_t* sDesc = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // [9 taps * k-steps][2]: descriptor templates (A, B)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < p.npad; i += T4_THREADS) sBias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
@@ -110,58 +122,72 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     const uint32_t row_bytes = (uint32_t)p.cchunk * 2;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, aphase = 0, bbuf = 0, bphase = 0;
-            for (int s = blockIdx.x; s < p.n_super; s += gridDim.x) {
-                const int t0 = s * p.T, t1 = min(t0 + p.T, p.m_tiles);
-                for (int cc = 0; cc < p.nchunks; ++cc) {
-                    mbar_wait(&bempty[bbuf], bphase ^ 1);
+        // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+        uint32_t stage = 0, aphase = 0, bbuf = 0, bphase = 0;
+        for (int s = blockIdx.x; s < p.n_super; s += gridDim.x) {
+            const int t0 = s * p.T, t1 = min(t0 + p.T, p.m_tiles);
+            for (int cc = 0; cc < p.nchunks; ++cc) {
+                mbar_wait(&bempty[bbuf], bphase ^ 1);
+                uint8_t* b_dst = sB + (size_t)bbuf * p.b_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(&bfull[bbuf], p.b_tx);
-                    uint8_t* b_dst = sB + (size_t)bbuf * p.b_bytes;
+#pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap)
                         tma_load_2d(&maps.b, &bfull[bbuf], b_dst + (size_t)tap * p.npad * row_bytes, tap * p.cin + cc * p.cchunk, 0);
-                    if (++bbuf == 2) bbuf = 0, bphase ^= 1;
-                    for (int mt = t0; mt < t1; ++mt) {
-                        const int img = mt / per_img, t = mt - img * per_img;
-                        const int y0 = (t / p.tiles_x) * p.th, x0 = (t % p.tiles_x) * p.tw;
-                        mbar_wait(&aempty[stage], aphase ^ 1);
+                }
+                __syncwarp();
+                if (++bbuf == 2) bbuf = 0, bphase ^= 1;
+                for (int mt = t0; mt < t1; ++mt) {
+                    const int img = mt / per_img, t = mt - img * per_img;
+                    const int y0 = (t / p.tiles_x) * p.th, x0 = (t % p.tiles_x) * p.tw;
+                    mbar_wait(&aempty[stage], aphase ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(&afull[stage], p.a_tx);
                         tma_load_4d(&maps.a, &afull[stage], sA + (size_t)stage * p.a_bytes, cc * p.cchunk, x0 - 1, y0 - 1, img);
-                        if (++stage == (uint32_t)p.stages) stage = 0, aphase ^= 1;
                     }
+                    __syncwarp();
+                    if (++stage == (uint32_t)p.stages) stage = 0, aphase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // One thread issues every MMA: keep its work per MMA to two 8-byte loads and two adds.  The descriptors of a
-        // (tile, chunk) unit differ between stages only in their start address, so the 9*ksteps templates are built once.
+        // One thread issues every MMA, so its instruction count per MMA is the kernel's pace when N is small (an N=32 MMA
+        // occupies the tensor pipe for only 16 cycles).  The descriptors of a (tile, chunk) unit differ only in the start
+        // address field of their low word: nine tap offsets live in registers, the k-step offset is an immediate, the
+        // whole unit is unrolled -> two integer adds per MMA.
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const int ksteps = p.cchunk / 16;
-        const int nmma = 9 * ksteps;
-        for (int k = lane; k < nmma; k += 32) {
-            const int tap = k / ksteps, ks = k - tap * ksteps;
-            sDesc[2 * k] = make_sw_desc((uint32_t)((tap / 3) * p.wl + tap % 3) * row_bytes + ks * 32, row_bytes, p.base_off_mode);
-            sDesc[2 * k + 1] = make_sw_desc((uint32_t)tap * p.npad * row_bytes + ks * 32, row_bytes, 0);
-        }
-        __syncwarp();
+        const uint64_t dtempl = make_sw_desc(0, row_bytes, 0);
+        const uint32_t d_lo = (uint32_t)dtempl, d_hi = (uint32_t)(dtempl >> 32);
+        uint32_t tap_a[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) tap_a[tap] = ((uint32_t)((tap / 3) * p.wl + tap % 3) * row_bytes) >> 4;
+        const uint32_t tap_b = ((uint32_t)p.npad * row_bytes) >> 4;
+        // Control flow and operands stay warp-uniform (all 32 lanes walk the loops and poll the barriers); only the issue
+        // itself is predicated on lane 0.  With the loops inside `if (lane == 0)` ptxas cannot prove the descriptors
+        // uniform and wraps every UTCHMMA in an R2UR waterfall loop (~15 instructions per MMA).
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);  // read from shared memory: tell ptxas it is uniform
         uint32_t stage = 0, aphase = 0, bbuf = 0, bphase = 0, it = 0;
         for (int s = blockIdx.x; s < p.n_super; s += gridDim.x, ++it) {
             const int ntile = min(p.T, p.m_tiles - s * p.T);
             for (int cc = 0; cc < p.nchunks; ++cc) {
-                if (lane == 0) mbar_wait(&bfull[bbuf], bphase);
-                __syncwarp();
-                const uint64_t b_add = (uint64_t)(smem_u32(sB + (size_t)bbuf * p.b_bytes) >> 4);
+                mbar_wait(&bfull[bbuf], bphase);
+                const uint32_t b_lo = d_lo + (smem_u32(sB + (size_t)bbuf * p.b_bytes) >> 4);
                 for (int t = 0; t < ntile; ++t) {
-                    if (lane == 0) {
-                        if (cc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1);  // the epilogue has drained this accumulator
-                        mbar_wait(&afull[stage], aphase);
-                        tc_fence_after();
-                        const uint64_t a_add = (uint64_t)(smem_u32(sA + (size_t)stage * p.a_bytes) >> 4);
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.npad);
-                        umma_bf16(d_tmem, sDesc[0] + a_add, sDesc[1] + b_add, idesc, cc ? 1u : 0u);
-                        for (int k = 1; k < nmma; ++k) umma_bf16(d_tmem, sDesc[2 * k] + a_add, sDesc[2 * k + 1] + b_add, idesc, 1u);
+                    if (cc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1);  // the epilogue has drained this accumulator
+                    mbar_wait(&afull[stage], aphase);
+                    tc_fence_after();
+                    const uint32_t a_lo = d_lo + (smem_u32(sA + (size_t)stage * p.a_bytes) >> 4);
+                    const uint32_t d_tmem = tmem_u + (uint32_t)(t * p.npad);
+                    const uint32_t first = cc ? 1u : 0u;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ++ks)
+                                umma_bf16_lohi(d_tmem, a_lo + tap_a[tap] + 2 * ks, d_hi, b_lo + tap * tap_b + 2 * ks, d_hi, idesc,
+                                               (tap | ks) ? 1u : first);
+                        }
                         umma_commit(&aempty[stage]);
                         if (cc == p.nchunks - 1) umma_commit(&tfull[t]);
                         if (t == ntile - 1) umma_commit(&bempty[bbuf]);
@@ -301,7 +327,10 @@ bool conv3x3_tc4_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int s
 }
 
 // the multi-accumulator kernel pays off when the filter does not fit shared memory next to the activation ring
-bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y) { return x->c >= 128 && y->c >= 16; }
+bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y) {
+    static const int min_cin = getenv("DBL_TC4_MIN_CIN") ? atoi(getenv("DBL_TC4_MIN_CIN")) : 128;  // tuning aid
+    return x->c >= min_cin && y->c >= 16;
+}
 
 int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int act, int epi, cudaStream_t st) {
     static int num_sms = 0, max_smem = 0;
@@ -310,9 +339,13 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaSuccess;
+#define DBL_T4_ATTR(A, K) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc4_kernel<A, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+        DBL_T4_ATTR(0, 1); DBL_T4_ATTR(0, 2); DBL_T4_ATTR(0, 4);
+        DBL_T4_ATTR(1, 1); DBL_T4_ATTR(1, 2); DBL_T4_ATTR(1, 4);
+        DBL_T4_ATTR(2, 1); DBL_T4_ATTR(2, 2); DBL_T4_ATTR(2, 4);
+#undef DBL_T4_ATTR
         if (e != cudaSuccess) {
             set_error("conv3x3_tc4: cannot opt in to %d bytes of shared memory: %s", max_smem, cudaGetErrorString(e));
             num_sms = 0;
@@ -339,7 +372,7 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
     p.tiles_x = cdiv(p.w, p.tw), p.tiles_y = cdiv(p.h, p.th);
     p.m_tiles = p.n * p.tiles_x * p.tiles_y;
     // ---- K chunking + shared-memory budget: 2 weight buffers + >= 3 activation stages
-    const size_t fixed = 1024 + (((size_t)p.npad + 3) & ~(size_t)3) * 4 + (2 * T4_MAX_STAGES + 4 + 2 * T4_MAX_ACC) * 8 + 16 + 36 * 2 * 8;
+    const size_t fixed = 1024 + (((size_t)p.npad + 3) & ~(size_t)3) * 4 + (2 * T4_MAX_STAGES + 4 + 2 * T4_MAX_ACC) * 8 + 16;
     const int halo_px = p.rows_h * p.wl;
     const int need_px = 128 + 2 * p.wl + 2 > halo_px ? 128 + 2 * p.wl + 2 : halo_px;  // junk rows read a little past the box
     int cchunk = 0;
@@ -397,12 +430,19 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
     }
     const size_t smem = fixed + (size_t)p.stages * p.a_bytes + 2 * (size_t)p.b_bytes;
     const int grid = p.n_super < num_sms ? p.n_super : num_sms;
-    if (act == DBL_ACT_SILU)
-        launch_k(conv3x3_tc4_kernel<DBL_ACT_SILU>, grid, T4_THREADS, smem, st, maps, p);
-    else if (act == DBL_ACT_GELU)
-        launch_k(conv3x3_tc4_kernel<DBL_ACT_GELU>, grid, T4_THREADS, smem, st, maps, p);
-    else
-        launch_k(conv3x3_tc4_kernel<DBL_ACT_NONE>, grid, T4_THREADS, smem, st, maps, p);
+    const int ks = cchunk / 16;
+#define DBL_T4_GO(A, K) launch_k(conv3x3_tc4_kernel<A, K>, grid, T4_THREADS, smem, st, maps, p)
+#define DBL_T4_ACT(A)            \
+    do {                         \
+        if (ks == 4) DBL_T4_GO(A, 4); \
+        else if (ks == 2) DBL_T4_GO(A, 2); \
+        else DBL_T4_GO(A, 1);    \
+    } while (0)
+    if (act == DBL_ACT_SILU) DBL_T4_ACT(DBL_ACT_SILU);
+    else if (act == DBL_ACT_GELU) DBL_T4_ACT(DBL_ACT_GELU);
+    else DBL_T4_ACT(DBL_ACT_NONE);
+#undef DBL_T4_ACT
+#undef DBL_T4_GO
     count_launch();
     return check_launch("dbl_conv2d(tcgen05 3x3 multi-accumulator)");
 }
