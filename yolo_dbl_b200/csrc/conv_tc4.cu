@@ -328,7 +328,7 @@ bool conv3x3_tc4_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int s
 
 // the multi-accumulator kernel pays off when the filter does not fit shared memory next to the activation ring
 bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y) {
-    static const int min_cin = getenv("DBL_TC4_MIN_CIN") ? atoi(getenv("DBL_TC4_MIN_CIN")) : 128;  // tuning aid
+    static const int min_cin = getenv("DBL_TC4_MIN_CIN") ? atoi(getenv("DBL_TC4_MIN_CIN")) : 32;  // tuning aid
     return x->c >= min_cin && y->c >= 16;
 }
 

@@ -15,6 +15,7 @@ Reference control flow being replaced: ``BaseModel._predict_once`` (``nn/tasks.p
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -74,6 +75,7 @@ class DBLEngine:
         # off when a specific conv implementation is forced or every top-level layer output must exist (parity tests)
         self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
         self.fuse_stem = self.fuse_thin and not keep_layers
+        self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
         # run on `lanes` streams: inside a captured CUDA graph they become parallel branches, so small kernels overlap
@@ -207,7 +209,7 @@ class DBLEngine:
         """Bottleneck.forward (block.py:344-357)"""
         c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
         add = shortcut and x.c == y.c
-        if self.fuse_thin and add and x.c in (16, 32, 64) and c_ * 2 == x.c and x.buf.data_ptr() != y.buf.data_ptr() \
+        if self.fuse_thin and add and x.c in (16, 32, 64) and x.c <= self.fuse_bn_max_c and c_ * 2 == x.c and x.buf.data_ptr() != y.buf.data_ptr() \
                 and self.sd[p + ".cv1.conv.weight"].shape[-1] == 3 and self.sd[p + ".cv2.conv.weight"].shape[-1] == 3:
             # cv1 -> cv2 -> +x in one kernel, hidden tensor in shared memory (csrc/conv_mma.cu)
             w1, b1 = _fold(self.sd[p + ".cv1.conv.weight"], self.sd, p + ".cv1.bn")
