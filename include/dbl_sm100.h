@@ -162,6 +162,29 @@ typedef struct dbl_head_levels {
  * dist2bbox (tal.py:348-357) + sigmoid.  y: f32 [B][4+nc][A] exactly like the reference's first output. */
 int dbl_detect_decode(const dbl_head_levels* lv, float* y, dbl_stream_t stream);
 
+/* ---- fused Detect tail (csrc/head_fused.cu) ---------------------------------------------------------------------
+ * The last 1x1 convolutions of both head branches (nn/modules/head.py:86-100: nn.Conv2d(c2, 64, 1) and nn.Conv2d(c3, nc, 1))
+ * + dbl_detect_decode + dbl_decode_filter in one kernel: the 64+nc fp32 logits per anchor never reach HBM.
+ *   f2 / f3: bf16 NHWC branch features (c2 = 64 and c3 channels); w2_packed / w3_packed: dbl_mma_pack_weights layout of the
+ *   [64][1][c2] and [ceil8(nc)][1][c3] weights (rows >= nc zero); b2 / b3: f32 biases.
+ * Outputs, each optional: level[i].logits (f32 NHWC, `logit_pitch` floats per pixel: what forward() returns as feats),
+ * y (f32 [B][4+nc][A], the reference's first output) and `cand` (filled exactly like dbl_decode_filter does). */
+typedef struct dbl_head_fused_level {
+    const void* f2;
+    const void* f3;
+    const void* w2_packed;
+    const void* w3_packed;
+    const float* b2;
+    const float* b3;
+    float* logits;
+    int32_t pitch2, pitch3, h, w;
+    float stride;
+} dbl_head_fused_level;
+typedef struct dbl_head_fused {
+    dbl_head_fused_level level[3];
+    int32_t num_levels, batch, nc, c2, c3, logit_pitch;
+} dbl_head_fused;
+
 /* Candidate lists: per image up to `cap` entries, unordered; pos = anchor*npos_per_anchor + k is the position the
  * entry has in the reference's filtered list and is the tie-break key of the stable sort. */
 typedef struct dbl_candidates {
@@ -182,6 +205,10 @@ int dbl_nms_filter(const float* pred, int batch, int nc, int anchors, int64_t st
 /* decode + filter fused: same candidates as dbl_detect_decode -> dbl_nms_filter without materialising y. */
 int dbl_decode_filter(const dbl_head_levels* lv, float conf_thres, int multi_label, const int32_t* classes,
                       int num_classes_kept, const dbl_candidates* cand, dbl_stream_t stream);
+/* 1 when dbl_head_decode has an instantiation for these branch widths / class count */
+int dbl_head_decode_supported(int c2, int c3, int nc);
+int dbl_head_decode(const dbl_head_fused* hd, float* y, float conf_thres, int multi_label, const int32_t* classes,
+                    int num_classes_kept, const dbl_candidates* cand, dbl_stream_t stream);
 /* non_max_suppression stage 2 (ops.py:281-297) + torchvision.ops.nms: stable descending sort, max_nms truncation,
  * boxes + cls*max_wh, greedy IoU suppression in strict fp32, max_det cut.
  *   out_rows f32 [B][max_det][6] (x1,y1,x2,y2,conf,cls), out_pos int32 [B][max_det], out_count int32 [B]

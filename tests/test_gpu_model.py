@@ -177,3 +177,18 @@ def test_fused_stem_engine_matches_layerwise_engine():
         assert float(d12[:, :4].flatten().quantile(0.99)) <= 1.5 and float(d12[:, 4:].max()) <= 5e-2
         if name == "f32":
             assert float(dref[:, :4].flatten().quantile(0.99)) <= 1.5 and float(dref[:, 4:].flatten().quantile(0.99)) <= 1e-2
+    # fused Detect tail (dbl_head_decode): feats, y and the candidate lists come from the same kernel and must agree
+    assert e_fused.head_fused is not None and e_layer.head_fused is None
+    y2, feats = e_fused.forward(x.cuda())
+    torch.cuda.synchronize()
+    hw = [tuple(f.shape[2:]) for f in feats]
+    y_from_feats = O.detect_decode(torch.cat([f.cpu().reshape(2, f.shape[1], -1) for f in feats], 2), hw, [8.0, 16.0, 32.0])
+    torch.testing.assert_close(y2.cpu(), y_from_feats, rtol=1e-3, atol=1e-3)
+    for kw in (dict(conf=0.25, iou=0.7), dict(conf=0.05, iou=0.5, multi_label=True), dict(conf=0.1, iou=0.6, classes=[0, 2])):
+        rows, counts, _ = e_fused.detect(x.cuda(), **kw)
+        torch.cuda.synchronize()
+        want, _ = N.non_max_suppression(y2.cpu().numpy(), kw["conf"], kw["iou"], max_det=300, multi_label=kw.get("multi_label", False),
+                                        classes=kw.get("classes"))
+        assert counts.tolist() == [len(w) for w in want], (kw, counts.tolist(), [len(w) for w in want])
+        for i, w in enumerate(want):
+            assert rows[i, : int(counts[i])].cpu().numpy().tobytes() == w.tobytes(), (kw, i)

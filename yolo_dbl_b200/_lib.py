@@ -39,6 +39,17 @@ class HeadLevels(C.Structure):
                 ("num_levels", C.c_int32), ("batch", C.c_int32), ("nc", C.c_int32), ("pitch", C.c_int32)]
 
 
+class HeadFusedLevel(C.Structure):
+    _fields_ = [("f2", C.c_void_p), ("f3", C.c_void_p), ("w2_packed", C.c_void_p), ("w3_packed", C.c_void_p), ("b2", C.c_void_p),
+                ("b3", C.c_void_p), ("logits", C.c_void_p), ("pitch2", C.c_int32), ("pitch3", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("stride", C.c_float)]
+
+
+class HeadFused(C.Structure):
+    _fields_ = [("level", HeadFusedLevel * 3), ("num_levels", C.c_int32), ("batch", C.c_int32), ("nc", C.c_int32),
+                ("c2", C.c_int32), ("c3", C.c_int32), ("logit_pitch", C.c_int32)]
+
+
 class Candidates(C.Structure):
     _fields_ = [("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("pos", C.c_void_p),
                 ("count", C.c_void_p), ("cap", C.c_int32), ("batch", C.c_int32)]
@@ -74,6 +85,8 @@ _SIGNATURES = {
     "dbl_nms_filter": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, _P,
                                  C.c_int, C.POINTER(Candidates), _P]),
     "dbl_decode_filter": (C.c_int, [C.POINTER(HeadLevels), C.c_float, C.c_int, _P, C.c_int, C.POINTER(Candidates), _P]),
+    "dbl_head_decode_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "dbl_head_decode": (C.c_int, [C.POINTER(HeadFused), _P, C.c_float, C.c_int, _P, C.c_int, C.POINTER(Candidates), _P]),
     "dbl_nms_sort_capacity": (C.c_size_t, [C.c_int]),
     "dbl_nms": (C.c_int, [C.POINTER(Candidates), C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
 }

@@ -75,6 +75,7 @@ class DBLEngine:
         # off when a specific conv implementation is forced or every top-level layer output must exist (parity tests)
         self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
         self.fuse_stem = self.fuse_thin and not keep_layers
+        self.fuse_head = self.fuse_thin and not keep_layers  # last head convs + decode + filter in one kernel (dbl_head_decode)
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
@@ -320,6 +321,10 @@ class DBLEngine:
         pitch = (64 + nc + 3) // 4 * 4
         self.head_pitch = pitch
         self.head: List[Act] = []
+        c3_all = sd[f"{p}.cv3.0.0.1.conv.weight"].shape[0]
+        c2_all = sd[f"{p}.cv2.0.0.conv.weight"].shape[0]
+        fused = self.fuse_head and bool(self.lib.dbl_head_decode_supported(c2_all, c3_all, nc))
+        self.head_fused = L.HeadFused() if fused else None
         for i, x in enumerate(xs):
             hd = self._alloc(x.h, x.w, pitch, torch.float32)
             self.head.append(hd)
@@ -327,7 +332,8 @@ class DBLEngine:
             b1, b2 = self._alloc(x.h, x.w, c2b), self._alloc(x.h, x.w, c2b)
             self._conv_bn(x, f"{p}.cv2.{i}.0", b1)
             self._conv_bn(b1, f"{p}.cv2.{i}.1", b2)
-            self._conv_bias(b2, f"{p}.cv2.{i}.2", hd.slice(0, 64))
+            if not fused:
+                self._conv_bias(b2, f"{p}.cv2.{i}.2", hd.slice(0, 64))
             c3 = sd[f"{p}.cv3.{i}.0.1.conv.weight"].shape[0]
             cur = x
             for j, cj in ((0, x.c), (1, c3)):
@@ -337,7 +343,26 @@ class DBLEngine:
                 self._dw(cur, wdw, bdw, d, 3, 1, 1, L.ACT_SILU, q + ".0")
                 cur = self._alloc(x.h, x.w, c3)
                 self._conv_bn(d, q + ".1", cur)
-            self._conv_bias(cur, f"{p}.cv3.{i}.2", hd.slice(64, nc))
+            if not fused:
+                self._conv_bias(cur, f"{p}.cv3.{i}.2", hd.slice(64, nc))
+                continue
+            # fused tail: the two final 1x1 convs + decode + filter run in dbl_head_decode (launched after the forward list)
+            w2 = sd[f"{p}.cv2.{i}.2.weight"].float()
+            w3 = sd[f"{p}.cv3.{i}.2.weight"].float()
+            ncp = (nc + 7) // 8 * 8
+            w3p = torch.zeros(ncp, w3.shape[1], 1, 1)
+            w3p[:nc] = w3
+            lvl = self.head_fused.level[i]
+            lvl.f2, lvl.f3 = b2.desc.data, cur.desc.data
+            lvl.pitch2, lvl.pitch3 = b2.buf.shape[3], cur.buf.shape[3]
+            lvl.w2_packed, lvl.w3_packed = L.ptr(self._pack_mma(w2)), L.ptr(self._pack_mma(w3p))
+            lvl.b2 = L.ptr(self._dev(sd[f"{p}.cv2.{i}.2.bias"], torch.float32))
+            lvl.b3 = L.ptr(self._dev(sd[f"{p}.cv3.{i}.2.bias"], torch.float32))
+            lvl.logits = hd.buf.data_ptr()
+            lvl.h, lvl.w = x.h, x.w
+        if fused:
+            hf = self.head_fused
+            hf.num_levels, hf.batch, hf.nc, hf.c2, hf.c3, hf.logit_pitch = len(xs), self.B, nc, c2_all, c3_all, pitch
 
     # ------------------------------------------------------------------------------------------------ stem
     def _stem_pair_ok(self) -> bool:
@@ -470,6 +495,12 @@ class DBLEngine:
             lv.data[i], lv.h[i], lv.w[i], lv.stride[i] = a.buf.data_ptr(), a.h, a.w, float(det.extra["strides"][i])
         lv.num_levels, lv.batch, lv.nc, lv.pitch = len(self.head), self.B, spec.nc, self.head_pitch
         self.levels = lv
+        if self.head_fused is not None:  # two descriptions of the fused tail: with logits (forward) and without (detect)
+            for i in range(len(self.head)):
+                self.head_fused.level[i].stride = float(det.extra["strides"][i])
+            self.head_fused_nolog = L.HeadFused.from_buffer_copy(self.head_fused)
+            for i in range(len(self.head)):
+                self.head_fused_nolog.level[i].logits = None
         self.y = torch.zeros(self.B, 4 + spec.nc, self.A, dtype=torch.float32, device=self.dev)
 
     # ------------------------------------------------------------------------------------------------ lanes
@@ -570,6 +601,10 @@ class DBLEngine:
                 main.wait_stream(streams[lane])
 
     def _launch_decode(self, stream: int):
+        if self.head_fused is not None:  # final head convs + decode in one kernel; also materialises the raw logits (feats)
+            L.check(self.lib.dbl_head_decode(C.byref(self.head_fused), self.y.data_ptr(), C.c_float(0.0), 0, None, 0, None, stream),
+                    "dbl_head_decode")
+            return
         L.check(self.lib.dbl_detect_decode(C.byref(self.levels), self.y.data_ptr(), stream), "dbl_detect_decode")
 
     def _post(self, key: tuple) -> dict:
@@ -596,8 +631,12 @@ class DBLEngine:
         conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = key
         d = self._post(key)
         ncls = len(classes) if classes else 0
-        L.check(self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]), ncls,
-                                           C.byref(d["cand"]), stream), "dbl_decode_filter")
+        if self.head_fused is not None:
+            L.check(self.lib.dbl_head_decode(C.byref(self.head_fused_nolog), None, C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]),
+                                             ncls, C.byref(d["cand"]), stream), "dbl_head_decode")
+        else:
+            L.check(self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]), ncls,
+                                               C.byref(d["cand"]), stream), "dbl_decode_filter")
         L.check(self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
                                  d["keys"].data_ptr(), d["rows"].data_ptr(), d["out_pos"].data_ptr(), d["out_count"].data_ptr(), stream),
                 "dbl_nms")
@@ -692,8 +731,12 @@ class DBLEngine:
                     d = self._post(post_key)
                     n = len(self.ops)
                     ev[n][0].record()
-                    self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
-                                               len(classes), C.byref(d["cand"]), st)
+                    if self.head_fused is not None:
+                        self.lib.dbl_head_decode(C.byref(self.head_fused_nolog), None, C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
+                                                 len(classes), C.byref(d["cand"]), st)
+                    else:
+                        self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
+                                                   len(classes), C.byref(d["cand"]), st)
                     ev[n][1].record()
                     ev[n + 1][0].record()
                     self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(agnostic), C.c_float(max_wh), int(max_nms), int(max_det),
@@ -707,8 +750,13 @@ class DBLEngine:
                 rows.append(dict(m, ms=acc[i] / reps))
             if post_key is not None:
                 no = 64 + self.spec.nc
-                rows.append(dict(what="decode_filter", kern="decode_filter", flops=0.0, bytes=float(self.B * self.A * no * 4),
-                                 ms=acc[len(self.ops)] / reps))
+                if self.head_fused is not None:
+                    c2, c3 = self.head_fused.c2, self.head_fused.c3
+                    rows.append(dict(what="head_decode", kern="head_decode", flops=2.0 * self.B * self.A * (c2 * 64 + c3 * self.spec.nc),
+                                     bytes=float(self.B * self.A * (c2 + c3) * 2), ms=acc[len(self.ops)] / reps))
+                else:
+                    rows.append(dict(what="decode_filter", kern="decode_filter", flops=0.0, bytes=float(self.B * self.A * no * 4),
+                                     ms=acc[len(self.ops)] / reps))
                 rows.append(dict(what="sort_nms", kern="sort_nms", flops=0.0, bytes=0.0, ms=acc[len(self.ops) + 1] / reps))
         return rows
 
