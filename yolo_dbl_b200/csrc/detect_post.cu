@@ -329,11 +329,64 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
     __shared__ float4 s_pbox[32];
     __shared__ unsigned s_kmask;
     __syncthreads();
-    // 4. greedy suppression, 32 candidates per round: warp 0 resolves the chunk sequentially (exactly the reference's
-    //    order), then the whole block applies the chunk's kept boxes to the tail in one pass.  `kept` / `cursor` are
-    //    block-uniform.
-    int cursor = 0, kept = 0;
-    while (kept < max_det && cursor < m) {
+    // 4. greedy suppression, 32 candidates per round.  "Pull" form (max_det <= 1024, the kept boxes fit shared memory): warp w
+    //    tests chunk member w against every box kept so far (lanes stride over the kept list) and against the later members
+    //    of its chunk (one IoU per lane -> one ballot = its row of the 32x32 chunk matrix); warp 0 then resolves the chunk in
+    //    order.  Every round costs ~kept/32 + 1 IoUs per thread and two barriers, independent of how long the tail is; the
+    //    older "push" form below (kept boxes applied to the whole tail each round) remains for max_det > 1024.
+    int kept = 0;
+    if (max_det <= 1024) {
+        float4* kbox = reinterpret_cast<float4*>(nms_smem);                     // [1024] kept boxes, class-offset
+        uint32_t* cmask = reinterpret_cast<uint32_t*>(nms_smem + 1024 * 16);    // [32] rows of the chunk matrix
+        uint32_t* calive = cmask + 32;                                          // chunk members no kept box suppresses
+        __shared__ int s_nkept;
+        if (tid == 0) s_nkept = 0, *calive = 0;
+        __syncthreads();
+        const int w = tid >> 5, lane = tid & 31;
+        for (int cursor = 0; cursor < m; cursor += 32) {
+            const int kept0 = s_nkept;  // block-uniform: written before the barrier that ended the previous round
+            if (kept0 >= max_det) break;
+            const int c = cursor + w, j = cursor + lane;
+            const bool valid = c < m;
+            const float4 bx = valid ? sbox[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ar = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+            bool hit = false;
+            for (int k = lane; k < kept0 && !hit; k += 32) {
+                const float4 kb = kbox[k];
+                hit = iou_exceeds(kb, __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y)), bx, ar, iou_thr);
+            }
+            const bool sup = __any_sync(0xffffffffu, hit);
+            const float4 q = j < m ? sbox[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float qa = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+            const unsigned row = __ballot_sync(0xffffffffu, valid && j < m && lane > w && iou_exceeds(bx, ar, q, qa, iou_thr));
+            if (lane == 0) {
+                cmask[w] = row;
+                if (valid && !sup) atomicOr(calive, 1u << w);
+            }
+            __syncthreads();
+            if (w == 0) {  // here q is the box of chunk member `lane`
+                const unsigned alive = *calive, myrow = cmask[lane];
+                unsigned removed = 0;
+                int k2 = kept0;
+                for (int l = 0; l < 32 && k2 < max_det; ++l) {
+                    const unsigned rl = __shfl_sync(0xffffffffu, myrow, l);
+                    if (((alive >> l) & 1u) && !((removed >> l) & 1u)) {  // uniform across the warp
+                        removed |= rl;
+                        const float kx = __shfl_sync(0xffffffffu, q.x, l), ky = __shfl_sync(0xffffffffu, q.y, l);
+                        const float kz = __shfl_sync(0xffffffffu, q.z, l), kw = __shfl_sync(0xffffffffu, q.w, l);
+                        if (lane == 0) s_keep[k2] = cursor + l, kbox[k2] = make_float4(kx, ky, kz, kw);
+                        ++k2;
+                    }
+                }
+                if (lane == 0) s_nkept = k2, *calive = 0;
+            }
+            __syncthreads();
+        }
+        kept = s_nkept;
+    }
+    // push form:
+    int cursor = 0;
+    while (max_det > 1024 && kept < max_det && cursor < m) {
         if (tid < 32) {
             const int c = cursor + tid;
             const bool alive = c < m && !dead[c];

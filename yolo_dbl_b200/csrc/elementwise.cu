@@ -66,14 +66,14 @@ __global__ void __launch_bounds__(256) dysample_kernel(const __nv_bfloat16* __re
                                                        int opitch, int ypitch, int groups) {
     pdl_launch_dependents();
     pdl_wait();
+    // grid (ceil(wo*cg/256), ho, n): the row and the image come from the block index, so the per-thread index math is one
+    // 32-bit division (ncu: the flat 64-bit version of this kernel was ALU-bound on its div/mod chains)
     const int cg = c / 8;
     const int ho = 2 * h, wo = 2 * w;
-    const long long total = (long long)n * ho * wo * cg;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int cgi = (int)(idx % cg);
-    const long long pix = idx / cg;
-    const int ox = (int)(pix % wo), oy = (int)((pix / wo) % ho), b = (int)(pix / ((long long)wo * ho));
+    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= wo * cg) return;
+    const int ox = tix / cg, cgi = tix - ox * cg;
+    const int oy = blockIdx.y, b = blockIdx.z;
     const int hh = oy >> 1, ww = ox >> 1, i = oy & 1, j = ox & 1;
     const int g = (cgi * 8) / (c / groups);
     const int m = g * 4 + i * 2 + j;
@@ -221,8 +221,8 @@ extern "C" int dbl_dysample(const dbl_tensor* x, const dbl_tensor* off, const db
     DBL_REQUIRE(y->n == x->n && y->h == 2 * x->h && y->w == 2 * x->w && y->c == x->c, DBL_E_ARG, "dbl_dysample: output shape");
     DBL_REQUIRE(groups > 0 && x->c % groups == 0 && (x->c / groups) % 8 == 0, DBL_E_UNSUPPORTED,
                 "dbl_dysample: channels per group must be a multiple of 8");
-    const long long total = (long long)y->n * y->h * y->w * (y->c / 8);
-    launch_k(dysample_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(s), 
+    DBL_REQUIRE(y->h <= 65535 && y->n <= 65535, DBL_E_UNSUPPORTED, "dbl_dysample: grid too large");
+    launch_k(dysample_kernel, dim3((unsigned)cdiv(y->w * (y->c / 8), 256), (unsigned)y->h, (unsigned)y->n), 256, 0, as_stream(s), 
         reinterpret_cast<const __nv_bfloat16*>(x->data), reinterpret_cast<const float*>(off->data),
         reinterpret_cast<__nv_bfloat16*>(y->data), x->n, x->h, x->w, x->c, x->pitch, off->pitch, y->pitch, groups);
     count_launch();

@@ -44,7 +44,7 @@ template <int C3, int NCP>
 struct HfCfg {
     static constexpr int C2 = 64, MPX = 128;
     static constexpr int G2 = C2 / 8, G3 = C3 / 8;
-    static constexpr int PS = MPX * 16;  // plane stride: 128 pixels x 16 bytes (bank-conflict free for ldmatrix and cp.async)
+    static constexpr int PS = (MPX + 1) * 16;  // plane stride = 16 mod 128 bytes: the 8 planes of one pixel (one quarter-warp of cp.async) hit 8 different bank groups
     static constexpr int NB2 = 8, NB3 = NCP / 8;
     static constexpr int KS2 = C2 / 16, KS3 = C3 / 16;
     static constexpr int W2B = KS2 * NB2 * 256, W3B = KS3 * NB3 * 256;
@@ -101,6 +101,43 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
     const uint32_t row16 = (uint32_t)(((lane & 7) + 8 * ((lane >> 3) & 1)) * 16);
     const uint32_t a_lane = row16 + (lane >= 16 ? K::PS : 0) + (uint32_t)warp * 256;  // this warp's 16 anchors
 
+    // ---------------- class branch first: C3 -> nc logits; thread t owns classes [t*2*NB3, (t+1)*2*NB3) ----------------
+    float acc3[K::NB3][4];
+#pragma unroll
+    for (int j = 0; j < K::NB3; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(sB3 + t * 2 * K::NB3 + 2 * j);
+        acc3[j][0] = acc3[j][2] = bb.x, acc3[j][1] = acc3[j][3] = bb.y;
+    }
+#pragma unroll
+    for (int ks = 0; ks < K::KS3; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(sA3 + a_lane + (uint32_t)(2 * ks) * K::PS, a);
+#pragma unroll
+        for (int j = 0; j < K::NB3; ++j) {
+            const uint2 bw = lds64(sW3 + (uint32_t)((ks * K::NB3 + j) * 256) + lane * 8);
+            mma16816(acc3[j], a, bw.x, bw.y);
+        }
+    }
+    // Cheap pre-filter: sigmoid is monotonic, so max_c sigmoid(l_c) = sigmoid(max_c l_c) up to an ulp of expf; a warp none of
+    // whose 16 anchors can reach the threshold (with a 1e-6 safety margin for that ulp) needs neither the 2*NB3 exact
+    // sigmoids per thread nor the box branch at all.  The exact per-class arithmetic below decides for everybody else.
+    const bool want_all = p.y != nullptr || L.logits != nullptr;
+    bool maybe = false;
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < K::NB3; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (t * 2 * K::NB3 + 2 * j + e < p.nc) m = fmaxf(m, acc3[j][2 * rh + e]);
+        }
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        maybe = maybe || (px0 + warp * 16 + g + 8 * rh < hw && sigmoid_exact(m) > p.conf - 1e-6f);
+    }
+    if (!want_all && !__any_sync(0xffffffffu, maybe)) return;
+
     // ---------------- box branch: 64 -> 64 logits = 4 sides x 16 DFL bins; thread t of a quad owns side t ----------------
     float acc2[K::NB2][4];
 #pragma unroll
@@ -118,42 +155,27 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
             mma16816(acc2[j], a, bw.x, bw.y);
         }
     }
-    // ---------------- class branch: C3 -> nc logits; thread t owns classes [t*2*NB3, (t+1)*2*NB3) ----------------
-    float acc3[K::NB3][4];
-#pragma unroll
-    for (int j = 0; j < K::NB3; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(sB3 + t * 2 * K::NB3 + 2 * j);
-        acc3[j][0] = acc3[j][2] = bb.x, acc3[j][1] = acc3[j][3] = bb.y;
-    }
-#pragma unroll
-    for (int ks = 0; ks < K::KS3; ++ks) {
-        uint32_t a[4];
-        ldsm_x4(sA3 + a_lane + (uint32_t)(2 * ks) * K::PS, a);
-#pragma unroll
-        for (int j = 0; j < K::NB3; ++j) {
-            const uint2 bw = lds64(sW3 + (uint32_t)((ks * K::NB3 + j) * 256) + lane * 8);
-            mma16816(acc3[j], a, bw.x, bw.y);
-        }
-    }
 
     // ---------------- per anchor: decode + filter (+ optional logits / y) ----------------
-#pragma unroll
+#pragma unroll 1
     for (int rh = 0; rh < 2; ++rh) {
         const int cell = px0 + warp * 16 + g + 8 * rh;
         const bool live = cell < hw;
         const int a = L.start + cell;
         float v[REG_MAX];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[2 * j] = acc2[j][2 * rh], v[2 * j + 1] = acc2[j][2 * rh + 1];
+        for (int j = 0; j < 8; ++j) v[2 * j] = rh ? acc2[j][2] : acc2[j][0], v[2 * j + 1] = rh ? acc2[j][3] : acc2[j][1];
+        float lg3[2 * K::NB3];
+#pragma unroll
+        for (int j = 0; j < K::NB3; ++j) lg3[2 * j] = rh ? acc3[j][2] : acc3[j][0], lg3[2 * j + 1] = rh ? acc3[j][3] : acc3[j][1];
         if (L.logits && live) {
             float* lp = L.logits + ((size_t)b * hw + cell) * p.lpitch;
 #pragma unroll
             for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(lp + t * 16)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 #pragma unroll
-            for (int j = 0; j < K::NB3; ++j) {
-                const int c = t * 2 * K::NB3 + 2 * j;
-                if (c < p.nc) lp[64 + c] = acc3[j][2 * rh];
-                if (c + 1 < p.nc) lp[64 + c + 1] = acc3[j][2 * rh + 1];
+            for (int i = 0; i < 2 * K::NB3; ++i) {
+                const int c = t * 2 * K::NB3 + i;
+                if (c < p.nc) lp[64 + c] = lg3[i];
             }
         }
         // scores of this thread's classes, best class of the anchor (lowest index among equal maxima, like the reference)
@@ -161,14 +183,11 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
         float best = -CUDART_INF_F;
         int bi = 0;
 #pragma unroll
-        for (int j = 0; j < K::NB3; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int c = t * 2 * K::NB3 + 2 * j + e;
-                const float s = c < p.nc ? sigmoid_exact(acc3[j][2 * rh + e]) : -CUDART_INF_F;
-                sc[2 * j + e] = s;
-                if (s > best) best = s, bi = c;
-            }
+        for (int i = 0; i < 2 * K::NB3; ++i) {
+            const int c = t * 2 * K::NB3 + i;
+            const float s = c < p.nc ? sigmoid_exact(lg3[i]) : -CUDART_INF_F;
+            sc[i] = s;
+            if (s > best) best = s, bi = c;
         }
 #pragma unroll
         for (int d = 1; d < 4; d <<= 1) {  // quad reduction; classes are ordered by t, so ties keep the lower t
