@@ -102,6 +102,16 @@ int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const float* bias
 int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int w, const float* w0, const float* b0, int c0,
                   const void* w1_packed, const float* b1, const dbl_tensor* y, dbl_stream_t stream);
 
+/* ---- fused depthwise-separable convolution (csrc/dsconv_mma.cu) -------------------------------------------------
+ * DSConv.forward (nn/modules/conv.py:91-108): y = SiLU(pw(dw(x)) + b_pw) [+|* r], depthwise k x k (pad (k-1)/2, stride 1|2) and
+ * pointwise 1x1 in ONE kernel; with dw_act = 1 the depthwise stage is DWConv + BN + SiLU (bias b_dw, Detect's class branch,
+ * nn/modules/head.py:93-100).  w_dw: f32 [k*k][cin]; w_pw_packed: dbl_mma_pack_weights of bf16 [cout][1][cin] (BN folded).
+ * Only the (k, stride, cin, cout) combinations dbl_dsconv_supported() reports are instantiated.  x and y must not alias
+ * (r may alias y). */
+int dbl_dsconv_supported(int k, int stride, int cin, int cout);
+int dbl_dsconv(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw_act, const void* w_pw_packed, const float* b_pw,
+               const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int epi, dbl_stream_t stream);
+
 /* ---- depthwise convolution ---------------------------------------------------------------------------------------
  * DSConv.dw (conv.py:96-99), DWConv (conv.py:128-133), LSKblock.conv0 / conv_spatial (LSKA.py:31-32).
  *   w: f32 [k*k][c]   bias: f32 [c] or NULL   pad = dil*(k-1)/2 */

@@ -400,3 +400,49 @@ TC4_CASES = [
 @pytest.mark.parametrize("case", TC4_CASES)
 def test_conv3x3_multi_accumulator_kernel(case):
     _run_conv_case(case, L.IMPL_TCGEN05_MULTI, seed=11)
+
+
+# ---- fused depthwise-separable convolution (csrc/dsconv_mma.cu) -----------------------------------------------------
+@pytest.mark.parametrize("k,s,cin,cout,dw_act,epi,n,h,w", [
+    (3, 1, 64, 64, 0, L.EPI_NONE, 2, 40, 40), (7, 1, 64, 64, 0, L.EPI_ADD, 2, 40, 40), (3, 1, 32, 32, 0, L.EPI_NONE, 1, 24, 36),
+    (7, 1, 32, 32, 0, L.EPI_ADD, 1, 40, 40), (3, 1, 128, 128, 0, L.EPI_NONE, 2, 20, 20), (7, 1, 128, 128, 0, L.EPI_ADD, 1, 20, 20),
+    (3, 2, 128, 128, 0, L.EPI_NONE, 1, 80, 80), (3, 2, 128, 256, 0, L.EPI_NONE, 2, 40, 40), (3, 1, 64, 80, 1, L.EPI_NONE, 1, 80, 80),
+    (3, 1, 80, 80, 1, L.EPI_NONE, 2, 40, 40), (3, 1, 128, 80, 1, L.EPI_NONE, 1, 40, 40), (3, 1, 256, 80, 1, L.EPI_NONE, 2, 20, 20),
+    (3, 1, 128, 64, 1, L.EPI_NONE, 1, 13, 19), (3, 1, 256, 64, 1, L.EPI_NONE, 1, 10, 10), (7, 1, 64, 64, 0, L.EPI_ADD, 1, 33, 50)])
+def test_dsconv_fused(k, s, cin, cout, dw_act, epi, n, h, w):
+    lib = L.require_device()
+    assert lib.dbl_dsconv_supported(k, s, cin, cout) == 1
+    g = torch.Generator().manual_seed(k * 100 + cin + cout)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wdw = torch.randn(cin, 1, k, k, generator=g) / k
+    bdw = torch.randn(cin, generator=g) * 0.3 if dw_act else None
+    wpw = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    bpw = torch.randn(cout, generator=g) * 0.3
+    d = F.conv2d(x, wdw, bdw, s, (k - 1) // 2, 1, cin)
+    if dw_act:
+        d = F.silu(d)
+    d = bf16_round(d)  # the depthwise result is held as bf16 in shared memory
+    ref = F.silu(F.conv2d(d, wpw, bpw))
+    r = bf16_round(torch.randn(ref.shape, generator=g)) if epi else None
+    if epi == L.EPI_ADD:
+        ref = ref + r
+    xbuf, xv = to_nhwc(x, pad_c=8, c_off=0)
+    ybuf, yv = empty_nhwc(n, ref.shape[2], ref.shape[3], cout, pad_c=16, c_off=8)
+    rv = None
+    if epi:
+        rbuf, rv = to_nhwc(r)
+    wd = wdw.reshape(cin, k * k).t().contiguous().to(dev())
+    bd = None if bdw is None else bdw.to(dev())
+    cout_, cin_ = wpw.shape[:2]
+    wdev = wpw.permute(0, 2, 3, 1).contiguous().to(dev(), torch.bfloat16)
+    nbytes = lib.dbl_mma_packed_bytes(cout_, cin_, 1)
+    wp = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev())
+    assert lib.dbl_mma_pack_weights(wdev.data_ptr(), cout_, cin_, 1, wp.data_ptr(), stream()) == 0
+    bp = bpw.to(dev())
+    rc = lib.dbl_dsconv(C.byref(xv), wd.data_ptr(), None if bd is None else bd.data_ptr(), dw_act, wp.data_ptr(), bp.data_ptr(),
+                        None if rv is None else C.byref(rv), C.byref(yv), k, s, epi, stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(ybuf, 8, cout), ref, f"dsconv k{k} s{s} {cin}->{cout}", abs_=3e-2)
+    assert bool((ybuf[..., :8].float() == -3.0).all()) and bool((ybuf[..., 8 + cout:].float() == -3.0).all())
+    assert lib.dbl_dsconv_supported(5, 1, 48, 24) == 0

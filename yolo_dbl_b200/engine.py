@@ -76,6 +76,10 @@ class DBLEngine:
         self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
         self.fuse_stem = self.fuse_thin and not keep_layers
         self.fuse_head = self.fuse_thin and not keep_layers  # last head convs + decode + filter in one kernel (dbl_head_decode)
+        # dw + pw of every DSConv / Detect class-branch pair in one kernel (dbl_dsconv).  Correct and tested, but measured
+        # SLOWER than the two-kernel form inside the multi-lane graph (13.7k vs 14.4k images/s: its large CTAs serialise
+        # fill -> depthwise -> pointwise at low occupancy), so it stays opt-in until the depthwise stage is pipelined.
+        self.fuse_ds = os.environ.get("DBL_FUSE_DS", "0") == "1"
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
@@ -196,10 +200,30 @@ class DBLEngine:
         self._emit(self.lib.dbl_dwconv2d, (C.byref(x.desc), L.ptr(wd), L.ptr(bd), C.byref(y.desc), k, s, d, act), what, "dwconv",
                    2.0 * npix * y.c * k * k, 2 * self.B * x.h * x.w * x.c + 2 * npix * y.c + 4 * k * k * y.c)
 
+    def _dsconv_fused(self, x: Act, wdw: torch.Tensor, bdw: Optional[torch.Tensor], wpw: torch.Tensor, bpw: torch.Tensor, y: Act,
+                      s: int, epi, r, what: str) -> bool:
+        """dw k x k (+bias+SiLU when bdw is given) -> pw 1x1 + bias + SiLU (+ residual) in one kernel (csrc/dsconv_mma.cu);
+        False when no instantiation exists or fusion is off -> the caller emits the two-kernel form"""
+        k, cin, cout = wdw.shape[-1], wdw.shape[0], wpw.shape[0]
+        if not (self.fuse_thin and self.fuse_ds and self.lib.dbl_dsconv_supported(k, s, cin, cout)) or x.buf.data_ptr() == y.buf.data_ptr():
+            return False
+        wd = self._dev(wdw.reshape(cin, k * k).t(), torch.float32)
+        bd = self._dev(bdw, torch.float32) if bdw is not None else None
+        wp, bp = self._pack_mma(wpw), self._dev(bpw, torch.float32)
+        npix = self.B * y.h * y.w
+        args = (C.byref(x.desc), L.ptr(wd), L.ptr(bd), 1 if bdw is not None else 0, L.ptr(wp), L.ptr(bp),
+                C.byref(r.desc) if r is not None else None, C.byref(y.desc), k, s, epi if r is not None else L.EPI_NONE)
+        nbytes = 2 * self.B * x.h * x.w * cin + 2 * npix * cout * (2 if r is not None else 1) + 4 * k * k * cin + 2 * cin * cout
+        self._emit(self.lib.dbl_dsconv, args, what, "dsconv", 2.0 * npix * cin * (k * k + cout), nbytes)
+        return True
+
     def _dsconv(self, x: Act, p: str, y: Act, s: int = 1, epi=L.EPI_NONE, r=None):
         """DSConv (conv.py:91-108): depthwise -> pointwise -> BN -> SiLU, BN folded into the pointwise GEMM"""
         wdw = self.sd[p + ".dw.weight"].float()
         k = wdw.shape[-1]
+        wf, bf = _fold(self.sd[p + ".pw.weight"], self.sd, p + ".bn")
+        if self._dsconv_fused(x, wdw, None, wf, bf, y, s, epi, r, p):
+            return
         t = self._alloc(x.h // s, x.w // s, x.c)
         self._dw(x, wdw, None, t, k, s, 1, L.ACT_NONE, p + ".dw")
         w, b = _fold(self.sd[p + ".pw.weight"], self.sd, p + ".bn")
@@ -339,10 +363,13 @@ class DBLEngine:
             for j, cj in ((0, x.c), (1, c3)):
                 q = f"{p}.cv3.{i}.{j}"
                 wdw, bdw = _fold(sd[q + ".0.conv.weight"], sd, q + ".0.bn")  # DWConv = Conv(g=c) + BN + SiLU
-                d = self._alloc(x.h, x.w, cj)
-                self._dw(cur, wdw, bdw, d, 3, 1, 1, L.ACT_SILU, q + ".0")
-                cur = self._alloc(x.h, x.w, c3)
-                self._conv_bn(d, q + ".1", cur)
+                nxt = self._alloc(x.h, x.w, c3)
+                wpw, bpw = _fold(sd[q + ".1.conv.weight"], sd, q + ".1.bn")
+                if not self._dsconv_fused(cur, wdw, bdw, wpw, bpw, nxt, 1, L.EPI_NONE, None, q):
+                    d = self._alloc(x.h, x.w, cj)
+                    self._dw(cur, wdw, bdw, d, 3, 1, 1, L.ACT_SILU, q + ".0")
+                    self._conv_bn(d, q + ".1", nxt)
+                cur = nxt
             if not fused:
                 self._conv_bias(cur, f"{p}.cv3.{i}.2", hd.slice(64, nc))
                 continue
