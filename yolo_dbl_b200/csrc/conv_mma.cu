@@ -105,16 +105,28 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
         const int per_img = p.tiles_x * p.tiles_y;
         const int img = tile / per_img, r = tile - img * per_img;
         const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
-        const __nv_bfloat16* ximg = p.x + (size_t)img * p.h * p.w * p.xpitch;
         const uint32_t dst0 = sIn + buf * K::IN_BYTES;
-        constexpr int ITEMS = (TH + 4) * K::WI * K::GI;
-        for (int i = tid; i < ITEMS; i += NT) {
-            const int gi = i % K::GI, pix = i / K::GI;
-            const int ly = pix / K::WI, lx = pix - ly * K::WI;
-            const int gy = oy0 - 2 + ly, gx = ox0 - 2 + lx;
-            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-            const __nv_bfloat16* src = ok ? ximg + ((size_t)gy * p.w + gx) * p.xpitch + gi * 8 : p.x;
-            cp_async16(dst0 + gi * K::PSI + pix * 16, src, ok);
+        // a thread keeps its (plane, column) and walks down the rows: per 16-byte item one bounds test, one pointer add and
+        // the cp.async (the flat item loop spent ~125 instructions per item on div/mod and 64-bit address arithmetic)
+        constexpr int ROW_ITEMS = K::WI * K::GI;
+        constexpr int COL_PASSES = (ROW_ITEMS + NT - 1) / NT;
+        constexpr int ROWS_PER_PASS = NT >= 2 * ROW_ITEMS ? NT / ROW_ITEMS : 1;
+#pragma unroll
+        for (int cp = 0; cp < COL_PASSES; ++cp) {
+            const int e = ROWS_PER_PASS > 1 ? tid % ROW_ITEMS : tid + cp * NT;
+            const int ly0 = ROWS_PER_PASS > 1 ? tid / ROW_ITEMS : 0;
+            if (e >= ROW_ITEMS || ly0 >= ROWS_PER_PASS) continue;
+            const int gi = e % K::GI, lx = e / K::GI;
+            const int gx = ox0 - 2 + lx;
+            const bool colok = gx >= 0 && gx < p.w;
+            const __nv_bfloat16* src = p.x + (((size_t)img * p.h + (oy0 - 2 + ly0)) * p.w + gx) * p.xpitch + gi * 8;
+            const size_t rstep = (size_t)ROWS_PER_PASS * p.w * p.xpitch;
+            uint32_t dst = dst0 + gi * K::PSI + (ly0 * K::WI + lx) * 16;
+            for (int ly = ly0; ly < TH + 4; ly += ROWS_PER_PASS) {
+                const bool ok = colok && (unsigned)(oy0 - 2 + ly) < (unsigned)p.h;
+                cp_async16(dst, ok ? src : p.x, ok);
+                src += rstep, dst += ROWS_PER_PASS * K::WI * 16;
+            }
         }
     };
 
@@ -163,8 +175,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
                 for (int rh = 0; rh < 2; ++rh) {
                     const int q = (m0 + mb) * 16 + g + 8 * rh;
                     const int hy = q / K::WI, hx = q - hy * K::WI;
-                    const int gy = oy0 - 1 + hy, gx = ox0 - 1 + hx;
-                    const bool inside = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;  // cv2 zero-pads cv1's OUTPUT
+                    const bool inside = (unsigned)(oy0 - 1 + hy) < (unsigned)p.h && (unsigned)(ox0 - 1 + hx) < (unsigned)p.w;  // cv2 zero-pads cv1's OUTPUT
                     uint32_t v[K::NB1];
 #pragma unroll
                     for (int j = 0; j < K::NB1; ++j)
@@ -176,6 +187,9 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
         __syncthreads();
 
         // ---------------- cv2 + residual -> global ----------------
+        // 64-bit address of the tile origin once per tile; per pixel a 32-bit offset (the tensor is < 2^31 elements per tile row span)
+        __nv_bfloat16* const ytile = p.y + (((size_t)img * p.h + oy0) * p.w + ox0) * p.ypitch + t * 2 * K::NB2;
+        const int rows_ok = p.h - oy0, cols_ok = min(TW, p.w - ox0);
         for (int m0 = warp * MB; m0 < K::M2; m0 += NWARPS * MB) {
             float acc[MB][K::NB2][4];
 #pragma unroll
@@ -192,8 +206,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
                 for (int rh = 0; rh < 2; ++rh) {
                     const int o = (m0 + mb) * 16 + g + 8 * rh;
                     const int oy = o / K::WI, ox = o - oy * K::WI;
-                    const int gy = oy0 + oy, gx = ox0 + ox;
-                    if (ox >= TW || gy >= p.h || gx >= p.w) continue;
+                    if (ox >= cols_ok || oy >= rows_ok) continue;
                     uint32_t res[K::NB2];
                     if (p.add) planar_load<K::NB2>(in, K::PSI, o + 2 * K::WI + 2, t, res);
                     uint32_t v[K::NB2];
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
                         }
                         v[j] = pack2(a, b);
                     }
-                    global_store<K::NB2>(p.y + (((size_t)img * p.h + gy) * p.w + gx) * p.ypitch + t * 2 * K::NB2, v);
+                    global_store<K::NB2>(ytile + (uint32_t)((oy * p.w + ox) * p.ypitch), v);
                 }
             }
         }
@@ -265,20 +278,30 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
         const int per_img = p.tiles_x * p.tiles_y;
         const int img = tile / per_img, r = tile - img * per_img;
         const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
-        const __nv_bfloat16* ximg = p.x + (size_t)img * p.h * p.wd * p.xpitch;
         const uint32_t dst0 = sIn + buf * K::IN_BYTES;
         constexpr int ROWS = S * TH + (S == 1 ? 2 : 1), COLS = S * TW + (S == 1 ? 2 : 1);  // input footprint of the tile
-        constexpr int ITEMS = ROWS * COLS * K::GI;
-        for (int i = tid; i < ITEMS; i += NT) {
-            const int gi = i % K::GI, pix = i / K::GI;
-            const int ly = pix / COLS, lx = pix - ly * COLS;
-            const int gy = S * oy0 - 1 + ly, gx = S * ox0 - 1 + lx;
-            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.wd;
-            const __nv_bfloat16* src = ok ? ximg + ((size_t)gy * p.wd + gx) * p.xpitch + gi * 8 : p.x;
-            uint32_t d;
-            if (S == 1) d = (uint32_t)((ly * K::WP + lx) * 16);
-            else d = (uint32_t)(((ly & 1) * 2 + (lx & 1)) * K::PARB + ((ly >> 1) * K::WP + (lx >> 1)) * 16);
-            cp_async16(dst0 + gi * K::PS + d, src, ok);
+        // (plane, column) fixed per thread, rows walked with a pointer increment (see bottleneck_mma_kernel)
+        constexpr int ROW_ITEMS = COLS * K::GI;
+        constexpr int COL_PASSES = (ROW_ITEMS + NT - 1) / NT;
+        constexpr int ROWS_PER_PASS = NT >= 2 * ROW_ITEMS ? NT / ROW_ITEMS : 1;
+#pragma unroll
+        for (int cp = 0; cp < COL_PASSES; ++cp) {
+            const int e = ROWS_PER_PASS > 1 ? tid % ROW_ITEMS : tid + cp * NT;
+            const int ly0 = ROWS_PER_PASS > 1 ? tid / ROW_ITEMS : 0;
+            if (e >= ROW_ITEMS || ly0 >= ROWS_PER_PASS) continue;
+            const int gi = e % K::GI, lx = e / K::GI;
+            const int gx = S * ox0 - 1 + lx;
+            const bool colok = gx >= 0 && gx < p.wd;
+            const __nv_bfloat16* src = p.x + (((size_t)img * p.h + (S * oy0 - 1 + ly0)) * p.wd + gx) * p.xpitch + gi * 8;
+            const size_t rstep = (size_t)ROWS_PER_PASS * p.wd * p.xpitch;
+            for (int ly = ly0; ly < ROWS; ly += ROWS_PER_PASS) {
+                const bool ok = colok && (unsigned)(S * oy0 - 1 + ly) < (unsigned)p.h;
+                uint32_t d;
+                if (S == 1) d = (uint32_t)((ly * K::WP + lx) * 16);
+                else d = (uint32_t)(((ly & 1) * 2 + (lx & 1)) * K::PARB + ((ly >> 1) * K::WP + (lx >> 1)) * 16);
+                cp_async16(dst0 + gi * K::PS + d, ok ? src : p.x, ok);
+                src += rstep;
+            }
         }
     };
 
@@ -302,6 +325,10 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
         const int img = tile / per_img, r = tile - img * per_img;
         const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
         const uint32_t in = sIn + buf * K::IN_BYTES;
+        const size_t tile0 = ((size_t)img * p.ho + oy0) * p.wo + ox0;  // 64-bit once per tile, 32-bit offsets per pixel
+        __nv_bfloat16* const ytile = p.y + tile0 * p.ypitch + t * 2 * K::NB;
+        const __nv_bfloat16* const rtile = p.r ? p.r + tile0 * p.rpitch + t * 2 * K::NB : nullptr;
+        const int rows_ok = min(TH, p.ho - oy0), cols_ok = min(TW, p.wo - ox0);
         for (int m0 = warp * MB; m0 < K::M; m0 += NWARPS * MB) {
             float acc[MB][K::NB][4];
 #pragma unroll
@@ -319,11 +346,10 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
                 for (int rh = 0; rh < 2; ++rh) {
                     const int o = (m0 + mb) * 16 + g + 8 * rh;
                     const int oy = o / K::WP, ox = o - oy * K::WP;
-                    const int gy = oy0 + oy, gx = ox0 + ox;
-                    if (ox >= TW || oy >= TH || gy >= p.ho || gx >= p.wo) continue;
-                    const size_t opix = ((size_t)img * p.ho + gy) * p.wo + gx;
+                    if (ox >= cols_ok || oy >= rows_ok) continue;
+                    const uint32_t opix = (uint32_t)(oy * p.wo + ox);  // relative to the tile origin
                     uint32_t res[K::NB];
-                    if (p.epi != DBL_EPI_NONE) global_load<K::NB>(p.r + opix * p.rpitch + t * 2 * K::NB, res);
+                    if (p.epi != DBL_EPI_NONE) global_load<K::NB>(rtile + opix * (uint32_t)p.rpitch, res);
                     uint32_t v[K::NB];
 #pragma unroll
                     for (int j = 0; j < K::NB; ++j) {
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
                         }
                         v[j] = pack2(a, b);
                     }
-                    global_store<K::NB>(p.y + opix * p.ypitch + t * 2 * K::NB, v);
+                    global_store<K::NB>(ytile + opix * (uint32_t)p.ypitch, v);
                 }
             }
         }
@@ -429,15 +455,19 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
     {
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)img * 3 * p.h * p.w;
         const size_t plane = (size_t)p.h * p.w;
-        for (int i = tid; i < K::RI * K::PI; i += NT) {
-            const int ly = i / K::PI, lx = i - ly * K::PI;
-            const int gy = 2 * oy0 - 2 + ly, gx = 2 * ox0 - 2 + lx;
+        // a thread keeps its column and walks down the rows (NT / PI rows per pass): no div/mod per pixel
+        static_assert(NT % K::PI == 0, "threads must cover whole input rows");
+        constexpr int RPP = NT / K::PI;
+        const int lx = tid % K::PI, ly0 = tid / K::PI;
+        const int gx = 2 * ox0 - 2 + lx;
+        const bool colok = gx >= 0 && gx < p.w;
+        const TIN* s = xin + (size_t)(2 * oy0 - 2 + ly0) * p.w + gx;
+        uint32_t dst = sIn + (uint32_t)((ly0 * K::PI + lx) * 8);
+        for (int ly = ly0; ly < K::RI; ly += RPP) {
             float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-            if (gy >= 0 && gy < p.h && gx >= 0 && gx < p.w) {
-                const TIN* s = xin + (size_t)gy * p.w + gx;
-                c0 = (float)__ldg(s), c1 = (float)__ldg(s + plane), c2 = (float)__ldg(s + 2 * plane);
-            }
-            sts64(sIn + i * 8, make_uint2(pack2(c0, c1), pack2(c2, 0.f)));
+            if (colok && (unsigned)(2 * oy0 - 2 + ly) < (unsigned)p.h) c0 = (float)__ldg(s), c1 = (float)__ldg(s + plane), c2 = (float)__ldg(s + 2 * plane);
+            sts64(dst, make_uint2(pack2(c0, c1), pack2(c2, 0.f)));
+            s += (size_t)RPP * p.w, dst += RPP * K::PI * 8;
         }
         // the few pixels past the last row that junk GEMM rows touch: keep them finite
         for (int i = K::RI * K::PI + tid; i < K::IN_BYTES / 8; i += NT) sts64(sIn + i * 8, make_uint2(0u, 0u));
@@ -482,8 +512,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
                     const int q = (m0 + mb) * 16 + g + 8 * rh;
                     const int ly = q / K::PI, lx = q - ly * K::PI;
                     if (ly >= K::R0 || lx >= K::W0) continue;
-                    const int gy = 2 * oy0 - 1 + ly, gx = 2 * ox0 - 1 + lx;
-                    const bool inside = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;  // layer 1 zero-pads layer 0's OUTPUT
+                    const bool inside = (unsigned)(2 * oy0 - 1 + ly) < (unsigned)p.h && (unsigned)(2 * ox0 - 1 + lx) < (unsigned)p.w;  // layer 1 zero-pads layer 0's OUTPUT
                     uint32_t v[K::NB0];
 #pragma unroll
                     for (int j = 0; j < K::NB0; ++j)
@@ -502,6 +531,8 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
         const bool hi = lane >= 16;
         const uint32_t a_lane = row16 + (C0 > 8 && hi ? K::PS0 : 0);
         constexpr int MB = 1;
+        __nv_bfloat16* const ytile = p.y + (((size_t)img * p.ho + oy0) * p.wo + ox0) * p.ypitch + t * 2 * K::NB1;
+        const int rows_ok = min(TH, p.ho - oy0), cols_ok = min(TW, p.wo - ox0);
         for (int m0 = warp * MB; m0 < K::M1; m0 += NWARPS * MB) {
             float acc[MB][K::NB1][4];
 #pragma unroll
@@ -514,12 +545,11 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
             for (int rh = 0; rh < 2; ++rh) {
                 const int o = m0 * 16 + g + 8 * rh;
                 const int oy = o / K::WP, ox = o - oy * K::WP;
-                const int gy = oy0 + oy, gx = ox0 + ox;
-                if (ox >= TW || oy >= TH || gy >= p.ho || gx >= p.wo) continue;
+                if (ox >= cols_ok || oy >= rows_ok) continue;
                 uint32_t v[K::NB1];
 #pragma unroll
                 for (int j = 0; j < K::NB1; ++j) v[j] = pack2(silu_fast(acc[0][j][2 * rh]), silu_fast(acc[0][j][2 * rh + 1]));
-                global_store<K::NB1>(p.y + (((size_t)img * p.ho + gy) * p.wo + gx) * p.ypitch + t * 2 * K::NB1, v);
+                global_store<K::NB1>(ytile + (uint32_t)((oy * p.wo + ox) * p.ypitch), v);
             }
         }
     }
