@@ -31,7 +31,7 @@
 
 namespace dbl {
 
-constexpr int T4_EPI_WARPS = 8;
+constexpr int T4_EPI_WARPS = 16;
 constexpr int T4_THREADS = 64 + 32 * T4_EPI_WARPS;  // warp 0 TMA producer, warp 1 MMA issuer, the rest epilogue
 constexpr int T4_MAX_STAGES = 6;
 constexpr int T4_MAX_ACC = 16;

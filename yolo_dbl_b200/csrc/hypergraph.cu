@@ -54,8 +54,8 @@ __global__ void hg_context_kernel(const __nv_bfloat16* __restrict__ x, float* __
     p[D + d] = mx;
 }
 
-// K2: prototypes and their folded forms.  grid (B), block 256.
-__global__ void __launch_bounds__(256) hg_proto_kernel(const float* __restrict__ part, dbl_hypergraph_weights wt, float* __restrict__ P,
+// K2: prototypes and their folded forms.  grid (B), block 1024 (one warp per output row: 32 warps keep 32 rows of loads in flight).
+__global__ void __launch_bounds__(1024) hg_proto_kernel(const float* __restrict__ part, dbl_hypergraph_weights wt, float* __restrict__ P,
                                                        float* __restrict__ cvec, int N, int D) {
     pdl_launch_dependents();
     pdl_wait();
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) hg_proto_kernel(const float* __restrict__
     for (int idx = threadIdx.x; idx < E * D; idx += blockDim.x) {  // P[e,i] = s * sum_o proto[e,o] * Wp[o,i]
         const int e = idx / D, i = idx % D;
         float acc = 0.f;
-        for (int o = 0; o < D; ++o) acc = fmaf(proto[e * D + o], __ldg(wt.pre_head_w + (size_t)o * D + i), acc);
+#pragma unroll 8
+        for (int o = 0; o < D; ++o) acc = fmaf(proto[e * D + o], __ldg(wt.pre_head_w + (size_t)o * D + i), acc);  // 8 loads in flight
         P[((size_t)b * E + e) * D + i] = acc * scale;
     }
     for (int e = warp; e < E; e += nwarp) {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_logits_kernel(const __nv_bflo
 }
 
 // K4a: softmax normalisation in place + partial He = A^T X over a token slice.  grid (HG_EDGE_SPLIT, B), block 256.
-constexpr int HG_EDGE_SPLIT = 8;
+constexpr int HG_EDGE_SPLIT = 32;  // token slices per image: short, latency-bound loops -> more CTAs and more loads in flight
 __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ logits,
                                                                const float* __restrict__ stat_part, float* __restrict__ He, int N, int D,
                                                                int E, int nblk, int pitch) {
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat
     float acc[HG_MAX_E];
 #pragma unroll
     for (int e = 0; e < HG_MAX_E; ++e) acc[e] = 0.f;
+#pragma unroll 4
     for (int n = n0 + r; n < n1; n += R) {
         const float xv = __bfloat162float(x[((size_t)b * N + n) * pitch + d]);
         const float* a = lg + (size_t)n * E;
@@ -221,8 +223,8 @@ __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat
     }
 }
 
-// K4b: He2 = GELU(He We^T + be), Q = He2 Wn^T.  grid (B), block 256.
-__global__ void __launch_bounds__(256) hg_edges_final_kernel(const float* __restrict__ He, dbl_hypergraph_weights wt, float* __restrict__ Q,
+// K4b: He2 = GELU(He We^T + be), Q = He2 Wn^T.  grid (B), block 1024.
+__global__ void __launch_bounds__(1024) hg_edges_final_kernel(const float* __restrict__ He, dbl_hypergraph_weights wt, float* __restrict__ Q,
                                                              int D) {
     pdl_launch_dependents();
     pdl_wait();
@@ -315,7 +317,7 @@ extern "C" int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights*
     auto* yp = reinterpret_cast<__nv_bfloat16*>(y->data);
 
     launch_k(hg_context_kernel, dim3(HG_CTX_SPLIT, B), D, 0, st, xp, f + L.ctx_part, N, D, x->pitch);
-    launch_k(hg_proto_kernel, B, 256, (2 * D + E * D) * sizeof(float), st, f + L.ctx_part, *wt, f + L.P, f + L.cvec, N, D);
+    launch_k(hg_proto_kernel, B, 1024, (2 * D + E * D) * sizeof(float), st, f + L.ctx_part, *wt, f + L.P, f + L.cvec, N, D);
     const size_t sm3 = ((size_t)E * D + 2 * E * (HG_TOK_BLOCK / 32)) * sizeof(float);
     launch_k(hg_logits_kernel, dim3(L.nblk, B), HG_TOK_BLOCK, sm3, st, xp, f + L.P, f + L.cvec, f + L.logits, f + L.stat_part, N, D, E,
                                                                  x->pitch);
@@ -324,7 +326,7 @@ extern "C" int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights*
     cudaError_t me = cudaMemsetAsync(f + L.He, 0, (size_t)B * E * D * sizeof(float), st);
     DBL_REQUIRE(me == cudaSuccess, DBL_E_CUDA, "dbl_hypergraph: memset failed: %s", cudaGetErrorString(me));
     launch_k(hg_edges_partial_kernel, dim3(HG_EDGE_SPLIT, B), 256, sm4, st, xp, f + L.logits, f + L.stat_part, f + L.He, N, D, E, L.nblk, x->pitch);
-    launch_k(hg_edges_final_kernel, B, 256, (size_t)2 * E * D * sizeof(float), st, f + L.He, *wt, f + L.Q, D);
+    launch_k(hg_edges_final_kernel, B, 1024, (size_t)2 * E * D * sizeof(float), st, f + L.He, *wt, f + L.Q, D);
     launch_k(hg_nodes_kernel, dim3(L.nblk, B), HG_TOK_BLOCK, ((size_t)E * D + D) * sizeof(float), st, 
         xp, f + L.logits, f + L.Q, wt->node_b, yp, N, D, E, x->pitch, y->pitch);
     count_launch(6);
