@@ -223,15 +223,19 @@ def main():
 
     from yolo_dbl_b200.parallel import gather_detections
 
+    d2h = torch.cuda.Stream(device=dev)
+
     def e2e_run(k, src):
         n = 0
-        for rows, counts in model.detect_stream((src[i & 1] for i in range(k)), **NMS):
-            if world > 1:  # the path's one collective: final gather of the fixed-capacity detections (NCCL all-gather)
-                g_rows, g_cnt = gather_detections(rows, counts, args.batch * world)
-                rows, counts = g_rows[rank * args.batch:(rank + 1) * args.batch], g_cnt[rank * args.batch:(rank + 1) * args.batch]
-            out_rows.copy_(rows, non_blocking=True)
-            out_cnt.copy_(counts, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads the result on the host every step
+        for rows, counts, ev in model.detect_stream((src[i & 1] for i in range(k)), with_event=True, **NMS):
+            d2h.wait_event(ev)  # this batch's result is complete; the next batch is already queued on the compute stream
+            with torch.cuda.stream(d2h):
+                if world > 1:  # the path's one collective: final gather of the fixed-capacity detections (NCCL all-gather)
+                    g_rows, g_cnt = gather_detections(rows, counts, args.batch * world)
+                    rows, counts = g_rows[rank * args.batch:(rank + 1) * args.batch], g_cnt[rank * args.batch:(rank + 1) * args.batch]
+                out_rows.copy_(rows, non_blocking=True)
+                out_cnt.copy_(counts, non_blocking=True)
+            d2h.synchronize()  # the caller reads the result on the host every step
             n += 1
         return n
 

@@ -137,21 +137,29 @@ class DBLBackend(nn.Module):
             x, conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms)
         return rows, counts
 
-    def detect_stream(self, batches, **nms):
-        """Generator over an iterable of host (pinned) or device batches: yields (rows, counts) per batch while the
-        host->device copy of the NEXT batch runs on a second stream (the analogue of predict(..., stream=True),
-        reference engine/predictor.py:219-304).  Yielded tensors are engine-owned: consume them before advancing."""
+    def detect_stream(self, batches, with_event: bool = False, **nms):
+        """Generator over an iterable of host (pinned) or device batches: yields (rows, counts) per batch -- the analogue of
+        predict(..., stream=True) (reference engine/predictor.py:219-304) -- software-pipelined two ways: the host->device
+        copy of batch i+1 runs on a copy stream while batch i computes, and batch i+1 is already QUEUED behind batch i when
+        batch i's result is handed out, so the GPU never idles while the caller reads a result.
+
+        The yielded tensors are one of two result slots: they stay valid until the generator has been advanced TWICE.
+        With ``with_event=True`` a third item is yielded, the CUDA event recorded when that batch's result was complete: a
+        caller that reads results on its own stream (``stream.wait_event(ev)``) overlaps its device->host copy with the
+        next batch; a caller that just uses the current stream needs nothing (stream order)."""
         it = iter(batches)
         nxt = next(it, None)
         if nxt is None:
             return
         nxt = self._prep(nxt)
         eng = self.engine(nxt.shape[0], nxt.shape[2], nxt.shape[3])
+        kw = {{"agnostic_nms": "agnostic"}.get(k, k): v for k, v in nms.items()}
         with torch.cuda.device(self._device):
             copy_stream = torch.cuda.Stream(device=self._device)
             staging = [torch.empty(nxt.shape, dtype=nxt.dtype, device=self._device) for _ in range(2)]
             ready = [None, None]
             done = [None, None]
+            out = [None, None]
 
             def stage(x, slot):
                 if staging[slot].dtype != x.dtype:
@@ -164,20 +172,29 @@ class DBLBackend(nn.Module):
                     ready[slot].record(copy_stream)
 
             stage(nxt, 0)
+            pending = None
             i = 0
             while nxt is not None:
                 slot = i & 1
+                cur = torch.cuda.current_stream(self._device)
+                cur.wait_event(ready[slot])
+                rows, counts, _ = eng.detect(staging[slot], **kw)
+                if out[slot] is None:
+                    out[slot] = (torch.empty_like(rows), torch.empty_like(counts))
+                out[slot][0].copy_(rows, non_blocking=True)  # result slot: the engine's own buffers are rewritten by batch i+1
+                out[slot][1].copy_(counts, non_blocking=True)
+                done[slot] = torch.cuda.Event()
+                done[slot].record(cur)
+                item = (out[slot][0], out[slot][1], done[slot]) if with_event else (out[slot][0], out[slot][1])
                 nxt = next(it, None)
                 if nxt is not None:
                     nxt = self._prep(nxt)
                     stage(nxt, slot ^ 1)
-                cur = torch.cuda.current_stream(self._device)
-                cur.wait_event(ready[slot])
-                rows, counts, _ = eng.detect(staging[slot], **{{"agnostic_nms": "agnostic"}.get(k, k): v for k, v in nms.items()})
-                done[slot] = torch.cuda.Event()
-                done[slot].record(cur)
-                yield rows, counts
+                if pending is not None:
+                    yield pending  # batch i-1, with batch i already queued behind it
+                pending = item
                 i += 1
+            yield pending
 
 
 # ---------------------------------------------------------------------------------------------------------------------
