@@ -255,14 +255,22 @@ def main():
     if rank == 0:
         rows = eng.profile_ops(reps=5, post_key=key)
         table = kernel_table(rows, peaks)
-        top = table[0]
+        top = table[0]  # the kernel (family) with the largest share of the step; per-launch averages below
         t_tensor, t_hbm = top["flops"] / (peaks["bf16_tflops_sustained"] * 1e12), top["bytes"] / (peaks["hbm_gbs"] * 1e9)
         bound = "tensor" if t_tensor > t_hbm else "hbm"
         ach, peak, unit = (top["tflops"], peaks["bf16_tflops_sustained"], "TFLOP/s") if bound == "tensor" else (top["gbs"], peaks["hbm_gbs"], "GB/s")
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of the same command (profiles/r01_ncu_traffic.json)
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top["kern"], {}).get("dram_bytes_per_launch")
+        n = max(1, top["launches"])
         roof = {"kernel": top["kern"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
-                "traffic": None, "launches_per_step": top["launches"], "share_of_step": round(top["share"], 3),
-                "algorithmic_bytes_per_step": top["bytes"], "algorithmic_flops_per_step": top["flops"], "peak_source": peaks["source"],
-                "note": "aggregate over every launch of this kernel family in one step; per-launch rows in the kernel table"}
+                "traffic": traffic, "launches_per_step": top["launches"], "share_of_step": round(top["share"], 3),
+                "avg_launch_us": round(top["ms"] * 1e3 / n, 2), "algorithmic_bytes_per_launch": round(top["bytes"] / n),
+                "algorithmic_flops_per_launch": round(top["flops"] / n), "peak_source": peaks["source"],
+                "tensor_frac": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4), "hbm_frac": round(top["gbs"] / peaks["hbm_gbs"], 4),
+                "note": "achieved = sum of algorithmic bytes (or flops) of this kernel's launches in one step / sum of their CUDA-event times; "
+                        "per-launch rows: --kernel-table"}
         if args.kernel_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             json.dump({"families": table, "launches": rows, "peaks": peaks}, open(args.kernel_table, "w"), indent=1)

@@ -67,6 +67,10 @@ int64_t dbl_launch_count(void);
 int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y,
                int k, int stride, int pad, int dil, int act, int epi, int impl, dbl_stream_t stream);
 
+/* Which kernel dbl_conv2d runs for this problem: 0 CUDA-core direct, 1 tcgen05 + TMA (1x1 GEMM / one box per tap), 3 tcgen05 halo reuse
+ * with resident weights, 4 tcgen05 halo reuse with multi-accumulator super-tiles; -1 for invalid tensors. */
+int dbl_conv2d_which(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil, int impl);
+
 /* Layer 0 of the graph (cfg/models/v13/yolov13_DBL.yaml:9, Conv [32,3,1]) fused with the input cast of
  * BasePredictor.preprocess (engine/predictor.py:116-134): x is the user's f32 NCHW image batch (n,3,h,w) in 0..1,
  * w f32 [cout][3][3][3], y bf16 NHWC, SiLU applied. */

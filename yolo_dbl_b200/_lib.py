@@ -64,6 +64,7 @@ _SIGNATURES = {
     "dbl_set_pdl": (C.c_int, [C.c_int]),
     "dbl_launch_count": (C.c_int64, []),
     "dbl_conv2d": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "dbl_conv2d_which": (C.c_int, [_TP, _TP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbl_stem_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
     "dbl_stem_conv_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _TP, C.c_int, _P]),
     "dbl_mma_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

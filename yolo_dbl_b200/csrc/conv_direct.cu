@@ -523,6 +523,19 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
     return check_launch("dbl_conv2d(direct)");
 }
 
+/* which kernel dbl_conv2d would run for this problem: 0 direct (CUDA cores), 1 conv_tc (TMA per tap / 1x1 GEMM), 3 conv_tc3 (halo reuse,
+ * resident weights), 4 conv_tc4 (halo reuse, multi-accumulator), -1 invalid.  Lets callers attribute time to the right kernel. */
+extern "C" int dbl_conv2d_which(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil, int impl) {
+    if (!valid_tensor(x) || !valid_tensor(y)) return -1;
+    const bool tc_ok = conv2d_tcgen05_eligible(x, nullptr, y, k, stride, pad, dil);
+    const bool tc3_ok = conv3x3_tc3_eligible(x, y, k, stride, pad, dil);
+    const bool tc4_ok = conv3x3_tc4_eligible(x, y, k, stride, pad, dil);
+    if (tc4_ok && (impl == DBL_IMPL_TCGEN05_MULTI || ((impl == DBL_IMPL_AUTO || impl == DBL_IMPL_TCGEN05) && conv3x3_tc4_preferred(x, y)))) return 4;
+    if (tc3_ok && (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && (!tc_ok || conv3x3_tc3_preferred(x, y, stride))))) return 3;
+    if ((impl == DBL_IMPL_TCGEN05 || impl == DBL_IMPL_TCGEN05_TMA || impl == DBL_IMPL_AUTO) && tc_ok) return 1;
+    return 0;
+}
+
 extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bias, const dbl_tensor* y, int k, int stride,
                             int dil, int act, dbl_stream_t stream) {
     DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w, DBL_E_ARG, "dbl_dwconv2d: null/invalid tensor");

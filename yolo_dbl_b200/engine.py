@@ -84,7 +84,7 @@ class DBLEngine:
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
         # run on `lanes` streams: inside a captured CUDA graph they become parallel branches, so small kernels overlap
-        self.n_lanes = max(1, int(lanes)) if use_graph else 1
+        self.n_lanes = max(1, int(os.environ.get("DBL_LANES", lanes))) if use_graph else 1
         self.sd = {k: v.detach().to("cpu") for k, v in state_dict.items()}
         self._keep: List[object] = []        # weights, ctypes structs, scratch: everything launches point at
         self.ops: List[Tuple[Callable, tuple, str]] = []
@@ -149,8 +149,9 @@ class DBLEngine:
         npix = self.B * y.h * y.w
         ysz = 2 if y.buf.dtype == torch.bfloat16 else 4
         nbytes = 2 * self.B * x.h * x.w * x.c + ysz * npix * y.c + 2 * w.numel() + 4 * y.c + (2 * npix * y.c if r is not None else 0)
-        tc = self.conv_impl != L.IMPL_DIRECT and x.c % 16 == 0 and k in (1, 3)
-        self._emit(self.lib.dbl_conv2d, args, what, "conv_tc" if tc else "conv_direct", 2.0 * npix * y.c * x.c * k * k, nbytes)
+        which = self.lib.dbl_conv2d_which(C.byref(x.desc), C.byref(y.desc), k, s, k // 2, 1, self.conv_impl)
+        kern = {0: "conv_direct", 1: "conv_tc_1x1" if k == 1 else "conv_tc_tma", 3: "conv_tc3", 4: "conv_tc4"}.get(which, "conv_direct")
+        self._emit(self.lib.dbl_conv2d, args, what, kern, 2.0 * npix * y.c * x.c * k * k, nbytes)
 
     def _pack_mma(self, w: torch.Tensor) -> torch.Tensor:
         """[Cout,Cin,3,3] f32 -> device buffer in MMA B-fragment order (dbl_mma_pack_weights)"""
