@@ -20,7 +20,7 @@
 
 namespace dbl {
 
-constexpr int TC_EPI_WARPS = 16;                     // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
+constexpr int TC_EPI_WARPS = 8;                      // 2 per TMEM lane group: one warp per scheduler cannot hide its own latencies
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, the rest epilogue
 constexpr int TC_MAX_STAGES = 8;
 constexpr int MAX_ACC = 8;
@@ -72,7 +72,7 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
 }
 
 template <int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A][stages x B][bias f32 cout_pad][barriers][tmem ptr]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -383,8 +383,14 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     p.n_tiles = cdiv(y->c, p.npad);
     // accumulator ring in TMEM: as many buffers as fit (<= MAX_ACC); two are not enough to hide the MMA -> epilogue ->
     // MMA latency chain when tiles are small
-    p.nacc = 512 / p.npad;
+    // Two CTAs per SM when the reduction is short (1x1 convs with K <= 128: a CTA owns only a handful of tiles, so its
+    // prologue / pipeline fill / drain are most of its life and a second resident CTA hides them): each then takes half of
+    // TMEM and a small stage ring.
+    const int kblocks_total = k * k * (x->c / ((x->c % 64 == 0) ? 64 : ((x->c % 32 == 0) ? 32 : 16)));
+    const bool two_ctas = kblocks_total <= 2;
+    p.nacc = (two_ctas ? 256 : 512) / p.npad;
     if (p.nacc > MAX_ACC) p.nacc = MAX_ACC;
+    if (p.nacc < 1) p.nacc = 1;
     int cols = 32;
     while (cols < p.nacc * p.npad) cols <<= 1;
     p.tmem_cols = cols;
@@ -405,6 +411,7 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     const size_t fixed = 1024 /*align slack*/ + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * TC_MAX_STAGES + 2 * MAX_ACC) * 8 + 16;
     int stages = (int)(((size_t)max_smem - fixed) / (p.a_bytes + p.b_bytes));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (two_ctas && stages > 4) stages = 4;
     DBL_REQUIRE(stages >= 2, DBL_E_UNSUPPORTED, "conv_tc: tile does not fit shared memory");
     p.stages = stages;
     p.bias = bias;
@@ -445,7 +452,8 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     }
     const size_t smem = fixed + (size_t)stages * (p.a_bytes + p.b_bytes);
     const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < num_sms ? total : num_sms;
+    const int cap = (two_ctas && smem <= (size_t)100 * 1024) ? 2 * num_sms : num_sms;
+    const int grid = total < cap ? total : cap;
     if (act == DBL_ACT_SILU)
         launch_k(conv_tc_kernel<DBL_ACT_SILU>, grid, TC_THREADS, smem, st, maps, p);
     else if (act == DBL_ACT_GELU)
