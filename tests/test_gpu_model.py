@@ -192,3 +192,48 @@ def test_fused_stem_engine_matches_layerwise_engine():
         assert counts.tolist() == [len(w) for w in want], (kw, counts.tolist(), [len(w) for w in want])
         for i, w in enumerate(want):
             assert rows[i, : int(counts[i])].cpu().numpy().tobytes() == w.tobytes(), (kw, i)
+
+
+def test_config5_1280_dense_nms_through_the_production_engine():
+    """BASELINE config 5: n-scale at 1280^2 (33 600 anchors > max_nms = 30 000), validator threshold conf = 0.001."""
+    spec = resolve(None, "n", 3)
+    sd = synth_state_dict(param_shapes(spec), 0)
+    x = synth_images(1, 1280, 1280, 6)
+    eng = DBLEngine(spec, sd, 1, 1280, 1280)
+    y, _ = eng.forward(x.cuda())
+    y = y.clone()
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (1, 7, 33600) and bool(torch.isfinite(y).all())
+    # The synthetic weights are calibrated for ~640^2 statistics; at 1280^2 the oracle's own activations grow to |x| ~ 60, so
+    # bf16 rounding noise is amplified like in the wide scales (teacher-forced per-layer error stays <= 2e-2, identical on the
+    # CUDA-core and tensor-core paths: tools/diag_res.py).  Free-running drift is held to the wide-scale bound; what this
+    # config is about -- 33 600 anchors, max_nms truncation, dense NMS -- is checked bit-exactly below.
+    y_ref, _ = O.forward(sd, x, "n")
+    rel = float((y.cpu() - y_ref).norm() / y_ref.norm())
+    print(f"1280^2: rel-L2 of y {rel:.4f}")
+    assert rel <= 0.25
+    for kw in (dict(conf=0.001, iou=0.7), dict(conf=0.001, iou=0.7, multi_label=True)):
+        rows, counts, _ = eng.detect(x.cuda(), **kw)
+        torch.cuda.synchronize()
+        want, _ = N.non_max_suppression(y.cpu().numpy(), kw["conf"], kw["iou"], max_det=300, multi_label=kw.get("multi_label", False))
+        assert counts.tolist() == [len(w) for w in want]
+        assert rows[0, : int(counts[0])].cpu().numpy().tobytes() == want[0].tobytes(), kw
+
+
+def test_config4_l_scale_production_engine():
+    """BASELINE config 4: the l width/depth of the same yaml (44.7 M parameters), production (fused) engine vs the oracle."""
+    spec = resolve(None, "l", 3)
+    sd = synth_state_dict(param_shapes(spec), 7)
+    x = synth_images(2, 192, 256, 8)
+    eng = DBLEngine(spec, sd, 2, 192, 256)
+    y, _ = eng.forward(x.cuda())
+    y = y.clone()
+    torch.cuda.synchronize()
+    y_ref, _ = O.forward(sd, x, "l")
+    assert bool(torch.isfinite(y).all())
+    rel = float((y.cpu() - y_ref).norm() / y_ref.norm())
+    print(f"l scale 192x256: rel-L2 of y {rel:.4f}")
+    assert rel <= 0.25  # free-running drift bound used for the wide scales (see module docstring)
+    rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
+    want, _ = N.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
+    assert counts.tolist() == [len(w) for w in want]
