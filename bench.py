@@ -105,7 +105,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 8
+    per_step = 32  # bounded sample of the 64-image step: ~0.8 s of CPU work per step on 16 threads
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, per_step, steps, warmup)
     sample = f"{per_step} images/step of the {args.batch}-image workload, {steps} steps after {warmup} warm-up, oracle port (torch CPU fp32 + C NMS)"
@@ -278,9 +278,10 @@ def main():
     # ---- CPU baseline (rank 0, N == 1 only): the oracle port on all host threads, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, 8, 3, 1)
+        ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, 64, 6, 1)
         cpu = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"24 images (3 steps x 8) of the {args.batch}-image workload after 1 warm-up step; oracle port: torch CPU fp32 forward + C NMS"}
+               "sample": f"384 images (6 steps x 64 = the full {args.batch}-image step) after 1 warm-up step, ~10 s of CPU work; oracle port: "
+                         "torch CPU fp32 forward + C NMS on all host threads"}
 
     if rank == 0:
         line = {
