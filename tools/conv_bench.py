@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--impl", type=int, default=L.IMPL_TCGEN05)
+    ap.add_argument("--n", type=int, default=0, help="override the batch size of every shape")
     a = ap.parse_args()
     lib = L.require_device()
     dev = torch.device("cuda:0")
@@ -45,6 +46,7 @@ def main():
     for name, (n, h, w, cin, cout, k, s, epi, ydt) in SHAPES.items():
         if a.only and a.only not in name:
             continue
+        n = a.n or n
         ho, wo = (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
         x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
         wt = (torch.randn(cout, k, k, cin, device=dev) / (cin * k * k) ** 0.5).to(torch.bfloat16)

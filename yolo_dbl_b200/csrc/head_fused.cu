@@ -179,13 +179,25 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
             }
         }
         // scores of this thread's classes, best class of the anchor (lowest index among equal maxima, like the reference)
+        // Only classes that can reach the anchor's best score need the exact sigmoid when just (best, class) is wanted: for a
+        // maximum logit m <= 8 two logits more than ~2e-4 apart never round to the same float sigmoid, so a 1e-3 window around m
+        // contains every class that could win or tie (ties keep the lowest index, like the reference); saturated scores (m > 8),
+        // multi_label and the y output take every class.
+        float mq = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < 2 * K::NB3; ++i)
+            if (t * 2 * K::NB3 + i < p.nc) mq = fmaxf(mq, lg3[i]);
+        mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 1));
+        mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, 2));
+        const float lo = (p.y == nullptr && !p.multi_label && mq <= 8.0f) ? mq - 1e-3f : -CUDART_INF_F;
         float sc[2 * K::NB3];
         float best = -CUDART_INF_F;
         int bi = 0;
 #pragma unroll
         for (int i = 0; i < 2 * K::NB3; ++i) {
             const int c = t * 2 * K::NB3 + i;
-            const float s = c < p.nc ? sigmoid_exact(lg3[i]) : -CUDART_INF_F;
+            float s = -CUDART_INF_F;
+            if (c < p.nc && lg3[i] >= lo) s = sigmoid_exact(lg3[i]);
             sc[i] = s;
             if (s > best) best = s, bi = c;
         }
