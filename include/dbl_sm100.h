@@ -81,6 +81,18 @@ int dbl_stem_conv(const float* x_nchw, int n, int h, int w_, const float* w, con
 int dbl_stem_conv_u8(const uint8_t* x_nchw, int n, int h, int w_, const float* w, const float* bias, const dbl_tensor* y,
                      int stride, dbl_stream_t stream);
 
+/* ---- image-source pre-process -----------------------------------------------------------
+ * LetterBox.__call__ (data/augment.py:1558-1600, auto=False, centre, pad value 114) + BGR->RGB + HWC->CHW of
+ * BasePredictor.preprocess (engine/predictor.py:116-134) for a batch of uint8 HWC BGR images of different sizes in one launch; the
+ * bilinear resize repeats cv2.resize(INTER_LINEAR)'s 8-bit fixed-point arithmetic.  `table_dev` is a DEVICE array of `batch`
+ * descriptors (src = device pointer to the image, pitch = bytes per source row, new_h/new_w = resized size, top/left = where it
+ * goes inside the H x W output).  dst: uint8 NCHW (batch,3,H,W), RGB -- exactly what dbl_stem_pair(x_is_u8 = 1) consumes. */
+typedef struct dbl_lb_image {
+    const void* src;
+    int32_t h, w, pitch, new_h, new_w, top, left, reserved;
+} dbl_lb_image;
+int dbl_letterbox_u8(const dbl_lb_image* table_dev, int batch, uint8_t* dst_nchw, int H, int W, int pad_value, dbl_stream_t stream);
+
 /* ---- thin high-resolution layers: warp-level MMA kernels (csrc/conv_mma.cu) --------------------------------------
  * Layers whose arithmetic intensity is far below the B200 ridge (3..64 channels at 640^2..80^2) are HBM-bound; these
  * entry points fuse neighbouring reference modules so every activation crosses HBM once.

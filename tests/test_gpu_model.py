@@ -237,3 +237,55 @@ def test_config4_l_scale_production_engine():
     rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
     want, _ = N.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
     assert counts.tolist() == [len(w) for w in want]
+
+
+def _synth_bgr(h0, w0, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h0 // 8 + 2, w0 // 8 + 2, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((8, 8, 1), np.float32))[:h0, :w0]
+    return np.clip(img + rng.normal(0, 12, img.shape), 0, 255).astype(np.uint8)
+
+
+def test_letterbox_kernel_bit_exact_vs_oracle_and_reference_golden():
+    """dbl_letterbox_u8: integer work -> bit-exact against the oracle's fixed-point restatement of
+    LetterBox/cv2.resize; against the reference's own cv2 output the oracle's stated tolerance applies (<= 1 grey level on <= 0.5 %)."""
+    import letterbox_oracle as LB
+
+    m = DBLBackend.synthetic("n", 3, seed=0, device="cuda:0")
+    # ragged batch: down/up-scaling, identity, odd sizes, a 1-pixel-wide strip, in one launch
+    sizes = [(150, 260), (50, 37), (96, 128), (97, 131), (301, 299), (480, 640), (1080, 1920), (17, 400), (3, 5)]
+    imgs = [_synth_bgr(h, w, 100 + i) for i, (h, w) in enumerate(sizes)]
+    for shape in [(96, 128), (160, 160), (640, 640)]:
+        got = m.preprocess(imgs, shape).cpu().numpy()
+        want = LB.preprocess(imgs, shape)
+        assert got.shape == want.shape and got.dtype == np.uint8
+        np.testing.assert_array_equal(got, want)
+    for name in ["down_wide", "up_tall", "same", "odd", "square_down"]:
+        g = np.load(os.path.join(GOLDEN, f"letterbox_{name}.npz"))
+        shape = tuple(int(v) for v in g["shape"])
+        got = m.preprocess([g["img"]], shape).cpu().numpy()[0]
+        ref = np.ascontiguousarray(g["out"][..., ::-1].transpose(2, 0, 1))
+        d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+        assert int(d.max()) <= 1 and float((d > 0).mean()) <= 5e-3
+
+
+def test_predict_on_image_sources_scales_boxes_back_like_the_reference():
+    """YOLO.predict(list of HWC BGR uint8 images): GPU letterbox -> detect -> scale_boxes, vs the same steps through the oracle."""
+    import letterbox_oracle as LB
+
+    yolo = YOLO("yolov13n_DBL.yaml", nc=3)
+    imgs = [_synth_bgr(h, w, 7 + i) for i, (h, w) in enumerate([(240, 320), (500, 375), (128, 96)])]
+    res = yolo.predict(imgs, conf=0.05, imgsz=(128, 160))
+    x = torch.from_numpy(LB.preprocess(imgs, (128, 160)))
+    rows, counts = yolo.model.detect(x.pin_memory(), conf=0.05, iou=0.7)
+    rows, counts = rows.cpu().numpy(), counts.tolist()
+    assert len(res) == 3 and sum(counts) > 0
+    for i, (r, im) in enumerate(zip(res, imgs)):
+        assert r.orig_shape == im.shape[:2] and len(r) == counts[i]
+        want = rows[i, : counts[i]].copy()
+        want[:, :4] = LB.scale_boxes((128, 160), want[:, :4], im.shape[:2])
+        np.testing.assert_allclose(r.boxes.data.cpu().numpy(), want, rtol=1e-6, atol=1e-4)
+        b = r.boxes.xyxy.cpu().numpy()
+        assert (b[:, [0, 2]] >= 0).all() and (b[:, [0, 2]] <= im.shape[1]).all() and (b[:, [1, 3]] <= im.shape[0]).all()
+    one = yolo.predict(imgs[0], conf=0.05, imgsz=(128, 160))
+    assert len(one) == 1 and torch.equal(one[0].boxes.data, res[0].boxes.data)

@@ -50,6 +50,11 @@ class HeadFused(C.Structure):
                 ("c2", C.c_int32), ("c3", C.c_int32), ("logit_pitch", C.c_int32)]
 
 
+class LbImage(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("pitch", C.c_int32), ("new_h", C.c_int32), ("new_w", C.c_int32),
+                ("top", C.c_int32), ("left", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Candidates(C.Structure):
     _fields_ = [("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("pos", C.c_void_p),
                 ("count", C.c_void_p), ("cap", C.c_int32), ("batch", C.c_int32)]
@@ -74,6 +79,7 @@ _SIGNATURES = {
     "dbl_stem_pair": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _TP, _P]),
     "dbl_dsconv_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbl_dsconv": (C.c_int, [_TP, _P, _P, C.c_int, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, _P]),
+    "dbl_letterbox_u8": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_dwconv2d": (C.c_int, [_TP, _P, _P, _TP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_avgpool2": (C.c_int, [_TP, _TP, _P]),
     "dbl_upsample2_nearest": (C.c_int, [_TP, _TP, _P]),

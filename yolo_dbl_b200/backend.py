@@ -24,6 +24,30 @@ from .engine import DBLEngine
 from .synth import synth_state_dict
 
 
+def letterbox_params(h0: int, w0: int, H: int, W: int):
+    """LetterBox geometry (reference data/augment.py:1564-1590; auto=False, scaleup, centre): (new_h, new_w, top, left, gain)"""
+    r = min(H / h0, W / w0)
+    new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
+    dw, dh = (W - new_w) / 2, (H - new_h) / 2
+    return new_h, new_w, int(round(dh - 0.1)), int(round(dw - 0.1)), r
+
+
+def scale_boxes_(rows: torch.Tensor, img1_shape, img0_shape) -> torch.Tensor:
+    """ops.scale_boxes + clip_boxes (reference utils/ops.py:92-127, 319-338) on the xyxy columns of `rows`, in place, fp32"""
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    rows[..., 0] -= pad[0]
+    rows[..., 1] -= pad[1]
+    rows[..., 2] -= pad[0]
+    rows[..., 3] -= pad[1]
+    rows[..., :4] /= gain
+    rows[..., 0].clamp_(0, img0_shape[1])
+    rows[..., 1].clamp_(0, img0_shape[0])
+    rows[..., 2].clamp_(0, img0_shape[1])
+    rows[..., 3].clamp_(0, img0_shape[0])
+    return rows
+
+
 class DBLBackend(nn.Module):
     """B200 executor behind the reference's model interface.
 
@@ -128,6 +152,42 @@ class DBLBackend(nn.Module):
         return y.clone(), [f.clone() for f in feats]
 
     __call__ = forward
+
+    def preprocess(self, images, imgsz=(640, 640)) -> torch.Tensor:
+        """Image sources: a list of HWC BGR uint8 arrays (what cv2.imread returns, any sizes) -> uint8 [B,3,H,W] RGB on the device,
+        letterboxed like BasePredictor.pre_transform / LetterBox (reference engine/predictor.py:145-161, data/augment.py:1558-1600).
+        One pinned upload of the raw pixels + ONE kernel (dbl_letterbox_u8) for the whole batch; the float cast and /255 happen
+        inside the stem kernel."""
+        import numpy as np
+
+        lib = L.require_device()
+        H, W = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        if H % 32 or W % 32:
+            raise ValueError("imgsz must be a multiple of 32")
+        arrs = [np.ascontiguousarray(im) for im in images]
+        for a in arrs:
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("expected HWC uint8 images with 3 channels (BGR)")
+        sizes = [a.size for a in arrs]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 255) // 256 * 256)
+        host = torch.empty(offs[-1], dtype=torch.uint8).pin_memory()
+        for a, o in zip(arrs, offs):
+            host[o:o + a.size] = torch.from_numpy(a.reshape(-1))
+        with torch.cuda.device(self._device):
+            raw = host.to(self._device, non_blocking=True)
+            tab = (L.LbImage * len(arrs))()
+            for k, (a, o) in enumerate(zip(arrs, offs)):
+                h0, w0 = a.shape[:2]
+                new_h, new_w, top, left, _ = letterbox_params(h0, w0, H, W)
+                tab[k] = L.LbImage(raw.data_ptr() + o, h0, w0, w0 * 3, new_h, new_w, top, left, 0)
+            tab_host = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).pin_memory()
+            tab_dev = tab_host.to(self._device, non_blocking=True)
+            out = torch.empty(len(arrs), 3, H, W, dtype=torch.uint8, device=self._device)
+            L.check(lib.dbl_letterbox_u8(tab_dev.data_ptr(), len(arrs), out.data_ptr(), H, W, 114, L.current_stream()), "dbl_letterbox_u8")
+            out._dbl_keep = (raw, tab_dev)  # stream-ordered: keep the sources alive until the caller drops the result
+        return out
 
     def detect(self, x, conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None,
                max_nms=30000):
@@ -340,7 +400,7 @@ class YOLO:
     def predict(self, source, conf=None, iou=None, max_det=None, agnostic_nms=None, classes=None, **kw) -> List[Results]:
         o = self.overrides
         if not isinstance(source, torch.Tensor):
-            raise NotImplementedError("pass a BCHW float tensor in 0..1 (LoadTensor source)")
+            return self._predict_images(source, conf, iou, max_det, agnostic_nms, classes, kw.get("imgsz", 640))
         rows, counts = self.model.detect(
             source, conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
             agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
@@ -348,5 +408,28 @@ class YOLO:
         counts = counts.tolist()
         shape = tuple(source.shape[2:])
         return [Results(rows[i, : counts[i]].clone(), shape, self.names, path=f"image{i}.jpg") for i in range(len(counts))]
+
+    def _predict_images(self, source, conf, iou, max_det, agnostic_nms, classes, imgsz) -> List[Results]:
+        """Image sources (one HWC BGR uint8 array or a list of them): GPU letterbox -> detect -> boxes scaled back to each original
+        image (DetectionPredictor.postprocess, reference models/yolo/detect/predict.py:23-41)."""
+        import numpy as np
+
+        images = [source] if isinstance(source, np.ndarray) else list(source)
+        if not images or not all(isinstance(im, np.ndarray) for im in images):
+            raise NotImplementedError("pass a BCHW tensor, one HWC uint8 image or a list of HWC uint8 images")
+        o = self.overrides
+        H, W = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        x = self.model.preprocess(images, (H, W))
+        rows, counts = self.model.detect(
+            x, conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
+            agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
+            max_det=o["max_det"] if max_det is None else max_det, classes=classes if classes is not None else o["classes"])
+        counts = counts.tolist()
+        out = []
+        for i, im in enumerate(images):
+            r = rows[i, : counts[i]].clone()
+            scale_boxes_(r, (H, W), im.shape[:2])
+            out.append(Results(r, tuple(im.shape[:2]), self.names, path=f"image{i}.jpg"))
+        return out
 
     __call__ = predict

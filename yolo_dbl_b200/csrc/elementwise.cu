@@ -182,6 +182,61 @@ static int launch_resample(int mode, const dbl_tensor* x, const dbl_tensor* y, c
     return check_launch(name);
 }
 
+
+// ---- letterbox pre-process ---------------------------------------------------------------------------------------------
+// LetterBox.__call__ (data/augment.py:1558-1600; auto=False, centre, pad 114) + the BGR->RGB / HWC->CHW of BasePredictor.preprocess
+// (engine/predictor.py:127-129) for a batch of uint8 images of DIFFERENT sizes in one launch.  The bilinear resize repeats the
+// fixed-point arithmetic of cv2.resize(INTER_LINEAR) for 8-bit images: 11-bit coefficients cvRound(f * 2048), horizontal pass in
+// int32, vertical pass (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+__device__ __forceinline__ void lb_coeff(int d, int n_out, int n_in, int& s0, int& s1, int& a0, int& a1) {
+    const double scale = (double)n_in / (double)n_out;
+    float f = (float)(((double)d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) f = 0.f, s = 0;
+    if (s >= n_in - 1) f = 0.f, s = n_in - 1;
+    a1 = __float2int_rn(f * 2048.f);
+    a0 = __float2int_rn((1.f - f) * 2048.f);
+    s0 = s, s1 = min(s + 1, n_in - 1);
+}
+
+__global__ void __launch_bounds__(256) letterbox_kernel(const dbl_lb_image* __restrict__ tab, uint8_t* __restrict__ dst, int H, int W, int pad) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const dbl_lb_image im = tab[b];
+    int r = pad, g = pad, bl = pad;
+    const int ry = y - im.top, rx = x - im.left;
+    if (ry >= 0 && ry < im.new_h && rx >= 0 && rx < im.new_w) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(im.src);
+        if (im.new_h == im.h && im.new_w == im.w) {
+            const uint8_t* px = src + (size_t)ry * im.pitch + rx * 3;
+            bl = px[0], g = px[1], r = px[2];
+        } else {
+            int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
+            lb_coeff(rx, im.new_w, im.w, x0, x1, ax0, ax1);
+            lb_coeff(ry, im.new_h, im.h, y0, y1, ay0, ay1);
+            const uint8_t* p00 = src + (size_t)y0 * im.pitch + x0 * 3;
+            const uint8_t* p01 = src + (size_t)y0 * im.pitch + x1 * 3;
+            const uint8_t* p10 = src + (size_t)y1 * im.pitch + x0 * 3;
+            const uint8_t* p11 = src + (size_t)y1 * im.pitch + x1 * 3;
+            int out[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int r0 = (int)p00[c] * ax0 + (int)p01[c] * ax1, r1 = (int)p10[c] * ax0 + (int)p11[c] * ax1;
+                const int v = (((ay0 * (r0 >> 4)) >> 16) + ((ay1 * (r1 >> 4)) >> 16) + 2) >> 2;
+                out[c] = min(max(v, 0), 255);
+            }
+            bl = out[0], g = out[1], r = out[2];
+        }
+    }
+    uint8_t* d = dst + ((size_t)b * 3 * H + y) * W + x;  // NCHW, RGB
+    d[0] = (uint8_t)r;
+    d[(size_t)H * W] = (uint8_t)g;
+    d[(size_t)2 * H * W] = (uint8_t)bl;
+}
+
 }  // namespace dbl
 
 using namespace dbl;
@@ -254,4 +309,13 @@ extern "C" int dbl_lsk_gate(const dbl_tensor* attn, const dbl_tensor* agg, const
         reinterpret_cast<__nv_bfloat16*>(y->data), y->n, y->h, y->w, y->c, attn->pitch, agg->pitch, y->pitch);
     count_launch();
     return check_launch("dbl_lsk_gate");
+}
+
+extern "C" int dbl_letterbox_u8(const dbl_lb_image* table_dev, int batch, uint8_t* dst_nchw, int H, int W, int pad_value, dbl_stream_t s) {
+    DBL_REQUIRE(table_dev && dst_nchw && batch > 0 && H > 0 && W > 0 && pad_value >= 0 && pad_value <= 255, DBL_E_ARG,
+                "dbl_letterbox_u8: null/invalid argument");
+    DBL_REQUIRE(H <= 65535 && batch <= 65535, DBL_E_UNSUPPORTED, "dbl_letterbox_u8: grid too large");
+    launch_k(letterbox_kernel, dim3((unsigned)cdiv(W, 256), (unsigned)H, (unsigned)batch), 256, 0, as_stream(s), table_dev, dst_nchw, H, W, pad_value);
+    count_launch();
+    return check_launch("dbl_letterbox_u8");
 }
