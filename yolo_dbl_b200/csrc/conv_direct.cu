@@ -414,10 +414,145 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
     }
 }
 
+// Third generation of the tiled depthwise kernel (v1 above: issue slots 47 % busy at 14 resident warps per SM, 128
+// registers).  Same idea -- one CTA = one (image, spatial tile, channel block), input tile + halo staged once with
+// 16-byte cp.async (zero fill = padding), filter block next to it as f32 -- but
+//  * a thread owns FOUR channels (one 8-byte shared-memory load per tap row) and R = 8 (or 4) output rows: the K filter
+//    taps of the current filter column are 28 registers instead of 56, the whole kernel fits ~80 registers, so 4-5 CTAs
+//    (20-25 warps) are resident per SM;
+//  * packed fp32 FMAs (fma.rn.f32x2, SASS FFMA2) over channel pairs: a bf16x2 word unpacks straight into an aligned
+//    register pair {w << 16, w & 0xffff0000}, the filter is read as float2.  Half the FMA issue slots, which leaves room
+//    for the LDS / unpack instructions next to the FMA pipe that is the real bound (49 FMA per output for 7x7);
+//  * staging index math through float reciprocals instead of two integer divisions per 16-byte chunk.
+// Numerics are those of v1 (IEEE fma per element, same summation order).
+// G4 = 4-channel groups per CTA (even: the staging copy moves 16 bytes = two groups); threads = G4 * tw * ty.
+template <int K, int S, int D, int R>
+__global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int h, int wd,
+                                                           int c, int xpitch, int ho, int wo, int ypitch, int act, int G4, int tw, int ty,
+                                                           int tiles_x) {
+    extern __shared__ __align__(16) uint8_t dw_smem[];
+    pdl_launch_dependents();
+    constexpr int PAD = D * (K - 1) / 2;
+    constexpr int ROWS_T = (R - 1) * S + (K - 1) * D + 1;  // input rows one thread walks
+    const int th = ty * R;
+    const int ir = (th - 1) * S + (K - 1) * D + 1, ic = (tw - 1) * S + (K - 1) * D + 1;
+    const int img = blockIdx.z, cb = blockIdx.y;
+    const int oy0 = (blockIdx.x / tiles_x) * th, ox0 = (blockIdx.x % tiles_x) * tw;
+    const int c0 = cb * G4 * 4;
+    const int c_here = min(G4 * 4, c - c0);  // channels of this block (the last block may be short; a multiple of 8)
+    float* sw = reinterpret_cast<float*>(dw_smem);                        // [K*K][G4*4]
+    const uint32_t sx = smem_u32(dw_smem) + (uint32_t)(K * K * G4 * 16);  // [ir][ic][G4] x 8 bytes
+    const int nt = blockDim.x;
+    for (int i = threadIdx.x; i < K * K * G4 * 4; i += nt) {
+        const int tap = i / (G4 * 4), cc = i - tap * (G4 * 4);
+        sw[i] = (cc < c_here) ? w[(size_t)tap * c + c0 + cc] : 0.f;
+    }
+    pdl_wait();  // the filter block above is constant data; the activations are the previous kernel's output
+    {
+        const __nv_bfloat16* ximg = x + (size_t)img * h * wd * xpitch + c0;
+        const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+        const int G8 = G4 >> 1, g8_here = c_here >> 3;
+        const int chunks = ir * ic * G8;
+        // exact small-integer divisions through reciprocals ((q + 0.5) / d is never within float error of an integer)
+        const float inv_g = 1.0f / (float)G8, inv_ic = 1.0f / (float)ic;
+        for (int i = threadIdx.x; i < chunks; i += nt) {
+            const int pix = __float2int_rd(((float)i + 0.5f) * inv_g), g = i - pix * G8;
+            const int ly = __float2int_rd(((float)pix + 0.5f) * inv_ic), lx = pix - ly * ic;
+            const int gy = iy0 + ly, gx = ix0 + lx;
+            const bool ok = g < g8_here && gy >= 0 && gy < h && gx >= 0 && gx < wd;
+            cp_async16(sx + (uint32_t)i * 16, ok ? ximg + ((size_t)gy * wd + gx) * xpitch + g * 8 : x, ok);
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int g = threadIdx.x % G4, xi = (threadIdx.x / G4) % tw, ys = threadIdx.x / (G4 * tw);
+    if (ys >= ty || g * 4 >= c_here) return;
+    const int ox = ox0 + xi, oyb = oy0 + ys * R;
+    if (ox >= wo || oyb >= ho) return;
+    unsigned long long acc[R][2];
+    {
+        ulonglong2 b2 = make_ulonglong2(0ull, 0ull);
+        if (bias) b2 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c0 + g * 4));
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r][0] = b2.x, acc[r][1] = b2.y;
+    }
+    const uint32_t xbase = sx + (uint32_t)(((ys * R * S) * ic + xi * S) * G4 + g) * 8;
+    // the filter-column loop stays ROLLED (fully unrolled, v1 was instruction-fetch bound)
+#pragma unroll 1
+    for (int kx = 0; kx < K; ++kx) {
+        unsigned long long wk[K][2];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(sw + (ky * K + kx) * G4 * 4 + g * 4);
+            wk[ky][0] = w0.x, wk[ky][1] = w0.y;
+        }
+#pragma unroll
+        for (int iy = 0; iy < ROWS_T; ++iy) {
+            bool used = false;  // compile-time: does any of the R outputs read input row iy?
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int d = iy - r * S;
+                if (d >= 0 && d % D == 0 && d / D < K) used = true;
+            }
+            if (!used) continue;
+            uint32_t v0, v1;
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(xbase + (uint32_t)((iy * ic + kx * D) * G4) * 8));
+            const unsigned long long x0 = bf16x2_to_f32x2(v0), x1 = bf16x2_to_f32x2(v1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int d = iy - r * S;
+                if (d >= 0 && d % D == 0 && d / D < K) {
+                    ffma2(acc[r][0], x0, wk[d / D][0]);
+                    ffma2(acc[r][1], x1, wk[d / D][1]);
+                }
+            }
+        }
+    }
+    __nv_bfloat16* yp = y + (((size_t)img * ho + oyb) * wo + ox) * ypitch + c0 + g * 4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (oyb + r < ho) {
+            float f[4];
+            f32x2_split(acc[r][0], f[0], f[1]);
+            f32x2_split(acc[r][1], f[2], f[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[i] = act == DBL_ACT_SILU ? silu_fast(f[i]) : f[i];
+            *reinterpret_cast<uint2*>(yp + (size_t)r * wo * ypitch) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
+        }
+    }
+}
+
+// host-side tile choice for dwconv_tile3_kernel: enumerate (G4, tw, ty), keep 96..256 threads and <= 44 KB of shared
+// memory (>= 5 resident CTAs), minimise  padded outputs x K^2  (FMA work incl. tile padding)  +  4 x staged pixels
+// (halo amplification); 16 channels per CTA (32-byte = full-sector rows) preferred over 8.
+static bool dw_pick_tile3(int k, int s, int d, int R, int c, int ho, int wo, int* G4_, int* tw_, int* ty_, size_t* smem_) {
+    double best = 1e300;
+    bool found = false;
+    for (int G4 = 2; G4 <= 4; G4 += 2) {
+        if (G4 * 4 > c && G4 > 2) continue;  // a short last block is fine, a block wider than the tensor is not
+        for (int tw = 4; tw <= (wo < 64 ? wo : 64); ++tw)
+            for (int ty = 1; ty <= 8; ++ty) {
+                const int threads = G4 * tw * ty;
+                if (threads < 96 || threads > 256) continue;
+                const int th = ty * R;
+                const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
+                const size_t smem = (size_t)k * k * G4 * 16 + (size_t)ir * ic * G4 * 8;
+                if (smem > 44 * 1024) continue;
+                const int tx_n = cdiv(wo, tw), ty_n = cdiv(ho, th);
+                const double padded = (double)tx_n * tw * ty_n * th, staged = (double)tx_n * ty_n * ir * ic;
+                double cost = padded * k * k + 4.0 * staged * (G4 == 2 ? 1.5 : 1.0);
+                cost *= 1.0 + 0.02 * (256 - threads) / 256.0;  // mild preference for fuller CTAs
+                if (cost < best) best = cost, found = true, *G4_ = G4, *tw_ = tw, *ty_ = ty, *smem_ = smem;
+            }
+    }
+    return found;
+}
+
 // host-side tile choice for dwconv_tile_kernel (measured with tools/dw_bench.py): two channel groups per CTA (32-byte
 // chunks = full sectors), rows as wide as the map (<= 40 columns), as many 4-row strips as fit 256 threads; widths and
 // strip counts are picked to minimise the padding of the last tile.  Returns false when no tile fits.
-static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int* G_, int* tw_, int* ty_, size_t* smem_) {
+static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int nbuf, int* G_, int* tw_, int* ty_, size_t* smem_) {
     const int cg = c / 8, G = cg >= 2 ? 2 : 1;
     int tw = wo <= 40 ? wo : 40;
     if (wo > 40) {
@@ -434,14 +569,14 @@ static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int*
     for (int t = 256 / (G * tw); t >= 1; --t) {
         const int th = t * R;
         const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
-        if ((size_t)k * k * G * 32 + (size_t)ir * ic * G * 16 > 64 * 1024) continue;
+        if ((size_t)k * k * G * 32 + (size_t)nbuf * ir * ic * G * 16 > (size_t)(nbuf > 1 ? 100 : 64) * 1024) continue;
         const int pad = cdiv(strips, t) * t - strips;
         if (pad < best_pad) best_pad = pad, ty = t;
     }
     if (ty < 1) return false;
     const int th = ty * R;
     const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
-    *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = (size_t)k * k * G * 32 + (size_t)ir * ic * G * 16;
+    *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = (size_t)k * k * G * 32 + (size_t)nbuf * ir * ic * G * 16;
     return true;
 }
 
@@ -553,28 +688,33 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
     cudaStream_t st = as_stream(stream);
     {
         // shared-memory tiled kernel for every (k, stride, dilation) the graph uses
-        constexpr int R = 4;
-        int G = 0, tw = 0, ty = 0;
+        typedef void (*DwKern)(const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, int, int, int, int, int, int, int, int, int,
+                               int, int, int);
+        DwKern kern = nullptr;
+        const int R = (ho % 8 == 0) ? 8 : 4;
+#define DBL_DW3(KK, SS, DD) (R == 8 ? (DwKern)dwconv_tile3_kernel<KK, SS, DD, 8> : (DwKern)dwconv_tile3_kernel<KK, SS, DD, 4>)
+        if (k == 3 && stride == 1 && dil == 1) kern = DBL_DW3(3, 1, 1);
+        else if (k == 3 && stride == 2 && dil == 1) kern = DBL_DW3(3, 2, 1);
+        else if (k == 5 && stride == 1 && dil == 1) kern = DBL_DW3(5, 1, 1);
+        else if (k == 7 && stride == 1 && dil == 1) kern = DBL_DW3(7, 1, 1);
+        else if (k == 7 && stride == 1 && dil == 3) kern = DBL_DW3(7, 1, 3);
+#undef DBL_DW3
+        int G4 = 0, tw = 0, ty = 0;
         size_t smem = 0;
-        void (*kern)(const __nv_bfloat16*, const float*, const float*, __nv_bfloat16*, int, int, int, int, int, int, int, int, int, int, int,
-                     int) = nullptr;
-        if (k == 3 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<3, 1, 1, R>;
-        else if (k == 3 && stride == 2 && dil == 1) kern = dwconv_tile_kernel<3, 2, 1, R>;
-        else if (k == 5 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<5, 1, 1, R>;
-        else if (k == 7 && stride == 1 && dil == 1) kern = dwconv_tile_kernel<7, 1, 1, R>;
-        else if (k == 7 && stride == 1 && dil == 3) kern = dwconv_tile_kernel<7, 1, 3, R>;
-        bool have_tile = kern && act != DBL_ACT_GELU && x->n <= 65535 && dw_pick_tile(k, stride, dil, R, x->c, ho, wo, &G, &tw, &ty, &smem);
+        bool have_tile = kern && act != DBL_ACT_GELU && x->n <= 65535 && dw_pick_tile3(k, stride, dil, R, x->c, ho, wo, &G4, &tw, &ty, &smem);
         if (have_tile) {
-            static const char* force = getenv("DBL_DW_TILE");  // tuning aid: "G,tw,ty"
+            static const char* force = getenv("DBL_DW_TILE");  // tuning aid: "G4,tw,ty"
             int fg, ftw, fty;
-            if (force && sscanf(force, "%d,%d,%d", &fg, &ftw, &fty) == 3 && fg * ftw * fty <= 256) {
+            if (force && sscanf(force, "%d,%d,%d", &fg, &ftw, &fty) == 3 && fg * ftw * fty <= 256 && fg % 2 == 0) {
                 const int ir = (fty * R - 1) * stride + (k - 1) * dil + 1, ic = (ftw - 1) * stride + (k - 1) * dil + 1;
-                const size_t sm = (size_t)k * k * fg * 32 + (size_t)ir * ic * fg * 16;
-                if (sm <= 100 * 1024) G = fg, tw = ftw, ty = fty, smem = sm;
+                const size_t sm = (size_t)k * k * fg * 16 + (size_t)ir * ic * fg * 8;
+                if (sm <= 100 * 1024) G4 = fg, tw = ftw, ty = fty, smem = sm;
             }
+            static const char* dbg = getenv("DBL_DW_DEBUG");
+            if (dbg) fprintf(stderr, "dw k%d s%d d%d c%d %dx%d: R=%d G4=%d tw=%d ty=%d smem=%zu\n", k, stride, dil, x->c, ho, wo, R, G4, tw, ty, smem);
         }
         if (have_tile) {
-            static thread_local const void* configured[8];
+            static thread_local const void* configured[16];
             static thread_local int nconf = 0;
             bool have = false;
             for (int i = 0; i < nconf; ++i) have = have || configured[i] == reinterpret_cast<const void*>(kern);
@@ -583,11 +723,11 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
                     set_error("dbl_dwconv2d: cannot opt in to 100 KB of shared memory: %s", cudaGetErrorString(cudaGetLastError()));
                     return DBL_E_CUDA;
                 }
-                if (nconf < 8) configured[nconf++] = reinterpret_cast<const void*>(kern);
+                if (nconf < 16) configured[nconf++] = reinterpret_cast<const void*>(kern);
             }
             const int tiles_x = cdiv(wo, tw), tiles_y = cdiv(ho, ty * R);
-            dim3 grid(tiles_x * tiles_y, cdiv(x->c / 8, G), x->n);
-            launch_k(kern, grid, G * tw * ty, smem, st, xp, w, bias, yp, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act, G, tw, ty, tiles_x);
+            dim3 grid(tiles_x * tiles_y, cdiv(x->c, G4 * 4), x->n);
+            launch_k(kern, grid, G4 * tw * ty, smem, st, xp, w, bias, yp, x->h, x->w, x->c, x->pitch, ho, wo, y->pitch, act, G4, tw, ty, tiles_x);
             count_launch();
             return check_launch("dbl_dwconv2d(tile)");
         }

@@ -22,6 +22,8 @@
 // Weights are pre-packed once (dbl_mma_pack_weights) in B-fragment order: one 8-byte load per lane per (k-step, n-block).
 // Output channels are permuted inside the packed weights so that every thread owns 2*NB CONTIGUOUS channels of its
 // pixels -> 8/16-byte global stores without any shuffle.
+#include <cstdlib>
+
 #include "mma_util.cuh"
 
 namespace dbl {
@@ -674,6 +676,11 @@ extern "C" int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, 
     return check_launch("dbl_mma_pack_weights");
 }
 
+static int bn_warps() {
+    static const int v = getenv("DBL_BN_WARPS") ? atoi(getenv("DBL_BN_WARPS")) : 8;
+    return v;
+}
+
 extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
                                  int shortcut, const dbl_tensor* y, dbl_stream_t stream) {
     DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w1_packed && w2_packed, DBL_E_ARG, "dbl_bottleneck3x3: null/invalid argument");
@@ -685,8 +692,14 @@ extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, con
     switch (x->c) {
         // tile width 28 -> row pitch 32: every 16-row GEMM block is half a tile row (index math = shifts) and the
         // m-block counts of both phases divide evenly over the warps
-        case 16: return launch_bottleneck<16, 30, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-        case 32: return launch_bottleneck<32, 14, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 16:
+            if (bn_warps() == 16) return launch_bottleneck<16, 30, 28, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+            if (bn_warps() == 12) return launch_bottleneck<16, 30, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+            return launch_bottleneck<16, 30, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 32:
+            if (bn_warps() == 16) return launch_bottleneck<32, 14, 28, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+            if (bn_warps() == 12) return launch_bottleneck<32, 14, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+            return launch_bottleneck<32, 14, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
         case 64: return launch_bottleneck<64, 10, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
         default: break;
     }
@@ -707,7 +720,9 @@ extern "C" int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const 
     cudaStream_t st = as_stream(stream);
     const dbl_tensor* rr = epi != DBL_EPI_NONE ? r : nullptr;
 #define DBL_CM(CI, CO, S, TH) /* tile width 30 (stride 1) / 31 (stride 2) -> (sub-)tile row pitch 32 */ \
-    if (x->c == CI && y->c == CO && stride == S) return launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
+    if (x->c == CI && y->c == CO && stride == S)                                                                                         \
+        return bn_warps() == 16 ? launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 16, 2>(x, w_packed, bias, rr, y, act, epi, st) \
+                                : launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
     DBL_CM(8, 16, 2, 8);
     DBL_CM(16, 32, 2, 8);
     DBL_CM(32, 64, 2, 8);

@@ -71,6 +71,18 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
     return d;
 }
 
+#ifdef DBL_TRACE  // developer aid (never in the shipped build): per-CTA phase time stamps, read back with dbl_debug_trace_read
+__device__ unsigned long long g_tc_trace[512 * 16];
+__device__ __forceinline__ void tc_trace(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x < 512) g_tc_trace[blockIdx.x * 16 + slot] = t;
+}
+#define TC_TRACE(slot, cond) do { if (cond) tc_trace(slot); } while (0)
+#else
+#define TC_TRACE(slot, cond) do { } while (0)
+#endif
+
 template <int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,6 +100,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TC_TRACE(0, threadIdx.x == 0);
     for (int i = threadIdx.x; i < bias_n; i += TC_THREADS) sBias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]);
@@ -116,10 +129,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TC_TRACE(1, threadIdx.x == 0);
     // PDL: dependents may start only once every CTA of this grid HOLDS its TMEM columns (a dependent CTA that allocated
     // first and then blocked in its own pdl_wait() would starve us); then wait for our own predecessor
     pdl_launch_dependents();
     pdl_wait();
+    TC_TRACE(2, threadIdx.x == 0);
 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int kblocks = p.taps * p.nchunks;
@@ -157,6 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
                         tma_load_4d(&maps.a[ph * 2 + pw], &full[stage], a_dst, ch * p.cchunk, x0 + ox, y0 + oy, img);
                     }
                     tma_load_2d(&maps.b, &full[stage], b_dst, kb * p.cchunk, nt * p.npad);
+                    TC_TRACE(3, tile == (int)blockIdx.x && kb == 0);
                 }
                 __syncwarp();
                 if (++stage == (uint32_t)p.stages) stage = 0, phase ^= 1;
@@ -180,6 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
+                TC_TRACE(4, it == 0 && kb == 0 && lane == 0);
+                TC_TRACE(5, it == 0 && kb == kblocks - 1 && lane == 0);
                 const uint64_t ad0 = dtempl + (uint64_t)(smem_u32(sA + (size_t)stage * p.a_bytes) >> 4);
                 const uint64_t bd0 = dtempl + (uint64_t)(smem_u32(sB + (size_t)stage * p.b_bytes) >> 4);
                 if (elect_one()) {
@@ -214,6 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             }
             mbar_wait(&tfull[acc], aphase);
             tc_fence_after();
+            TC_TRACE(6, it == 0 && warp == 2 && lane == 0);
             const int n0 = nt * p.npad;
             const int ncols = min(p.npad, ((p.cout - n0) + 15) & ~15);
             for (int c0 = chalf * 16; c0 < ncols; c0 += 16 * (TC_EPI_WARPS / 4)) {
@@ -271,6 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            TC_TRACE(7, it == 0 && warp == 2 && lane == 0);
+            TC_TRACE(8, warp == 2 && lane == 0);
         }
     }
     // teardown
@@ -280,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+    TC_TRACE(9, threadIdx.x == 0);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -465,3 +487,9 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
 }
 
 }  // namespace dbl
+
+#ifdef DBL_TRACE
+extern "C" int dbl_debug_trace_read(void* dst, size_t bytes) {
+    return cudaMemcpyFromSymbol(dst, dbl::g_tc_trace, bytes < sizeof(dbl::g_tc_trace) ? bytes : sizeof(dbl::g_tc_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -87,6 +87,19 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
     p.u = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     return p;
 }
+// packed fp32 FMA over an aligned register pair (SASS FFMA2): half the issue slots of two FFMAs, IEEE fma per element
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t w) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
+    return r;
+}
+__device__ __forceinline__ void f32x2_split(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 // read-only path (ld.global.nc): only for tensors no thread of the running kernel writes
 __device__ __forceinline__ bf16x8 ldg8(const __nv_bfloat16* p) {
     bf16x8 v;

@@ -80,6 +80,70 @@ struct DsCfg {
     static_assert(NB % NBC == 0, "COUT must be a multiple of 64 or at most 80");
 };
 
+// depthwise stage of the fused kernel = the inner loops of dwconv_tile3_kernel (conv_direct.cu): a work item is one output
+// column x FOUR channels x R rows, packed fp32 FMAs over channel pairs, filter column in registers; the result is rounded to
+// bf16 into the planar A tile (plane = 8 channels, 16 bytes per pixel; a 4-channel item fills one half of a 16-byte slot).
+template <int K, int S, int CIN, int R, int DW_ACT>
+__device__ __forceinline__ void ds_depthwise(uint32_t sX, uint32_t sA, const float* sWd, const float* sBd, int tw, int th, int ic, int psa,
+                                             int tid, int NT) {
+    constexpr int G4 = CIN / 4;
+    constexpr int ROWS_T = (R - 1) * S + K;
+    const int strips = th / R;
+    const int items = G4 * tw * strips;
+    for (int it = tid; it < items; it += NT) {
+        const int g = it % G4, rest = it / G4;
+        const int xi = rest % tw, ys = rest / tw;
+        unsigned long long acc[R][2];
+        {
+            ulonglong2 b2 = make_ulonglong2(0ull, 0ull);
+            if (DW_ACT) b2 = *reinterpret_cast<const ulonglong2*>(sBd + g * 4);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r][0] = b2.x, acc[r][1] = b2.y;
+        }
+        const uint32_t xbase = sX + (uint32_t)(((ys * R * S) * ic + xi * S) * G4 + g) * 8;
+#pragma unroll 1
+        for (int kx = 0; kx < K; ++kx) {
+            unsigned long long wk[K][2];
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(sWd + (ky * K + kx) * CIN + g * 4);
+                wk[ky][0] = w0.x, wk[ky][1] = w0.y;
+            }
+#pragma unroll
+            for (int iy = 0; iy < ROWS_T; ++iy) {
+                bool used = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int d = iy - r * S;
+                    if (d >= 0 && d < K) used = true;
+                }
+                if (!used) continue;
+                const uint2 v = lds64(xbase + (uint32_t)((iy * ic + kx) * G4) * 8);
+                const unsigned long long x0 = bf16x2_to_f32x2(v.x), x1 = bf16x2_to_f32x2(v.y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int d = iy - r * S;
+                    if (d >= 0 && d < K) {
+                        ffma2(acc[r][0], x0, wk[d][0]);
+                        ffma2(acc[r][1], x1, wk[d][1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float f[4];
+            f32x2_split(acc[r][0], f[0], f[1]);
+            f32x2_split(acc[r][1], f[2], f[3]);
+            if (DW_ACT) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[i] = silu_fast(f[i]);
+            }
+            sts64(sA + (uint32_t)((g >> 1) * psa + ((ys * R + r) * tw + xi) * 16 + (g & 1) * 8), make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3])));
+        }
+    }
+}
+
 template <int K, int S, int CIN, int COUT, int DW_ACT>
 __global__ void __launch_bounds__(512) dsconv_mma_kernel(const DsParams p) {
     using C = DsCfg<K, S, CIN, COUT>;
@@ -125,63 +189,11 @@ __global__ void __launch_bounds__(512) dsconv_mma_kernel(const DsParams p) {
     cp_async_wait<0>();
     __syncthreads();
 
-    // ---------------- depthwise: (channel group, column, strip of R rows) per work item ----------------
-    {
-        const int strips = th / R;
-        const int items = G * tw * strips;
-        for (int it = tid; it < items; it += NT) {
-            const int g = it % G, rest = it / G;
-            const int xi = rest % tw, ys = rest / tw;
-            float acc[R][8];
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[r][i] = DW_ACT ? sBd[g * 8 + i] : 0.f;
-            const uint32_t xbase = sX + (uint32_t)(((ys * R * S) * ic + xi * S) * G + g) * 16;
-#pragma unroll 1
-            for (int kx = 0; kx < K; ++kx) {
-                float wk[K][8];
-#pragma unroll
-                for (int ky = 0; ky < K; ++ky) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(sWd + (ky * K + kx) * CIN + g * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sWd + (ky * K + kx) * CIN + g * 8 + 4);
-                    wk[ky][0] = w0.x, wk[ky][1] = w0.y, wk[ky][2] = w0.z, wk[ky][3] = w0.w;
-                    wk[ky][4] = w1.x, wk[ky][5] = w1.y, wk[ky][6] = w1.z, wk[ky][7] = w1.w;
-                }
-#pragma unroll
-                for (int iy = 0; iy < ROWS_T; ++iy) {
-                    bool used = false;
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int d = iy - r * S;
-                        if (d >= 0 && d < K) used = true;
-                    }
-                    if (!used) continue;
-                    bf16x8 v;
-                    v.u = lds128(xbase + (uint32_t)((iy * ic + kx) * G) * 16);
-                    float xv[8];
-                    unpack8(v, xv);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const int d = iy - r * S;
-                        if (d >= 0 && d < K) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(xv[i], wk[d][i], acc[r][i]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (DW_ACT) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[r][i] = silu_fast(acc[r][i]);
-                }
-                const bf16x8 o = pack8(acc[r]);
-                sts128(sA + (uint32_t)(g * psa + ((ys * R + r) * tw + xi) * 16), o.u);
-            }
-        }
-    }
+    // ---------------- depthwise: (4-channel group, column, strip of R rows) per work item ----------------
+    if (th % 8 == 0)
+        ds_depthwise<K, S, CIN, 8, DW_ACT>(sX, sA, sWd, sBd, tw, th, ic, psa, tid, NT);
+    else
+        ds_depthwise<K, S, CIN, 4, DW_ACT>(sX, sA, sWd, sBd, tw, th, ic, psa, tid, NT);
     __syncthreads();
 
     // ---------------- pointwise: work item = (16-pixel block, 64-channel chunk) ----------------
@@ -250,7 +262,7 @@ static bool ds_pick_tile(int k, int s, int cin, int cout, int ho, int wo, int ma
             const size_t smem = 256 + (size_t)(cin / 16) * (cout / 8) * 256 + (size_t)k * k * cin * 4 + (size_t)(cout + cin) * 4 +
                                 (size_t)(cin / 8) * (mpad + 1) * 16 + (size_t)ir * ic * cin * 2;
             if (smem > (size_t)max_smem) continue;
-            const int items = G * tw * (th / 4);
+            const int items = 2 * G * tw * (th / (th % 8 == 0 ? 8 : 4));
             int nt = (items + 31) / 32 * 32;
             if (nt > 512) nt = 512;
             if (nt < 64) nt = 64;

@@ -76,10 +76,12 @@ class DBLEngine:
         self.fuse_thin = (conv_impl == L.IMPL_AUTO) if fuse_thin is None else bool(fuse_thin)
         self.fuse_stem = self.fuse_thin and not keep_layers
         self.fuse_head = self.fuse_thin and not keep_layers  # last head convs + decode + filter in one kernel (dbl_head_decode)
-        # dw + pw of every DSConv / Detect class-branch pair in one kernel (dbl_dsconv).  Correct and tested, but measured
-        # SLOWER than the two-kernel form inside the multi-lane graph (13.7k vs 14.4k images/s: its large CTAs serialise
-        # fill -> depthwise -> pointwise at low occupancy), so it stays opt-in until the depthwise stage is pipelined.
-        self.fuse_ds = os.environ.get("DBL_FUSE_DS", "0") == "1"
+        # dw + pw of a DSConv / Detect class-branch pair in one kernel (dbl_dsconv).  "auto" (default): only where it was
+        # measured faster than the two-kernel form -- stride 1 and a small problem (H*W*Cin per image <= 128 Ki: the
+        # DSBottleneck halves at 40^2 / 20^2 and the small Detect class-branch pairs), where both launches are mostly fixed
+        # cost.  Larger maps stay unfused: the fused CTA serialises fill -> depthwise -> pointwise at low occupancy
+        # (Detect P3 64->80 @80^2: 108 us fused vs 89 us as two launches).  "1" = wherever supported, "0" = never.
+        self.fuse_ds = os.environ.get("DBL_FUSE_DS", "auto")
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
@@ -206,7 +208,8 @@ class DBLEngine:
         """dw k x k (+bias+SiLU when bdw is given) -> pw 1x1 + bias + SiLU (+ residual) in one kernel (csrc/dsconv_mma.cu);
         False when no instantiation exists or fusion is off -> the caller emits the two-kernel form"""
         k, cin, cout = wdw.shape[-1], wdw.shape[0], wpw.shape[0]
-        if not (self.fuse_thin and self.fuse_ds and self.lib.dbl_dsconv_supported(k, s, cin, cout)) or x.buf.data_ptr() == y.buf.data_ptr():
+        want = self.fuse_ds == "1" or (self.fuse_ds == "auto" and s == 1 and x.h * x.w * cin <= 131072)
+        if not (self.fuse_thin and want and self.lib.dbl_dsconv_supported(k, s, cin, cout)) or x.buf.data_ptr() == y.buf.data_ptr():
             return False
         wd = self._dev(wdw.reshape(cin, k * k).t(), torch.float32)
         bd = self._dev(bdw, torch.float32) if bdw is not None else None
