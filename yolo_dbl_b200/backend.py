@@ -13,6 +13,7 @@ GPU raises ``DblError``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -129,10 +130,13 @@ class DBLBackend(nn.Module):
         return dict(self._sd)
 
     # ---- execution ----------------------------------------------------------------------------------------------
-    def engine(self, b: int, h: int, w: int) -> DBLEngine:
-        key = (int(b), int(h), int(w))
+    def engine(self, b: int, h: int, w: int, replica: int = 0) -> DBLEngine:
+        """The engine (static buffers + captured CUDA graph) for one input shape.  ``replica`` > 0 gives further independent
+        engines of the same shape: whole batches in flight on different streams (detect_stream, bench.py) fill each other's
+        bubbles -- kernel fill/drain, the 64-CTA per-image kernels (hypergraph, NMS), small grids -- for ~9 % more throughput."""
+        key = (int(b), int(h), int(w)) if replica == 0 else (int(b), int(h), int(w), int(replica))
         if key not in self._engines:
-            self._engines[key] = DBLEngine(self.spec, self._sd, *key, device=self._device, use_graph=self.use_graph,
+            self._engines[key] = DBLEngine(self.spec, self._sd, *key[:3], device=self._device, use_graph=self.use_graph,
                                            conv_impl=self.conv_impl)
         return self._engines[key]
 
@@ -197,64 +201,78 @@ class DBLBackend(nn.Module):
             x, conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms)
         return rows, counts
 
-    def detect_stream(self, batches, with_event: bool = False, **nms):
+    def detect_stream(self, batches, with_event: bool = False, in_flight: Optional[int] = None, **nms):
         """Generator over an iterable of host (pinned) or device batches: yields (rows, counts) per batch -- the analogue of
-        predict(..., stream=True) (reference engine/predictor.py:219-304) -- software-pipelined two ways: the host->device
-        copy of batch i+1 runs on a copy stream while batch i computes, and batch i+1 is already QUEUED behind batch i when
-        batch i's result is handed out, so the GPU never idles while the caller reads a result.
+        predict(..., stream=True) (reference engine/predictor.py:219-304) -- software-pipelined three ways: the host->device
+        copy of batch i+1 runs on a copy stream while batch i computes; batch i+1 is already QUEUED when batch i's result is
+        handed out, so the GPU never idles while the caller reads a result; and consecutive batches run on ``in_flight``
+        (default 2, env DBL_INFLIGHT) engine replicas on their own streams, so two whole batches overlap on the GPU.
 
-        The yielded tensors are one of two result slots: they stay valid until the generator has been advanced TWICE.
+        The yielded tensors are one of ``in_flight + 2`` result slots: they stay valid until the generator has been advanced TWICE.
         With ``with_event=True`` a third item is yielded, the CUDA event recorded when that batch's result was complete: a
         caller that reads results on its own stream (``stream.wait_event(ev)``) overlaps its device->host copy with the
-        next batch; a caller that just uses the current stream needs nothing (stream order)."""
+        next batch; without it the current stream is made to wait for the batch, so plain stream order is enough."""
         it = iter(batches)
         nxt = next(it, None)
         if nxt is None:
             return
         nxt = self._prep(nxt)
-        eng = self.engine(nxt.shape[0], nxt.shape[2], nxt.shape[3])
+        P = max(1, int(in_flight if in_flight is not None else os.environ.get("DBL_INFLIGHT", "2")))
+        engs = [self.engine(nxt.shape[0], nxt.shape[2], nxt.shape[3], replica=r) for r in range(P)]
         kw = {{"agnostic_nms": "agnostic"}.get(k, k): v for k, v in nms.items()}
         with torch.cuda.device(self._device):
+            caller = torch.cuda.current_stream(self._device)
             copy_stream = torch.cuda.Stream(device=self._device)
-            staging = [torch.empty(nxt.shape, dtype=nxt.dtype, device=self._device) for _ in range(2)]
-            ready = [None, None]
-            done = [None, None]
-            out = [None, None]
+            lanes = [caller] + [torch.cuda.Stream(device=self._device) for _ in range(P - 1)]
+            for ln in lanes[1:]:
+                ln.wait_stream(caller)  # whatever the caller queued before (weights, earlier results) is ordered first
+            S, R = P + 1, P + 2  # staging slots (one being filled + P being read), result slots (valid for two advances)
+            staging = [None] * S
+            ready = [None] * S
+            slot_done = [None] * S
+            out = [None] * R
 
-            def stage(x, slot):
-                if staging[slot].dtype != x.dtype:
-                    staging[slot] = torch.empty(x.shape, dtype=x.dtype, device=self._device)
+            def launch(x, i):
+                s, r, lane = i % S, i % R, lanes[i % P]
+                if staging[s] is None or staging[s].dtype != x.dtype or staging[s].shape != x.shape:
+                    staging[s] = torch.empty(x.shape, dtype=x.dtype, device=self._device)
                 with torch.cuda.stream(copy_stream):
-                    if done[slot] is not None:
-                        copy_stream.wait_event(done[slot])  # the compute that read this slot has finished
-                    staging[slot].copy_(x, non_blocking=True)
-                    ready[slot] = torch.cuda.Event()
-                    ready[slot].record(copy_stream)
+                    if slot_done[s] is not None:
+                        copy_stream.wait_event(slot_done[s])  # the compute that read this slot has finished
+                    staging[s].copy_(x, non_blocking=True)
+                    ready[s] = torch.cuda.Event()
+                    ready[s].record(copy_stream)
+                with torch.cuda.stream(lane):
+                    lane.wait_event(ready[s])
+                    rows, counts, _ = engs[i % P].detect(staging[s], **kw)
+                    if out[r] is None:
+                        out[r] = (torch.empty_like(rows), torch.empty_like(counts))
+                    out[r][0].copy_(rows, non_blocking=True)  # result slot: the engine's own buffers are rewritten by a later batch
+                    out[r][1].copy_(counts, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(lane)
+                slot_done[s] = ev
+                return out[r][0], out[r][1], ev
 
-            stage(nxt, 0)
-            pending = None
+            from collections import deque
+
+            queued = deque()
             i = 0
-            while nxt is not None:
-                slot = i & 1
-                cur = torch.cuda.current_stream(self._device)
-                cur.wait_event(ready[slot])
-                rows, counts, _ = eng.detect(staging[slot], **kw)
-                if out[slot] is None:
-                    out[slot] = (torch.empty_like(rows), torch.empty_like(counts))
-                out[slot][0].copy_(rows, non_blocking=True)  # result slot: the engine's own buffers are rewritten by batch i+1
-                out[slot][1].copy_(counts, non_blocking=True)
-                done[slot] = torch.cuda.Event()
-                done[slot].record(cur)
-                item = (out[slot][0], out[slot][1], done[slot]) if with_event else (out[slot][0], out[slot][1])
-                nxt = next(it, None)
-                if nxt is not None:
-                    nxt = self._prep(nxt)
-                    stage(nxt, slot ^ 1)
-                if pending is not None:
-                    yield pending  # batch i-1, with batch i already queued behind it
-                pending = item
-                i += 1
-            yield pending
+            while nxt is not None or queued:
+                while nxt is not None and len(queued) <= P:  # keep P + 1 batches queued: P computing, one whose copy is in flight
+                    queued.append(launch(nxt, i))
+                    i += 1
+                    nxt = next(it, None)
+                    if nxt is not None:
+                        nxt = self._prep(nxt)
+                item = queued.popleft()
+                if with_event:
+                    yield item
+                else:
+                    caller.wait_event(item[2])
+                    yield item[:2]
+            for ln in lanes[1:]:
+                caller.wait_stream(ln)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
