@@ -40,6 +40,10 @@ CONV_CASES = [
     (2, 40, 40, 128, 32, 1, 1, L.ACT_NONE, L.EPI_NONE, torch.float32, 0, 0),
     (1, 20, 20, 256, 320, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
     (1, 33, 50, 32, 48, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    # TMA-store epilogue of the 1x1 GEMM: partial last 64-channel sub-tile (80 = 64 + 16) into a channel slice, partial last pixel tile
+    (1, 40, 40, 64, 80, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 48),
+    (2, 33, 31, 32, 24, 1, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 8),
+    (3, 40, 40, 128, 192, 1, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 64, 64),
 ]
 
 

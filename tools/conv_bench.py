@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--impl", type=int, default=L.IMPL_TCGEN05)
     ap.add_argument("--n", type=int, default=0, help="override the batch size of every shape")
+    ap.add_argument("--act", type=int, default=L.ACT_SILU, help="0 none, 1 SiLU, 2 GELU")
+    ap.add_argument("--warm", action="store_true", help="no L2 flush between repetitions")
     a = ap.parse_args()
     lib = L.require_device()
     dev = torch.device("cuda:0")
@@ -55,12 +57,13 @@ def main():
         r = torch.randn(n, ho, wo, cout, device=dev).to(torch.bfloat16) if epi else None
         xv, yv = L.view(x), L.view(y)
         rv = L.view(r) if epi else None
-        args = (C.byref(xv), wt.data_ptr(), b.data_ptr(), C.byref(rv) if epi else None, C.byref(yv), k, s, k // 2, 1, L.ACT_SILU, epi, a.impl, st)
+        args = (C.byref(xv), wt.data_ptr(), b.data_ptr(), C.byref(rv) if epi else None, C.byref(yv), k, s, k // 2, 1, a.act, epi, a.impl, st)
         assert lib.dbl_conv2d(*args) == 0, lib.dbl_last_error().decode()
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(a.reps):
-            flush.zero_()
+            if not a.warm:
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             lib.dbl_conv2d(*args)

@@ -13,10 +13,11 @@
 //   epilogue (tcgen05.ld -> +bias -> SiLU/GELU -> (+|*) residual -> bf16/f32 -> global), mbarrier pipelines in between.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
-#include "tc_ptx.cuh"
+#include "mma_util.cuh"
 
 namespace dbl {
 
@@ -51,12 +52,16 @@ struct TcParams {
     int rpitch, ypitch, ydtype, act, epi;
     int y_vec;                 // 16-byte stores legal
     int r_vec;
+    int tma_out;               // 1: bf16 output tile staged in shared memory (128B-swizzled) and written by TMA bulk stores
 };
 
 struct TcMaps {
     CUtensorMap a[4];  // [0] stride-1 / flat; [ph*2+pw] parity maps for stride 2
     CUtensorMap b;
+    CUtensorMap y;     // output as [pixels][cout] (flat) for the TMA-store epilogue
 };
+
+constexpr uint32_t TC_OUT_BYTES = 128 * 128;  // one staged output sub-tile: 128 rows x 64 bf16 channels (128-byte swizzled rows)
 
 // K-major shared-memory matrix descriptor (tcgen05 "version 1"): rows of `row_bytes` (= swizzle span), 8-row groups
 // `8*row_bytes` apart.  layout_type: 2 = 128B swizzle, 4 = 64B, 6 = 32B.
@@ -98,6 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     uint64_t* tfull = bars + 2 * TC_MAX_STAGES;
     uint64_t* tempty = tfull + MAX_ACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_ACC);
+    uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);  // [2][TC_OUT_BYTES] when p.tma_out
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TC_TRACE(0, threadIdx.x == 0);
@@ -105,6 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a[0]);
         prefetch_tmap(&maps.b);
+        if (p.tma_out) prefetch_tmap(&maps.y);
         if (p.stride == 2) {
             prefetch_tmap(&maps.a[1]);
             prefetch_tmap(&maps.a[2]);
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         const int lg = warp & 3;          // TMEM lane group this warp may access
         const int chalf = (warp - 2) >> 2;  // which interleaved share of the column chunks this warp converts
         const int row = lg * 32 + lane;
-        uint32_t it = 0;
+        uint32_t it = 0, sub = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1;
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -235,6 +242,64 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             TC_TRACE(6, it == 0 && warp == 2 && lane == 0);
             const int n0 = nt * p.npad;
             const int ncols = min(p.npad, ((p.cout - n0) + 15) & ~15);
+            if (p.tma_out) {
+                // ---- staged epilogue: a thread's row-wise 16-byte pieces go to a 128B-swizzled shared-memory sub-tile
+                // (128 rows x 64 channels), one elected thread writes it with ONE TMA bulk store (full 128-byte lines, rows
+                // past the tensor clipped by the unit).  The direct form below issues, per 16 channels, a warp-wide store
+                // that touches 32 different lines with 16 bytes each: ~2000 LSU line-cycles per 128x128 tile, which paced
+                // every multi-tile 1x1 GEMM of the network.
+                const bool issuer = (warp == 2 && lane == 0);
+                for (int h0 = 0; h0 < ncols; h0 += 64, ++sub) {
+                    uint8_t* obuf = sOut + (sub & 1) * TC_OUT_BYTES;
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store that last read this buffer is done
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                    const int hcols = min(64, ncols - h0);
+                    for (int c0 = h0 + chalf * 16; c0 < h0 + hcols; c0 += 16 * (TC_EPI_WARPS / 4)) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.npad + c0, v);
+                        tmem_ld_wait();
+                        const int cg = n0 + c0;
+                        float f[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 bq = *reinterpret_cast<const float4*>(sBias + cg + 4 * q);
+                            f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
+                            f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
+                            f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);
+                            f[4 * q + 3] = act_t<ACT>(__uint_as_float(v[4 * q + 3]) + bq.w);
+                        }
+                        if (p.epi != DBL_EPI_NONE && opix >= 0) {
+                            const __nv_bfloat16* rp = p.r + (size_t)opix * p.rpitch + cg;
+                            float rr[16];
+                            if (cg + 16 <= p.cout && p.r_vec) {
+                                unpack8(ld8(rp), rr);
+                                unpack8(ld8(rp + 8), rr + 8);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) rr[i] = (cg + i < p.cout) ? __bfloat162float(rp[i]) : 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) f[i] = p.epi == DBL_EPI_ADD ? f[i] + rr[i] : f[i] * rr[i];
+                        }
+                        const uint32_t j = (uint32_t)((c0 - h0) >> 3);  // 16-byte chunk of the 128-byte row
+                        const uint32_t base = smem_u32(obuf) + (uint32_t)row * 128u;
+                        sts128(base + (((j) ^ ((uint32_t)row & 7u)) << 4), pack8(f).u);
+                        sts128(base + (((j + 1) ^ ((uint32_t)row & 7u)) << 4), pack8(f + 8).u);
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+                    if (issuer) {
+                        tma_store_2d(&maps.y, obuf, n0 + h0, mt * TILE_M);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                TC_TRACE(7, it == 0 && warp == 2 && lane == 0);
+                TC_TRACE(8, warp == 2 && lane == 0);
+                continue;
+            }
             for (int c0 = chalf * 16; c0 < ncols; c0 += 16 * (TC_EPI_WARPS / 4)) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.npad + c0, v);
@@ -294,7 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             TC_TRACE(8, warp == 2 && lane == 0);
         }
     }
-    // teardown
+    // teardown (the bulk stores read shared memory: they must have finished before the CTA exits)
+    if (p.tma_out && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -409,7 +475,8 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     // prologue / pipeline fill / drain are most of its life and a second resident CTA hides them): each then takes half of
     // TMEM and a small stage ring.
     const int kblocks_total = k * k * (x->c / ((x->c % 64 == 0) ? 64 : ((x->c % 32 == 0) ? 32 : 16)));
-    const bool two_ctas = kblocks_total <= 2;
+    static const int force_two = getenv("DBL_TC_TWO") ? atoi(getenv("DBL_TC_TWO")) : 0;  // tuning aid: K-block limit of the two-CTA mode
+    const bool two_ctas = kblocks_total <= (force_two > 0 ? force_two : 2);
     p.nacc = (two_ctas ? 256 : 512) / p.npad;
     if (p.nacc > MAX_ACC) p.nacc = MAX_ACC;
     if (p.nacc < 1) p.nacc = 1;
@@ -430,10 +497,18 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
     p.b_bytes = (p.b_bytes + 1023u) & ~1023u;  // keep every stage buffer 1024-byte aligned
     p.a_tx = (uint32_t)(p.flat ? TILE_M : p.tw * p.th) * row_bytes;
     p.b_tx = (uint32_t)p.npad * row_bytes;
-    const size_t fixed = 1024 /*align slack*/ + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * TC_MAX_STAGES + 2 * MAX_ACC) * 8 + 16;
+    static const int tma_out_env = getenv("DBL_TC_TMA_OUT") ? atoi(getenv("DBL_TC_TMA_OUT")) : 1;  // tuning aid
+    // (one N tile only: the 64-channel store box of a partial last sub-tile must not reach into the next tile's channels)
+    p.tma_out = (tma_out_env && p.flat && p.n_tiles == 1 && y->dtype == DBL_BF16 && ((size_t)y->pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(y->data) & 15) == 0) ? 1 : 0;
+    const size_t fixed = 1024 /*align slack*/ + (((size_t)p.n_tiles * p.npad + 3) & ~(size_t)3) * 4 + (2 * TC_MAX_STAGES + 2 * MAX_ACC) * 8 + 16 +
+                         (p.tma_out ? 1024 + 2 * (size_t)TC_OUT_BYTES : 0);
     int stages = (int)(((size_t)max_smem - fixed) / (p.a_bytes + p.b_bytes));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    if (two_ctas && stages > 4) stages = 4;
+    if (two_ctas) {
+        const int fit = (int)(((size_t)110 * 1024 - fixed) / (p.a_bytes + p.b_bytes));  // two resident CTAs: <= 110 KB each
+        if (stages > 4) stages = 4;
+        if (fit >= 2 && stages > fit) stages = fit;
+    }
     DBL_REQUIRE(stages >= 2, DBL_E_UNSUPPORTED, "conv_tc: tile does not fit shared memory");
     p.stages = stages;
     p.bias = bias;
@@ -472,9 +547,15 @@ int conv2d_tcgen05(const dbl_tensor* x, const void* w, const float* bias, const 
         const uint32_t box[2] = {(uint32_t)p.cchunk, (uint32_t)p.npad};
         if (!encode_map(&maps.b, w, 2, dims, strides, box, row_bytes)) return DBL_E_CUDA;
     }
+    if (p.tma_out) {
+        const uint64_t dims[2] = {(uint64_t)y->c, (uint64_t)y->n * y->h * y->w};
+        const uint64_t strides[1] = {(uint64_t)y->pitch * 2};
+        const uint32_t box[2] = {64, TILE_M};
+        if (!encode_map(&maps.y, y->data, 2, dims, strides, box, 128)) return DBL_E_CUDA;
+    }
     const size_t smem = fixed + (size_t)stages * (p.a_bytes + p.b_bytes);
     const int total = p.m_tiles * p.n_tiles;
-    const int cap = (two_ctas && smem <= (size_t)100 * 1024) ? 2 * num_sms : num_sms;
+    const int cap = (two_ctas && smem <= (size_t)110 * 1024) ? 2 * num_sms : num_sms;
     const int grid = total < cap ? total : cap;
     if (act == DBL_ACT_SILU)
         launch_k(conv_tc_kernel<DBL_ACT_SILU>, grid, TC_THREADS, smem, st, maps, p);

@@ -80,6 +80,18 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t alo, ui
         : "memory");
 }
 
+#ifdef DBL_TRACE  // developer aid (never in the shipped build): per-CTA time stamps, read back with dbl_debug_trace4_read
+__device__ unsigned long long g_t4_trace[160 * 64];
+__device__ __forceinline__ void t4_trace(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x < 160 && slot < 64) g_t4_trace[blockIdx.x * 64 + slot] = t;
+}
+#define T4_TRACE(slot, cond) do { if (cond) t4_trace(slot); } while (0)
+#else
+#define T4_TRACE(slot, cond) do { } while (0)
+#endif
+
 template <int ACT, int KSTEPS>
 __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid_constant__ T4Maps maps, const T4Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -97,13 +109,14 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + T4_MAX_ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T4_TRACE(0, threadIdx.x == 0);
     for (int i = threadIdx.x; i < p.npad; i += T4_THREADS) sBias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a);
         prefetch_tmap(&maps.b);
         for (int s = 0; s < p.stages; ++s) mbar_init(&afull[s], 1), mbar_init(&aempty[s], 1);
         for (int s = 0; s < 2; ++s) mbar_init(&bfull[s], 1), mbar_init(&bempty[s], 1);
-        for (int a = 0; a < p.T; ++a) mbar_init(&tfull[a], 1), mbar_init(&tempty[a], T4_EPI_WARPS);
+        for (int a = 0; a < p.T; ++a) mbar_init(&tfull[a], 1), mbar_init(&tempty[a], 4);  // one quad of epilogue warps drains a tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -117,6 +130,9 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();  // after the TMEM allocation (see conv_tc.cu)
     pdl_wait();
+    T4_TRACE(1, threadIdx.x == 0);
+    int tr_n = 0;  // trace counter (dead code unless DBL_TRACE)
+    (void)tr_n;
 
     const int per_img = p.tiles_x * p.tiles_y;
     const uint32_t row_bytes = (uint32_t)p.cchunk * 2;
@@ -159,9 +175,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t dtempl = make_sw_desc(0, row_bytes, 0);
         const uint32_t d_lo = (uint32_t)dtempl, d_hi = (uint32_t)(dtempl >> 32);
-        uint32_t tap_a[9];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) tap_a[tap] = ((uint32_t)((tap / 3) * p.wl + tap % 3) * row_bytes) >> 4;
+        const uint32_t px16 = row_bytes >> 4, row16 = ((uint32_t)p.wl * row_bytes) >> 4;  // descriptor steps: one halo pixel / one halo row
         const uint32_t tap_b = ((uint32_t)p.npad * row_bytes) >> 4;
         // Control flow and operands stay warp-uniform (all 32 lanes walk the loops and poll the barriers); only the issue
         // itself is predicated on lane 0.  With the loops inside `if (lane == 0)` ptxas cannot prove the descriptors
@@ -177,16 +191,29 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                     if (cc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1);  // the epilogue has drained this accumulator
                     mbar_wait(&afull[stage], aphase);
                     tc_fence_after();
+                    T4_TRACE(2 + tr_n, lane == 0 && tr_n < 30);
+                    ++tr_n;
                     const uint32_t a_lo = d_lo + (smem_u32(sA + (size_t)stage * p.a_bytes) >> 4);
                     const uint32_t d_tmem = tmem_u + (uint32_t)(t * p.npad);
                     const uint32_t first = cc ? 1u : 0u;
                     if (elect_one()) {
+                        // rolled tap loops, k-steps unrolled: two descriptor low words stepped by adds, nothing else live.
+                        // (Fully unrolled, the 72 descriptor pairs of a unit exceeded the uniform register file: ptxas spilled
+                        // them through MOV.SPILL / R2UR.FILL / LDL and the single issuing thread needed ~70-90 cycles per MMA,
+                        // 2.5x the 32 cycles an N <= 64 MMA occupies the tensor pipe -- measured with tools/tc4_trace.py.)
+                        uint32_t acc = first, a_row = a_lo, b_t = b_lo;
+#pragma unroll 1
+                        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll 1
+                            for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ++ks)
-                                umma_bf16_lohi(d_tmem, a_lo + tap_a[tap] + 2 * ks, d_hi, b_lo + tap * tap_b + 2 * ks, d_hi, idesc,
-                                               (tap | ks) ? 1u : first);
+                                for (int ks = 0; ks < KSTEPS; ++ks) {
+                                    umma_bf16_lohi(d_tmem, a_row + dx * px16 + 2 * ks, d_hi, b_t + 2 * ks, d_hi, idesc, acc);
+                                    acc = 1u;
+                                }
+                                b_t += tap_b;
+                            }
+                            a_row += row16;
                         }
                         umma_commit(&aempty[stage]);
                         if (cc == p.nchunks - 1) umma_commit(&tfull[t]);
@@ -200,26 +227,40 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
         }
     } else {
         // ===================== epilogue =====================
+        // The 16 warps form FOUR quads (one warp per TMEM lane group); quad q drains tiles q, q+4, ... of the super-tile,
+        // all of a tile's columns.  Four tiles are therefore in their epilogue at the same time: the per-tile latency chain
+        // (barrier -> tcgen05.ld -> activation -> residual load -> stores, ~1.5 us) overlaps instead of adding up, which is
+        // what paced this kernel when all 16 warps walked the tiles in lock step.  The residual of a chunk is requested
+        // before the accumulator is waited for.
         const int ew = warp - 2;
         const int lg = warp & 3;   // TMEM lane group this warp may access
-        const int chalf = ew >> 2;  // 0..1: interleaved share of the 16-column chunks
+        const int quad = ew >> 2;  // 0..3
+        constexpr int NQUAD = T4_EPI_WARPS / 4;
         const int row = lg * 32 + lane;
         const int ty = row / p.wl, tx = row - ty * p.wl;
+        const int ncols = min(p.npad, (p.cout + 15) & ~15);
+        const bool r_fast = p.epi != DBL_EPI_NONE && p.r_vec;
         uint32_t it = 0;
         for (int s = blockIdx.x; s < p.n_super; s += gridDim.x, ++it) {
             const int t0 = s * p.T, ntile = min(p.T, p.m_tiles - t0);
-            for (int t = 0; t < ntile; ++t) {
+            for (int t = quad; t < ntile; t += NQUAD) {
                 const int mt = t0 + t;
                 const int img = mt / per_img, tt = mt - img * per_img;
                 const int oy = (tt / p.tiles_x) * p.th + ty, ox = (tt % p.tiles_x) * p.tw + tx;
                 long long opix = -1;
                 if (ty < p.th && tx < p.tw && oy < p.h && ox < p.w) opix = ((long long)img * p.h + oy) * p.w + ox;
+                const __nv_bfloat16* rrow = p.r + (size_t)(opix < 0 ? 0 : opix) * p.rpitch;
+                bf16x8 rn0, rn1;  // residual of the NEXT chunk (coherent loads: r may be the tensor this kernel overwrites in place)
+                rn0.u = rn1.u = make_uint4(0u, 0u, 0u, 0u);
+                if (r_fast && opix >= 0 && 16 <= p.cout) rn0 = ld8(rrow), rn1 = ld8(rrow + 8);
                 mbar_wait(&tfull[t], it & 1);
                 tc_fence_after();
-                const int ncols = min(p.npad, (p.cout + 15) & ~15);
-                for (int c0 = chalf * 16; c0 < ncols; c0 += 16 * (T4_EPI_WARPS / 4)) {
+                T4_TRACE(32 + 2 * tr_n, warp == 2 && lane == 0 && tr_n < 15);
+                for (int c0 = 0; c0 < ncols; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * p.npad + c0), v);
+                    const bf16x8 rc0 = rn0, rc1 = rn1;
+                    if (r_fast && opix >= 0 && c0 + 32 <= p.cout) rn0 = ld8(rrow + c0 + 16), rn1 = ld8(rrow + c0 + 24);
                     tmem_ld_wait();
                     if (opix < 0) continue;
                     float f[16];
@@ -233,12 +274,12 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                     }
                     const bool full16 = c0 + 16 <= p.cout;
                     if (p.epi != DBL_EPI_NONE) {
-                        const __nv_bfloat16* rp = p.r + (size_t)opix * p.rpitch + c0;
                         float rr[16];
                         if (full16 && p.r_vec) {
-                            unpack8(ld8(rp), rr);
-                            unpack8(ld8(rp + 8), rr + 8);
+                            unpack8(rc0, rr);
+                            unpack8(rc1, rr + 8);
                         } else {
+                            const __nv_bfloat16* rp = rrow + c0;
 #pragma unroll
                             for (int i = 0; i < 16; ++i) rr[i] = (c0 + i < p.cout) ? __bfloat162float(rp[i]) : 0.f;
                         }
@@ -271,11 +312,14 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[t]);
+                T4_TRACE(33 + 2 * tr_n, warp == 2 && lane == 0 && tr_n < 15);
+                ++tr_n;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    T4_TRACE(63, threadIdx.x == 0);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -448,3 +492,9 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
 }
 
 }  // namespace dbl
+
+#ifdef DBL_TRACE
+extern "C" int dbl_debug_trace4_read(void* dst, size_t bytes) {
+    return cudaMemcpyFromSymbol(dst, dbl::g_t4_trace, bytes < sizeof(dbl::g_t4_trace) ? bytes : sizeof(dbl::g_t4_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
