@@ -27,7 +27,7 @@
 #include <cstring>
 #include <mutex>
 
-#include "tc_ptx.cuh"
+#include "mma_util.cuh"
 
 namespace dbl {
 
@@ -49,10 +49,15 @@ struct T4Params {
     const __nv_bfloat16* r;
     void* y;
     int rpitch, ypitch, ydtype, epi, y_vec, r_vec;
+    int b_single;          // 1: the whole filter is ONE chunk (cin == cchunk): staged once per CTA, stays resident
+    int tma_out;           // 1: bf16 output tiles staged in shared memory (128B-swizzled rows) and written by TMA bulk stores
+    int wl8;               // staging row pitch in pixels (wl rounded up to 8: every tile row starts a 1024-byte swizzle atom)
+    uint32_t o_bytes;      // staging bytes per epilogue quad
 };
 
 struct T4Maps {
     CUtensorMap a, b;
+    CUtensorMap y;  // output [N][H][W][cout], box = 64 channels x tw pixels of one row (TMA-store epilogue)
 };
 
 __device__ __forceinline__ uint64_t make_sw_desc(uint32_t saddr, uint32_t row_bytes, int base_off_mode) {
@@ -97,8 +102,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                                  // [stages][a_bytes]
-    uint8_t* sB = sA + (size_t)p.stages * p.a_bytes;    // [2][b_bytes]
-    float* sBias = reinterpret_cast<float*>(sB + 2 * (size_t)p.b_bytes);
+    uint8_t* sB = sA + (size_t)p.stages * p.a_bytes;    // [2][b_bytes] ([1] when the filter is resident)
+    float* sBias = reinterpret_cast<float*>(sB + (p.b_single ? 1 : 2) * (size_t)p.b_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + ((p.npad + 3) & ~3));
     uint64_t* afull = bars;
     uint64_t* aempty = afull + T4_MAX_STAGES;
@@ -107,6 +112,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     uint64_t* tfull = bempty + 2;              // [T4_MAX_ACC]
     uint64_t* tempty = tfull + T4_MAX_ACC;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + T4_MAX_ACC);
+    uint8_t* sOut = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);  // [quads][o_bytes] when p.tma_out
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T4_TRACE(0, threadIdx.x == 0);
@@ -114,6 +120,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a);
         prefetch_tmap(&maps.b);
+        if (p.tma_out) prefetch_tmap(&maps.y);
         for (int s = 0; s < p.stages; ++s) mbar_init(&afull[s], 1), mbar_init(&aempty[s], 1);
         for (int s = 0; s < 2; ++s) mbar_init(&bfull[s], 1), mbar_init(&bempty[s], 1);
         for (int a = 0; a < p.T; ++a) mbar_init(&tfull[a], 1), mbar_init(&tempty[a], 4);  // one quad of epilogue warps drains a tile
@@ -143,16 +150,18 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
         for (int s = blockIdx.x; s < p.n_super; s += gridDim.x) {
             const int t0 = s * p.T, t1 = min(t0 + p.T, p.m_tiles);
             for (int cc = 0; cc < p.nchunks; ++cc) {
-                mbar_wait(&bempty[bbuf], bphase ^ 1);
-                uint8_t* b_dst = sB + (size_t)bbuf * p.b_bytes;
-                if (elect_one()) {
-                    mbar_expect_tx(&bfull[bbuf], p.b_tx);
+                if (!p.b_single || s == (int)blockIdx.x) {  // single-chunk filter: staged once, resident for the life of the CTA
+                    mbar_wait(&bempty[bbuf], bphase ^ 1);
+                    uint8_t* b_dst = sB + (size_t)bbuf * p.b_bytes;
+                    if (elect_one()) {
+                        mbar_expect_tx(&bfull[bbuf], p.b_tx);
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d(&maps.b, &bfull[bbuf], b_dst + (size_t)tap * p.npad * row_bytes, tap * p.cin + cc * p.cchunk, 0);
+                        for (int tap = 0; tap < 9; ++tap)
+                            tma_load_2d(&maps.b, &bfull[bbuf], b_dst + (size_t)tap * p.npad * row_bytes, tap * p.cin + cc * p.cchunk, 0);
+                    }
+                    __syncwarp();
+                    if (!p.b_single && ++bbuf == 2) bbuf = 0, bphase ^= 1;
                 }
-                __syncwarp();
-                if (++bbuf == 2) bbuf = 0, bphase ^= 1;
                 for (int mt = t0; mt < t1; ++mt) {
                     const int img = mt / per_img, t = mt - img * per_img;
                     const int y0 = (t / p.tiles_x) * p.th, x0 = (t % p.tiles_x) * p.tw;
@@ -185,7 +194,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
         for (int s = blockIdx.x; s < p.n_super; s += gridDim.x, ++it) {
             const int ntile = min(p.T, p.m_tiles - s * p.T);
             for (int cc = 0; cc < p.nchunks; ++cc) {
-                mbar_wait(&bfull[bbuf], bphase);
+                if (!p.b_single || s == (int)blockIdx.x) mbar_wait(&bfull[bbuf], bphase);
                 const uint32_t b_lo = d_lo + (smem_u32(sB + (size_t)bbuf * p.b_bytes) >> 4);
                 for (int t = 0; t < ntile; ++t) {
                     if (cc == 0) mbar_wait(&tempty[t], (it & 1) ^ 1);  // the epilogue has drained this accumulator
@@ -217,12 +226,12 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                         }
                         umma_commit(&aempty[stage]);
                         if (cc == p.nchunks - 1) umma_commit(&tfull[t]);
-                        if (t == ntile - 1) umma_commit(&bempty[bbuf]);
+                        if (t == ntile - 1 && !p.b_single) umma_commit(&bempty[bbuf]);
                     }
                     __syncwarp();
                     if (++stage == (uint32_t)p.stages) stage = 0, aphase ^= 1;
                 }
-                if (++bbuf == 2) bbuf = 0, bphase ^= 1;
+                if (!p.b_single && ++bbuf == 2) bbuf = 0, bphase ^= 1;
             }
         }
     } else {
@@ -256,6 +265,67 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                 mbar_wait(&tfull[t], it & 1);
                 tc_fence_after();
                 T4_TRACE(32 + 2 * tr_n, warp == 2 && lane == 0 && tr_n < 15);
+                if (p.tma_out) {
+                    // ---- staged epilogue (see conv_tc.cu): the quad's 128 rows go to a 128B-swizzled staging tile whose tile
+                    // rows start on 1024-byte atoms; the quad's first lane writes every valid tile row with one TMA bulk store
+                    // (full lines, columns / rows past the map clipped) instead of 32-line-scattered 16-byte warp stores.
+                    uint8_t* obuf = sOut + (size_t)quad * p.o_bytes;
+                    const bool issuer = (lg == 0 && lane == 0);  // exactly one thread per quad (the quad's warps have distinct lane groups)
+                    const int sr = ty * p.wl8 + tx;              // staging row of this thread's pixel
+                    const uint32_t srow = smem_u32(obuf) + (uint32_t)sr * 128u;
+                    const int y0 = (tt / p.tiles_x) * p.th, x0 = (tt % p.tiles_x) * p.tw;
+                    for (int h0 = 0; h0 < ncols; h0 += 64) {
+                        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stores that read this buffer are done
+                        asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
+                        const int hend = min(h0 + 64, ncols);
+                        for (int c0 = h0; c0 < hend; c0 += 16) {
+                            uint32_t v[16];
+                            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * p.npad + c0), v);
+                            const bf16x8 rc0 = rn0, rc1 = rn1;
+                            if (r_fast && opix >= 0 && c0 + 32 <= p.cout) rn0 = ld8(rrow + c0 + 16), rn1 = ld8(rrow + c0 + 24);
+                            tmem_ld_wait();
+                            if (ty >= p.th) continue;  // junk GEMM rows past the tile have no staging row
+                            float f[16];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 bq = *reinterpret_cast<const float4*>(sBias + c0 + 4 * q);
+                                f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
+                                f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
+                                f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);
+                                f[4 * q + 3] = act_t<ACT>(__uint_as_float(v[4 * q + 3]) + bq.w);
+                            }
+                            if (p.epi != DBL_EPI_NONE && opix >= 0) {
+                                float rr[16];
+                                if (c0 + 16 <= p.cout && p.r_vec) {
+                                    unpack8(rc0, rr);
+                                    unpack8(rc1, rr + 8);
+                                } else {
+                                    const __nv_bfloat16* rp = rrow + c0;
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) rr[i] = (c0 + i < p.cout) ? __bfloat162float(rp[i]) : 0.f;
+                                }
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) f[i] = p.epi == DBL_EPI_ADD ? f[i] + rr[i] : f[i] * rr[i];
+                            }
+                            const uint32_t j = (uint32_t)((c0 - h0) >> 3);
+                            sts128(srow + ((j ^ ((uint32_t)sr & 7u)) << 4), pack8(f).u);
+                            sts128(srow + (((j + 1) ^ ((uint32_t)sr & 7u)) << 4), pack8(f + 8).u);
+                        }
+                        fence_proxy_async();
+                        asm volatile("bar.sync %0, 128;" ::"r"(quad + 1) : "memory");
+                        if (issuer) {
+                            for (int r = 0; r < p.th; ++r)
+                                if (y0 + r < p.h) tma_store_4d(&maps.y, obuf + (size_t)r * p.wl8 * 128, h0, x0, y0 + r, img);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[t]);
+                    T4_TRACE(33 + 2 * tr_n, warp == 2 && lane == 0 && tr_n < 15);
+                    ++tr_n;
+                    continue;
+                }
                 for (int c0 = 0; c0 < ncols; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * p.npad + c0), v);
@@ -317,6 +387,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
             }
         }
     }
+    if (p.tma_out && warp >= 2 && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the bulk stores read shared memory
     tc_fence_before();
     __syncthreads();
     T4_TRACE(63, threadIdx.x == 0);
@@ -415,21 +486,34 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
     p.rows_h = p.th + 2;
     p.tiles_x = cdiv(p.w, p.tw), p.tiles_y = cdiv(p.h, p.th);
     p.m_tiles = p.n * p.tiles_x * p.tiles_y;
-    // ---- K chunking + shared-memory budget: 2 weight buffers + >= 3 activation stages
+    // ---- K chunking + shared-memory budget: weight buffers (one resident buffer when the filter is a single chunk, else
+    // two) + >= 3 activation stages (+ the staging tiles of the TMA-store epilogue when they fit without shrinking the chunk)
     const size_t fixed = 1024 + (((size_t)p.npad + 3) & ~(size_t)3) * 4 + (2 * T4_MAX_STAGES + 4 + 2 * T4_MAX_ACC) * 8 + 16;
     const int halo_px = p.rows_h * p.wl;
     const int need_px = 128 + 2 * p.wl + 2 > halo_px ? 128 + 2 * p.wl + 2 : halo_px;  // junk rows read a little past the box
+    static const int tma_out_env = getenv("DBL_TC4_TMA_OUT") ? atoi(getenv("DBL_TC4_TMA_OUT")) : 0;  // opt-in: measured SLOWER here (39 vs 37 us on 64->32 @80^2): this kernel is paced by the MMAs' A-operand reads, and the staging tiles cost activation stages
+    const bool out_ok = tma_out_env && y->dtype == DBL_BF16 && ((size_t)y->pitch * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(y->data) & 15) == 0;
+    p.wl8 = (p.wl + 7) & ~7;
+    p.o_bytes = (uint32_t)(((size_t)p.th * p.wl8 * 128 + 1023) & ~(size_t)1023);
+    const size_t out_bytes = 1024 + (size_t)(T4_EPI_WARPS / 4) * p.o_bytes;
     int cchunk = 0;
-    for (int c = 64; c >= 16; c >>= 1) {
-        if (x->c % c) continue;
-        const size_t a_b = (((size_t)need_px * c * 2) + 1023) & ~(size_t)1023;
-        const size_t b_b = (((size_t)9 * p.npad * c * 2) + 1023) & ~(size_t)1023;
-        if (fixed + 2 * b_b + 3 * a_b <= (size_t)max_smem) {
-            cchunk = c;
-            p.a_bytes = (uint32_t)a_b, p.b_bytes = (uint32_t)b_b;
-            int stages = (int)(((size_t)max_smem - fixed - 2 * b_b) / a_b);
-            p.stages = stages > T4_MAX_STAGES ? T4_MAX_STAGES : stages;
-            break;
+    for (int pass = out_ok ? 0 : 1; pass < 2 && !cchunk; ++pass) {  // pass 0: with output staging (only at the largest chunk), pass 1: without
+        const size_t extra = pass == 0 ? out_bytes : 0;
+        for (int c = 64; c >= 16; c >>= 1) {
+            if (x->c % c) continue;
+            static const int bsingle_env = getenv("DBL_TC4_BSINGLE") ? atoi(getenv("DBL_TC4_BSINGLE")) : 1;  // tuning aid
+            const int nbuf = (x->c == c && c == 64 && bsingle_env) ? 1 : 2;  // measured: resident filter helps 64->128 @40^2 (31 vs 35.5 us), hurts 32->64 @80^2 (58.6 vs 51.4 us)
+            const size_t a_b = (((size_t)need_px * c * 2) + 1023) & ~(size_t)1023;
+            const size_t b_b = (((size_t)9 * p.npad * c * 2) + 1023) & ~(size_t)1023;
+            if (fixed + extra + nbuf * b_b + 3 * a_b <= (size_t)max_smem) {
+                cchunk = c;
+                p.a_bytes = (uint32_t)a_b, p.b_bytes = (uint32_t)b_b;
+                p.b_single = nbuf == 1, p.tma_out = pass == 0;
+                int stages = (int)(((size_t)max_smem - fixed - extra - nbuf * b_b) / a_b);
+                p.stages = stages > T4_MAX_STAGES ? T4_MAX_STAGES : stages;
+                break;
+            }
+            if (pass == 0) break;  // staging must not cost chunk width
         }
     }
     DBL_REQUIRE(cchunk > 0, DBL_E_UNSUPPORTED, "conv3x3_tc4: cin %d / cout %d does not fit shared memory", x->c, y->c);
@@ -472,7 +556,14 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
         const uint32_t box[2] = {(uint32_t)cchunk, (uint32_t)p.npad};
         if (!encode4(&maps.b, w, 2, dims, strides, box, row_bytes)) return DBL_E_CUDA;
     }
-    const size_t smem = fixed + (size_t)p.stages * p.a_bytes + 2 * (size_t)p.b_bytes;
+    if (p.tma_out) {
+        const uint64_t pitchB = (uint64_t)y->pitch * 2;
+        const uint64_t dims[4] = {(uint64_t)y->c, (uint64_t)y->w, (uint64_t)y->h, (uint64_t)y->n};
+        const uint64_t strides[3] = {pitchB, pitchB * y->w, pitchB * y->w * y->h};
+        const uint32_t box[4] = {64, (uint32_t)p.tw, 1, 1};
+        if (!encode4(&maps.y, y->data, 4, dims, strides, box, 128)) return DBL_E_CUDA;
+    }
+    const size_t smem = fixed + (size_t)p.stages * p.a_bytes + (p.b_single ? 1 : 2) * (size_t)p.b_bytes + (p.tma_out ? out_bytes : 0);
     const int grid = p.n_super < num_sms ? p.n_super : num_sms;
     const int ks = cchunk / 16;
 #define DBL_T4_GO(A, K) launch_k(conv3x3_tc4_kernel<A, K>, grid, T4_THREADS, smem, st, maps, p)
