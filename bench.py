@@ -109,14 +109,14 @@ def run_reference(args):
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, per_step, steps, warmup)
     sample = f"{per_step} images/step of the {args.batch}-image workload, {steps} steps after {warmup} warm-up, oracle port (torch CPU fp32 + C NMS)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_dict(args, 1),
         "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def config_dict(args, world):
@@ -149,7 +149,18 @@ def kernel_table(rows, peaks):
     return sorted(out, key=lambda f: -f["ms"])
 
 
+_STDOUT = sys.stdout
+
+
+def emit(line: dict):
+    """the ONE JSON line on the real stdout (fd 1 itself is pointed at stderr so library banners -- NCCL's version line -- stay out)"""
+    print(json.dumps(line), file=_STDOUT, flush=True)
+
+
 def main():
+    global _STDOUT
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -162,6 +173,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=2, help="whole 64-image steps in flight per GPU (engine replicas on their own streams)")
     ap.add_argument("--kernel-table", default="", help="write the per-launch timing table (json) here")
+    ap.add_argument("--quick", action="store_true", help="device-resident leg only (for runs under ncu): prints a reduced line, never a bench value")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -223,12 +235,19 @@ def main():
         for s in side:
             main.wait_stream(s)
 
-    clk = ClockSampler(local) if rank == 0 else None  # samples SM clocks / throttle reasons every 100 ms until the e2e legs are done
+    clk = ClockSampler(local) if rank == 0 and not args.quick else None  # samples SM clocks / throttle reasons every 100 ms until the e2e legs are done
     run_steps(max(warmup, P))
     ms_total = timed(lambda: run_steps(steps), 1)
     value = args.batch * world * steps / (ms_total * 1e-3)
     kps = eng.kernels_per_step.get((key, False, False), 0)
     launches = kps * steps
+
+    if args.quick:
+        if rank == 0:
+            emit({"metric": METRIC, "quick": True, "value": round(value, 1), "ms_per_step": round(ms_total / steps, 4), "gpu_launches": launches})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public API: pinned host batches -> H2D -> predict -> D2H of the detections, every step.
     # Image sources reach the reference as uint8 and are scaled on the device (engine/predictor.py:116-134); the same
@@ -323,7 +342,7 @@ def main():
             "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in f.items() if k in ("kern", "launches", "ms", "share", "gbs", "tflops", "hbm_frac", "tensor_frac")}
                         for f in table[:8]],
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

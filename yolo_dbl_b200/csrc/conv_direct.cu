@@ -305,117 +305,8 @@ __global__ void __launch_bounds__(128) dwconv_strip_kernel(const __nv_bfloat16* 
 }
 
 
-// depthwise conv, shared-memory tiled.  One CTA = one (image, spatial tile, block of G 8-channel groups).  The input tile
-// (+halo, zero-filled outside the image = the convolution's padding) is copied once with 16-byte cp.async in its natural
-// [row][col][channel-chunk] order and the filter block sits next to it as f32 [tap][G*8].  A thread owns one output
-// column x one channel group and R consecutive output rows: every 16-byte input chunk it reads feeds up to R outputs, the
-// K filter taps of the current filter column live in registers.  Lanes run over (channel group, column), so a warp's
-// shared-memory reads are contiguous 16-byte chunks (conflict free) and its global stores are full 128-byte lines.
-template <int K, int S, int D, int R>
-__global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int h, int wd,
-                                                          int c, int xpitch, int ho, int wo, int ypitch, int act, int G, int tw, int ty,
-                                                          int tiles_x) {
-    extern __shared__ __align__(16) uint8_t dw_smem[];
-    pdl_launch_dependents();
-    constexpr int PAD = D * (K - 1) / 2;
-    constexpr int ROWS_T = (R - 1) * S + (K - 1) * D + 1;  // input rows one thread walks
-    const int th = ty * R;
-    const int ir = (th - 1) * S + (K - 1) * D + 1, ic = (tw - 1) * S + (K - 1) * D + 1;
-    const int img = blockIdx.z, cb = blockIdx.y;
-    const int oy0 = (blockIdx.x / tiles_x) * th, ox0 = (blockIdx.x % tiles_x) * tw;
-    const int c0 = cb * G * 8;
-    const int g_here = min(G, c / 8 - cb * G);  // channel groups of this block (the last block may be short)
-    float* sw = reinterpret_cast<float*>(dw_smem);                      // [K*K][G*8]
-    const uint32_t sx = smem_u32(dw_smem) + (uint32_t)(K * K * G * 32);  // [ir][ic][G] x 16 bytes
-    const int nt = blockDim.x;
-    for (int i = threadIdx.x; i < K * K * G * 8; i += nt) {
-        const int tap = i / (G * 8), cc = i - tap * (G * 8);
-        sw[i] = (cc < g_here * 8) ? w[(size_t)tap * c + c0 + cc] : 0.f;
-    }
-    pdl_wait();  // the filter block above is constant data; the activations are the previous kernel's output
-    {
-        const __nv_bfloat16* ximg = x + (size_t)img * h * wd * xpitch + c0;
-        const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
-        const int items = ir * ic * G;
-        for (int i = threadIdx.x; i < items; i += nt) {
-            const int g = i % G, pix = i / G;
-            const int ly = pix / ic, lx = pix - ly * ic;
-            const int gy = iy0 + ly, gx = ix0 + lx;
-            const bool ok = g < g_here && gy >= 0 && gy < h && gx >= 0 && gx < wd;
-            cp_async16(sx + (uint32_t)i * 16, ok ? ximg + ((size_t)gy * wd + gx) * xpitch + g * 8 : x, ok);
-        }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const int g = threadIdx.x % G, xi = (threadIdx.x / G) % tw, ys = threadIdx.x / (G * tw);
-    if (ys >= ty || g >= g_here) return;
-    const int ox = ox0 + xi, oyb = oy0 + ys * R;
-    if (ox >= wo || oyb >= ho) return;
-    float acc[R][8];
-    {
-        float b8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + g * 8 + 4));
-            b8[0] = b0.x, b8[1] = b0.y, b8[2] = b0.z, b8[3] = b0.w, b8[4] = b1.x, b8[5] = b1.y, b8[6] = b1.z, b8[7] = b1.w;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[r][i] = b8[i];
-    }
-    const uint32_t xbase = sx + (uint32_t)(((ys * R * S) * ic + xi * S) * G + g) * 16;
-    // the filter-column loop stays ROLLED: fully unrolled this kernel is 65 KB of straight-line code that every warp runs
-    // exactly once, and ncu showed it stalled on instruction fetch for half of its cycles
-#pragma unroll 1
-    for (int kx = 0; kx < K; ++kx) {
-        float wk[K][8];
-#pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * G * 8 + g * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + (ky * K + kx) * G * 8 + g * 8 + 4);
-            wk[ky][0] = w0.x, wk[ky][1] = w0.y, wk[ky][2] = w0.z, wk[ky][3] = w0.w;
-            wk[ky][4] = w1.x, wk[ky][5] = w1.y, wk[ky][6] = w1.z, wk[ky][7] = w1.w;
-        }
-#pragma unroll
-        for (int iy = 0; iy < ROWS_T; ++iy) {
-            bool used = false;  // compile-time: does any of the R outputs read input row iy?
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int d = iy - r * S;
-                if (d >= 0 && d % D == 0 && d / D < K) used = true;
-            }
-            if (!used) continue;
-            bf16x8 v;
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v.u.x), "=r"(v.u.y), "=r"(v.u.z), "=r"(v.u.w)
-                         : "r"(xbase + (uint32_t)((iy * ic + kx * D) * G) * 16));
-            float xv[8];
-            unpack8(v, xv);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int d = iy - r * S;
-                if (d >= 0 && d % D == 0 && d / D < K) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[r][i] = fmaf(xv[i], wk[d / D][i], acc[r][i]);
-                }
-            }
-        }
-    }
-    __nv_bfloat16* yp = y + (((size_t)img * ho + oyb) * wo + ox) * ypitch + c0 + g * 8;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (oyb + r < ho) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[r][i] = act == DBL_ACT_SILU ? silu_fast(acc[r][i]) : acc[r][i];
-            stg8(yp + (size_t)r * wo * ypitch, pack8(acc[r]));
-        }
-    }
-}
-
-// Third generation of the tiled depthwise kernel (v1 above: issue slots 47 % busy at 14 resident warps per SM, 128
-// registers).  Same idea -- one CTA = one (image, spatial tile, channel block), input tile + halo staged once with
+// Tiled depthwise kernel, third generation (the first -- 8 channels x 4 rows per thread, scalar FMAs, 128 registers -- ran
+// its issue slots 47 % busy at 14 resident warps per SM).  One CTA = one (image, spatial tile, channel block), input tile + halo staged once with
 // 16-byte cp.async (zero fill = padding), filter block next to it as f32 -- but
 //  * a thread owns FOUR channels (one 8-byte shared-memory load per tap row) and R = 8 (or 4) output rows: the K filter
 //    taps of the current filter column are 28 registers instead of 56, the whole kernel fits ~80 registers, so 4-5 CTAs
@@ -424,7 +315,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tile_kernel(const __nv_bfloat16
 //    register pair {w << 16, w & 0xffff0000}, the filter is read as float2.  Half the FMA issue slots, which leaves room
 //    for the LDS / unpack instructions next to the FMA pipe that is the real bound (49 FMA per output for 7x7);
 //  * staging index math through float reciprocals instead of two integer divisions per 16-byte chunk.
-// Numerics are those of v1 (IEEE fma per element, same summation order).
+// Numerics are those of the scalar form (IEEE fma per element, same summation order).
 // G4 = 4-channel groups per CTA (even: the staging copy moves 16 bytes = two groups); threads = G4 * tw * ty.
 template <int K, int S, int D, int R>
 __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
@@ -478,7 +369,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat1
         for (int r = 0; r < R; ++r) acc[r][0] = b2.x, acc[r][1] = b2.y;
     }
     const uint32_t xbase = sx + (uint32_t)(((ys * R * S) * ic + xi * S) * G4 + g) * 8;
-    // the filter-column loop stays ROLLED (fully unrolled, v1 was instruction-fetch bound)
+    // the filter-column loop stays ROLLED (fully unrolled, the first generation was instruction-fetch bound)
 #pragma unroll 1
     for (int kx = 0; kx < K; ++kx) {
         unsigned long long wk[K][2];
@@ -547,37 +438,6 @@ static bool dw_pick_tile3(int k, int s, int d, int R, int c, int ho, int wo, int
             }
     }
     return found;
-}
-
-// host-side tile choice for dwconv_tile_kernel (measured with tools/dw_bench.py): two channel groups per CTA (32-byte
-// chunks = full sectors), rows as wide as the map (<= 40 columns), as many 4-row strips as fit 256 threads; widths and
-// strip counts are picked to minimise the padding of the last tile.  Returns false when no tile fits.
-static bool dw_pick_tile(int k, int s, int d, int R, int c, int ho, int wo, int nbuf, int* G_, int* tw_, int* ty_, size_t* smem_) {
-    const int cg = c / 8, G = cg >= 2 ? 2 : 1;
-    int tw = wo <= 40 ? wo : 40;
-    if (wo > 40) {
-        int best_pad = 1 << 30;
-        for (int t = 40; t >= 20; --t) {
-            const int pad = cdiv(wo, t) * t - wo;
-            if (pad < best_pad) best_pad = pad, tw = t;
-        }
-    }
-    if (tw < 4) tw = 4;
-    const int strips = cdiv(ho, R);
-    int ty = 0;
-    int best_pad = 1 << 30;
-    for (int t = 256 / (G * tw); t >= 1; --t) {
-        const int th = t * R;
-        const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
-        if ((size_t)k * k * G * 32 + (size_t)nbuf * ir * ic * G * 16 > (size_t)(nbuf > 1 ? 100 : 64) * 1024) continue;
-        const int pad = cdiv(strips, t) * t - strips;
-        if (pad < best_pad) best_pad = pad, ty = t;
-    }
-    if (ty < 1) return false;
-    const int th = ty * R;
-    const int ir = (th - 1) * s + (k - 1) * d + 1, ic = (tw - 1) * s + (k - 1) * d + 1;
-    *G_ = G, *tw_ = tw, *ty_ = ty, *smem_ = (size_t)k * k * G * 32 + (size_t)nbuf * ir * ic * G * 16;
-    return true;
 }
 
 }  // namespace dbl

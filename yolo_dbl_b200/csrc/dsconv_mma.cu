@@ -304,6 +304,24 @@ static int launch_ds(const dbl_tensor* x, const float* wdw, const float* bdw, co
         set_error("dbl_dsconv: no tile fits shared memory (cin %d cout %d k %d)", CIN, COUT, K);
         return DBL_E_UNSUPPORTED;
     }
+    {
+        static const char* force = getenv("DBL_DS_TILE");  // tuning aid: "tw,th" (th a multiple of 4)
+        int ftw, fth;
+        if (force && sscanf(force, "%d,%d", &ftw, &fth) == 2 && ftw >= 4 && fth >= 4 && fth % 4 == 0 && ftw * fth <= 320) {
+            const int ir = (fth - 1) * S + K, ic = (ftw - 1) * S + K, mpad = (ftw * fth + 15) & ~15;
+            const size_t sm = 256 + (size_t)(CIN / 16) * (COUT / 8) * 256 + (size_t)K * K * CIN * 4 + (size_t)(COUT + CIN) * 4 +
+                              (size_t)(CIN / 8) * (mpad + 1) * 16 + (size_t)ir * ic * CIN * 2;
+            if (sm <= (size_t)max_smem - 1024) {
+                p.tw = ftw, p.th = fth, smem = sm;
+                const int items = 2 * (CIN / 8) * ftw * (fth / (fth % 8 == 0 ? 8 : 4));
+                nt = (items + 31) / 32 * 32;
+                if (nt > 512) nt = 512;
+                if (nt < 64) nt = 64;
+            }
+        }
+        static const char* dbg = getenv("DBL_DS_DEBUG");
+        if (dbg) fprintf(stderr, "dsconv k%d s%d %d->%d %dx%d: tw=%d th=%d threads=%d smem=%zu\n", K, S, CIN, COUT, y->h, y->w, p.tw, p.th, nt, smem);
+    }
     p.tiles_x = cdiv(y->w, p.tw), p.tiles_y = cdiv(y->h, p.th);
     DBL_REQUIRE(p.tiles_y <= 65535 && x->n <= 65535, DBL_E_UNSUPPORTED, "dbl_dsconv: grid too large");
     launch_k(dsconv_mma_kernel<K, S, CIN, COUT, DW_ACT>, dim3(p.tiles_x, p.tiles_y, x->n), nt, smem, st, p);
