@@ -154,6 +154,27 @@ def test_uint8_input_and_pipelined_stream_match_float_path():
     for (r, c), (wr, wc) in zip(got, want):
         assert torch.equal(c, wc) and torch.equal(r, wr)
     assert int(sum(int(c.sum()) for _, c in got)) > 0
+    # any number of engine replicas in flight (own buffers, own graph, own stream) gives the same detections, with and without
+    # the completion event; five batches so that staging / result slots and replicas are all reused
+    xs5 = xs + [(synth_images(2, 96, 128, 30 + i) * 255).round().to(torch.uint8) for i in range(2)]
+    want5 = []
+    for x in xs5:
+        rows, counts = m.detect(x.pin_memory(), conf=0.1, iou=0.7)
+        want5.append((rows.clone(), counts.clone()))
+    for p in (1, 2, 3):
+        got = [(r.clone(), c.clone()) for r, c in m.detect_stream([x.pin_memory() for x in xs5], in_flight=p, conf=0.1, iou=0.7)]
+        assert len(got) == 5
+        for (r, c), (wr, wc) in zip(got, want5):
+            assert torch.equal(c, wc) and torch.equal(r, wr), f"in_flight={p}"
+    side = torch.cuda.Stream()
+    n = 0
+    for (r, c, ev), (wr, wc) in zip(m.detect_stream([x.pin_memory() for x in xs5], with_event=True, in_flight=2, conf=0.1, iou=0.7), want5):
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            rc, cc = r.cpu(), c.cpu()  # synchronous copies on the side stream: the caller has read the slot before advancing
+        assert torch.equal(cc, wc.cpu()) and torch.equal(rc, wr.cpu())
+        n += 1
+    assert n == 5
 
 
 def test_fused_stem_engine_matches_layerwise_engine():
