@@ -628,10 +628,10 @@ static int launch_conv_mma(const dbl_tensor* x, const void* wp, const float* b, 
     return check_launch("dbl_conv3x3_mma");
 }
 
-template <int C0, int C1, typename TIN>
+template <int C0, int C1, typename TIN, int TH = 16>
 static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0, const float* b0, const void* w1p, const float* b1,
                             const dbl_tensor* y, float scale, cudaStream_t st) {
-    constexpr int TH = 16, TW = 30, NWARPS = 8;  // input row pitch 64 pixels, layer-0 sub-tile pitch 32: index math = shifts
+    constexpr int TW = 30, NWARPS = 8;  // input row pitch 64 pixels, layer-0 sub-tile pitch 32: index math = shifts
     using K = StemCfg<C0, C1, TH, TW>;
     StemParams p;
     p.x = x, p.w0 = w0, p.b0 = b0, p.w1 = reinterpret_cast<const uint2*>(w1p), p.b1 = b1;
@@ -639,7 +639,7 @@ static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0,
     p.n = n, p.h = h, p.w = w, p.ho = y->h, p.wo = y->w, p.ypitch = y->pitch, p.in_scale = scale;
     p.tiles_x = cdiv(y->w, TW), p.tiles_y = cdiv(y->h, TH);
     auto kern = stem_pair_kernel<C0, C1, TH, TW, NWARPS, TIN>;
-    static thread_local bool configured = false;
+    static thread_local bool configured = false;  // one flag per template instantiation
     if (!configured) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
         if (e != cudaSuccess) {
@@ -676,11 +676,6 @@ extern "C" int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, 
     return check_launch("dbl_mma_pack_weights");
 }
 
-static int bn_warps() {
-    static const int v = getenv("DBL_BN_WARPS") ? atoi(getenv("DBL_BN_WARPS")) : 8;
-    return v;
-}
-
 extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
                                  int shortcut, const dbl_tensor* y, dbl_stream_t stream) {
     DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w1_packed && w2_packed, DBL_E_ARG, "dbl_bottleneck3x3: null/invalid argument");
@@ -692,14 +687,10 @@ extern "C" int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, con
     switch (x->c) {
         // tile width 28 -> row pitch 32: every 16-row GEMM block is half a tile row (index math = shifts) and the
         // m-block counts of both phases divide evenly over the warps
-        case 16:
-            if (bn_warps() == 16) return launch_bottleneck<16, 30, 28, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-            if (bn_warps() == 12) return launch_bottleneck<16, 30, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-            return launch_bottleneck<16, 30, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-        case 32:
-            if (bn_warps() == 16) return launch_bottleneck<32, 14, 28, 16, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-            if (bn_warps() == 12) return launch_bottleneck<32, 14, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
-            return launch_bottleneck<32, 14, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        // measured (layer 2 / layer 4 of YOLO-DBL-n at batch 64): C=16: 22 rows (3 resident CTAs) 266 us, 30 rows 285 us, 14 rows 269 us,
+        // 46 rows 341 us; C=32: 14 rows 182 us, 22 rows 211 us, 6 rows 206 us; 12 or 16 warps per CTA are slower than 8 for both
+        case 16: return launch_bottleneck<16, 22, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
+        case 32: return launch_bottleneck<32, 14, 28, 8, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
         case 64: return launch_bottleneck<64, 10, 28, 12, 2>(x, w1_packed, b1, w2_packed, b2, shortcut, y, st);
         default: break;
     }
@@ -720,9 +711,7 @@ extern "C" int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const 
     cudaStream_t st = as_stream(stream);
     const dbl_tensor* rr = epi != DBL_EPI_NONE ? r : nullptr;
 #define DBL_CM(CI, CO, S, TH) /* tile width 30 (stride 1) / 31 (stride 2) -> (sub-)tile row pitch 32 */ \
-    if (x->c == CI && y->c == CO && stride == S)                                                                                         \
-        return bn_warps() == 16 ? launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 16, 2>(x, w_packed, bias, rr, y, act, epi, st) \
-                                : launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
+    if (x->c == CI && y->c == CO && stride == S) return launch_conv_mma<CI, CO, S, TH, 32 - (S == 1 ? 2 : 1), 8, 2>(x, w_packed, bias, rr, y, act, epi, st)
     DBL_CM(8, 16, 2, 8);
     DBL_CM(16, 32, 2, 8);
     DBL_CM(32, 64, 2, 8);
@@ -744,6 +733,7 @@ extern "C" int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int 
     DBL_REQUIRE(vec8_ok(y), DBL_E_ARG, "dbl_stem_pair: y must be bf16 NHWC, 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const float scale = x_is_u8 ? 1.0f / 255.0f : 1.0f;
+    // tile height 16 measured best (layer 0+1 at batch 64: 8 rows 349 us, 16 rows 337 us, 32 rows 503 us, 4 rows 420 us)
 #define DBL_SP(A, B)                                                                                             \
     if (c0 == A && y->c == B)                                                                                    \
         return x_is_u8 ? launch_stem_pair<A, B, uint8_t>(x_nchw, n, h, w, w0, b0, w1_packed, b1, y, scale, st) \
