@@ -346,24 +346,7 @@ __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat1
     {
         const __nv_bfloat16* ximg = x + (size_t)img * h * wd * xpitch + c0;
         const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
-        const int G8 = G4 >> 1, g8_here = c_here >> 3;
-        const int chunks = ir * ic * G8;
-        // (row, column, group) of a thread's first 16-byte chunk through exact float reciprocals ((q + 0.5) / d is never within
-        // float error of an integer), then stepped by adds: the flat loop spent ~40 instructions per chunk on div / mod
-        const float inv_g = 1.0f / (float)G8, inv_ic = 1.0f / (float)ic;
-        int pix = __float2int_rd(((float)threadIdx.x + 0.5f) * inv_g), g = threadIdx.x - pix * G8;
-        int ly = __float2int_rd(((float)pix + 0.5f) * inv_ic), lx = pix - ly * ic;
-        const int dpix = __float2int_rd(((float)nt + 0.5f) * inv_g), dg = nt - dpix * G8;
-        const int dly = __float2int_rd(((float)dpix + 0.5f) * inv_ic), dlx = dpix - dly * ic;
-        for (int i = threadIdx.x; i < chunks; i += nt) {
-            const int gy = iy0 + ly, gx = ix0 + lx;
-            const bool ok = g < g8_here && gy >= 0 && gy < h && gx >= 0 && gx < wd;
-            cp_async16(sx + (uint32_t)i * 16, ok ? ximg + ((size_t)gy * wd + gx) * xpitch + g * 8 : x, ok);
-            g += dg;
-            const int cg = g >= G8 ? 1 : 0;
-            g -= cg * G8, lx += dlx + cg, ly += dly;
-            if (lx >= ic) lx -= ic, ++ly;
-        }
+        stage_tile16(sx, ximg, x, ir, ic, G4 >> 1, c_here >> 3, iy0, ix0, h, wd, xpitch, threadIdx.x, nt);
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();

@@ -176,21 +176,7 @@ __global__ void __launch_bounds__(512) dsconv_mma_kernel(const DsParams p) {
     {
         const __nv_bfloat16* ximg = p.x + (size_t)img * p.h * p.w * p.xpitch;
         const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
-        const int items = ir * ic * G;
-        // (row, column, group) of the first chunk once, then stepped by adds (no div / mod per 16-byte chunk)
-        int pix = tid / G, g = tid % G;
-        int ly = pix / ic, lx = pix - ly * ic;
-        const int dpix = NT / G, dg = NT % G;
-        const int dly = dpix / ic, dlx = dpix - dly * ic;
-        for (int i = tid; i < items; i += NT) {
-            const int gy = iy0 + ly, gx = ix0 + lx;
-            const bool ok = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-            cp_async16(sX + (uint32_t)i * 16, ok ? ximg + ((size_t)gy * p.w + gx) * p.xpitch + g * 8 : p.x, ok);
-            g += dg;
-            const int cg = g >= G ? 1 : 0;
-            g -= cg * G, lx += dlx + cg, ly += dly;
-            if (lx >= ic) lx -= ic, ++ly;
-        }
+        stage_tile16(sX, ximg, p.x, ir, ic, G, G, iy0, ix0, p.h, p.w, p.xpitch, tid, NT);
     }
     cp_async_commit();
     cp_async_wait<0>();

@@ -105,6 +105,33 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, b
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Stage a [rows][cols][G8] tile of 16-byte chunks (NHWC bf16, 8 channels per chunk) with cp.async, zero-filling everything
+// outside the image (= the convolution's padding).  A thread keeps its (column, channel group) and walks down the rows: per
+// chunk one row bounds test, one pointer add and the cp.async.  (ncu source view of the flat `for (i = tid; i < chunks; i += nt)`
+// form: ~68 instructions per chunk on index decomposition and 64-bit address arithmetic -- 58 % of the 3x3 depthwise kernel.)
+//   src_img: channel 0 of this CTA's channel block at pixel (0,0) of the image;  dummy: any valid global address (never read)
+__device__ __forceinline__ void stage_tile16(uint32_t dst_smem, const __nv_bfloat16* src_img, const void* dummy, int rows, int cols, int G8,
+                                             int g8_valid, int iy0, int ix0, int h, int w, int xpitch, int tid, int nt) {
+    const int row_items = cols * G8;
+    const int per_pass = row_items < nt ? row_items : nt;  // columns x groups handled per pass
+    const int rpp = nt / per_pass;                          // rows per pass (>= 1)
+    const int r0 = __float2int_rd(((float)tid + 0.5f) * (1.0f / (float)per_pass));  // exact: (q + 0.5) / d is never an integer
+    const int e_in = tid - r0 * per_pass;
+    if (r0 >= rpp) return;
+    for (int e = e_in; e < row_items; e += per_pass) {  // one pass unless a tile row is longer than the CTA
+        const int lx = G8 == 1 ? e : (G8 == 2 ? e >> 1 : e / G8), g = e - lx * G8;
+        const int gx = ix0 + lx;
+        const bool colok = g < g8_valid && gx >= 0 && gx < w;
+        const __nv_bfloat16* src = src_img + ((long long)(iy0 + r0) * w + gx) * xpitch + g * 8;
+        const long long rstep = (long long)rpp * w * xpitch;
+        uint32_t dst = dst_smem + (uint32_t)(r0 * row_items + e) * 16;
+        for (int ly = r0; ly < rows; ly += rpp) {
+            const bool ok = colok && (unsigned)(iy0 + ly) < (unsigned)h;
+            cp_async16(dst, ok ? static_cast<const void*>(src) : dummy, ok);
+            src += rstep, dst += (uint32_t)(rpp * row_items) * 16;
+        }
+    }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // SiLU through one MUFU: x*sigmoid(x) = 0.5x(1 + tanh(0.5x)); tanh.approx is ~2^-11 accurate, far below bf16 rounding
