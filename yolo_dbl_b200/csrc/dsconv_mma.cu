@@ -90,13 +90,17 @@ __device__ __forceinline__ void ds_depthwise(uint32_t sX, uint32_t sA, const flo
     constexpr int ROWS_T = (R - 1) * S + K;
     const int strips = th / R;
     const int items = G4 * tw * strips;
+    const uint32_t wd_s = smem_u32(sWd);
     for (int it = tid; it < items; it += NT) {
         const int g = it % G4, rest = it / G4;
         const int xi = rest % tw, ys = rest / tw;
         unsigned long long acc[R][2];
         {
             ulonglong2 b2 = make_ulonglong2(0ull, 0ull);
-            if (DW_ACT) b2 = *reinterpret_cast<const ulonglong2*>(sBd + g * 4);
+            if (DW_ACT) {
+                const uint4 bb = lds128(smem_u32(sBd) + (uint32_t)g * 16);
+                b2 = make_ulonglong2(((unsigned long long)bb.y << 32) | bb.x, ((unsigned long long)bb.w << 32) | bb.z);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r][0] = b2.x, acc[r][1] = b2.y;
         }
@@ -106,8 +110,9 @@ __device__ __forceinline__ void ds_depthwise(uint32_t sX, uint32_t sA, const flo
             unsigned long long wk[K][2];
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
-                const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(sWd + (ky * K + kx) * CIN + g * 4);
-                wk[ky][0] = w0.x, wk[ky][1] = w0.y;
+                // explicit shared-memory load: through the generic `const float*` parameter ptxas emitted LD.E.128 (generic) here
+                const uint4 w0 = lds128(wd_s + (uint32_t)(((ky * K + kx) * CIN + g * 4) * 4));
+                wk[ky][0] = ((unsigned long long)w0.y << 32) | w0.x, wk[ky][1] = ((unsigned long long)w0.w << 32) | w0.z;
             }
 #pragma unroll
             for (int iy = 0; iy < ROWS_T; ++iy) {
