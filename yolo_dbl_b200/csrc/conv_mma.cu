@@ -65,6 +65,7 @@ struct BnParams {
     const float* b2;
     int n, h, w, xpitch, ypitch, add;
     int tiles_x, tiles_y, ntiles;
+    fastdiv per_img, tx_div;  // tiles per image, tiles per row
 };
 
 template <int C, int TH, int TW>
@@ -104,9 +105,11 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
     pdl_launch_dependents();
 
     auto prefetch = [&](int tile, int buf) {
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int img = tile / per_img, r = tile - img * per_img;
-        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        // tile -> (image, tile row, tile column) by multiply-high (four integer divisions per tile were ~100 of the ~630
+        // instructions a warp spends on a tile of the thin stride-2 conv)
+        const int img = (int)fdiv((uint32_t)tile, p.per_img), r = tile - img * (int)p.per_img.d;
+        const int tyi = (int)fdiv((uint32_t)r, p.tx_div);
+        const int oy0 = tyi * TH, ox0 = (r - tyi * p.tiles_x) * TW;
         const uint32_t dst0 = sIn + buf * K::IN_BYTES;
         // a thread keeps its (plane, column) and walks down the rows: per 16-byte item one bounds test, one pointer add and
         // the cp.async (the flat item loop spent ~125 instructions per item on div/mod and 64-bit address arithmetic)
@@ -155,9 +158,11 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
         cp_async_wait<1>();
         __syncthreads();
 
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int img = tile / per_img, r = tile - img * per_img;
-        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        // tile -> (image, tile row, tile column) by multiply-high (four integer divisions per tile were ~100 of the ~630
+        // instructions a warp spends on a tile of the thin stride-2 conv)
+        const int img = (int)fdiv((uint32_t)tile, p.per_img), r = tile - img * (int)p.per_img.d;
+        const int tyi = (int)fdiv((uint32_t)r, p.tx_div);
+        const int oy0 = tyi * TH, ox0 = (r - tyi * p.tiles_x) * TW;
         const uint32_t in = sIn + buf * K::IN_BYTES;
 
         // ---------------- cv1: hidden tile (TH+2 rows, pitch WI) ----------------
@@ -242,6 +247,7 @@ struct CmParams {
     const float* b;
     int n, h, wd, ho, wo, xpitch, ypitch, rpitch, act, epi;
     int tiles_x, tiles_y, ntiles;
+    fastdiv per_img, tx_div;  // tiles per image, tiles per row
 };
 
 template <int CIN, int COUT, int S, int TH, int TW>
@@ -277,9 +283,11 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
     pdl_launch_dependents();
 
     auto prefetch = [&](int tile, int buf) {
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int img = tile / per_img, r = tile - img * per_img;
-        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        // tile -> (image, tile row, tile column) by multiply-high (four integer divisions per tile were ~100 of the ~630
+        // instructions a warp spends on a tile of the thin stride-2 conv)
+        const int img = (int)fdiv((uint32_t)tile, p.per_img), r = tile - img * (int)p.per_img.d;
+        const int tyi = (int)fdiv((uint32_t)r, p.tx_div);
+        const int oy0 = tyi * TH, ox0 = (r - tyi * p.tiles_x) * TW;
         const uint32_t dst0 = sIn + buf * K::IN_BYTES;
         constexpr int ROWS = S * TH + (S == 1 ? 2 : 1), COLS = S * TW + (S == 1 ? 2 : 1);  // input footprint of the tile
         // (plane, column) fixed per thread, rows walked with a pointer increment (see bottleneck_mma_kernel)
@@ -323,9 +331,11 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int img = tile / per_img, r = tile - img * per_img;
-        const int oy0 = (r / p.tiles_x) * TH, ox0 = (r % p.tiles_x) * TW;
+        // tile -> (image, tile row, tile column) by multiply-high (four integer divisions per tile were ~100 of the ~630
+        // instructions a warp spends on a tile of the thin stride-2 conv)
+        const int img = (int)fdiv((uint32_t)tile, p.per_img), r = tile - img * (int)p.per_img.d;
+        const int tyi = (int)fdiv((uint32_t)r, p.tx_div);
+        const int oy0 = tyi * TH, ox0 = (r - tyi * p.tiles_x) * TW;
         const uint32_t in = sIn + buf * K::IN_BYTES;
         const size_t tile0 = ((size_t)img * p.ho + oy0) * p.wo + ox0;  // 64-bit once per tile, 32-bit offsets per pixel
         __nv_bfloat16* const ytile = p.y + tile0 * p.ypitch + t * 2 * K::NB;
@@ -599,6 +609,7 @@ static int launch_bottleneck(const dbl_tensor* x, const void* w1p, const float* 
     p.w1 = reinterpret_cast<const uint2*>(w1p), p.w2 = reinterpret_cast<const uint2*>(w2p), p.b1 = b1, p.b2 = b2;
     p.n = x->n, p.h = x->h, p.w = x->w, p.xpitch = x->pitch, p.ypitch = y->pitch, p.add = add;
     p.tiles_x = cdiv(x->w, TW), p.tiles_y = cdiv(x->h, TH), p.ntiles = x->n * p.tiles_x * p.tiles_y;
+    p.per_img = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.ntiles), p.tx_div = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
     auto kern = bottleneck_mma_kernel<C, TH, TW, NWARPS, MB>;
     int grid = 0;
     const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_bottleneck3x3", &grid);
@@ -619,6 +630,7 @@ static int launch_conv_mma(const dbl_tensor* x, const void* wp, const float* b, 
     p.n = x->n, p.h = x->h, p.wd = x->w, p.ho = y->h, p.wo = y->w, p.xpitch = x->pitch, p.ypitch = y->pitch, p.rpitch = r ? r->pitch : 0;
     p.act = act, p.epi = r ? epi : DBL_EPI_NONE;
     p.tiles_x = cdiv(y->w, TW), p.tiles_y = cdiv(y->h, TH), p.ntiles = x->n * p.tiles_x * p.tiles_y;
+    p.per_img = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y), (uint64_t)p.ntiles), p.tx_div = make_fastdiv((uint32_t)p.tiles_x, (uint64_t)p.tiles_x * p.tiles_y);
     auto kern = conv3x3_mma_kernel<CIN, COUT, S, TH, TW, NWARPS, MB>;
     int grid = 0;
     const int rc = launch_persistent(kern, K::SMEM, NWARPS * 32, p.ntiles, st, "dbl_conv3x3_mma", &grid);

@@ -55,6 +55,18 @@ static inline bool same_shape(const dbl_tensor* a, const dbl_tensor* b) {
     return a->n == b->n && a->h == b->h && a->w == b->w && a->c == b->c;
 }
 
+// ---- division of a tile index by a run-time constant without the ~25-instruction integer division ---------------------
+// q = umulhi(x, m) with m = floor(2^32 / d) + 1 is exact while x * d < 2^32; the host leaves m = 0 (plain division) otherwise.
+struct fastdiv {
+    uint32_t d, m;
+};
+static inline fastdiv make_fastdiv(uint32_t d, uint64_t max_x) {
+    fastdiv f{d, 0};
+    if (d > 1 && max_x * d < (1ull << 32)) f.m = (uint32_t)((1ull << 32) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, fastdiv f) { return f.m ? __umulhi(x, f.m) : x / f.d; }
+
 // ---- device math ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
