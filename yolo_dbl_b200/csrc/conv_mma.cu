@@ -467,18 +467,30 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
     {
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)img * 3 * p.h * p.w;
         const size_t plane = (size_t)p.h * p.w;
-        // a thread keeps its column and walks down the rows (NT / PI rows per pass): no div/mod per pixel
-        static_assert(NT % K::PI == 0, "threads must cover whole input rows");
-        constexpr int RPP = NT / K::PI;
-        const int lx = tid % K::PI, ly0 = tid / K::PI;
+        // a thread keeps a PAIR of columns and walks down the rows (2 * NT / PI rows per pass): no div/mod per pixel, one 8-byte
+        // (f32) / 2-byte (u8) load per colour plane and one 16-byte shared store per two pixels.  Tile origins and the image width
+        // are even, so a pair is either inside the image or outside it as a whole.
+        static_assert(NT % (K::PI / 2) == 0, "threads must cover whole input rows");
+        constexpr int RPP = NT / (K::PI / 2);
+        const int lx = (tid % (K::PI / 2)) * 2, ly0 = tid / (K::PI / 2);
         const int gx = 2 * ox0 - 2 + lx;
-        const bool colok = gx >= 0 && gx < p.w;
+        const bool colok = gx >= 0 && gx + 1 < p.w;
         const TIN* s = xin + (size_t)(2 * oy0 - 2 + ly0) * p.w + gx;
         uint32_t dst = sIn + (uint32_t)((ly0 * K::PI + lx) * 8);
         for (int ly = ly0; ly < K::RI; ly += RPP) {
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-            if (colok && (unsigned)(2 * oy0 - 2 + ly) < (unsigned)p.h) c0 = (float)__ldg(s), c1 = (float)__ldg(s + plane), c2 = (float)__ldg(s + 2 * plane);
-            sts64(dst, make_uint2(pack2(c0, c1), pack2(c2, 0.f)));
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f;
+            if (colok && (unsigned)(2 * oy0 - 2 + ly) < (unsigned)p.h) {
+                if (sizeof(TIN) == 4) {
+                    const float2 va = __ldg(reinterpret_cast<const float2*>(s)), vb = __ldg(reinterpret_cast<const float2*>(s + plane)),
+                                 vc = __ldg(reinterpret_cast<const float2*>(s + 2 * plane));
+                    a0 = va.x, a1 = va.y, b0 = vb.x, b1 = vb.y, c0 = vc.x, c1 = vc.y;
+                } else {
+                    const uchar2 va = __ldg(reinterpret_cast<const uchar2*>(s)), vb = __ldg(reinterpret_cast<const uchar2*>(s + plane)),
+                                 vc = __ldg(reinterpret_cast<const uchar2*>(s + 2 * plane));
+                    a0 = (float)va.x, a1 = (float)va.y, b0 = (float)vb.x, b1 = (float)vb.y, c0 = (float)vc.x, c1 = (float)vc.y;
+                }
+            }
+            sts128(dst, make_uint4(pack2(a0, b0), pack2(c0, 0.f), pack2(a1, b1), pack2(c1, 0.f)));
             s += (size_t)RPP * p.w, dst += RPP * K::PI * 8;
         }
         // the few pixels past the last row that junk GEMM rows touch: keep them finite
@@ -516,21 +528,28 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
                     for (int j = 0; j < K::NB0; ++j) mma16816(acc[mb][j], a, bw[ky][j].x, bw[ky][j].y);
                 }
             }
+            // The MB = 2 blocks of an iteration are 32 consecutive GEMM rows of ONE layer-0 row (PI = 64, m0 even): the row index,
+            // its bounds test and the row / parity part of the parity-sub-tile address are computed once, the four (block, half)
+            // stores differ by constants.  (ncu source view: this epilogue was ~70 of the loop's 113 instructions.)
+            static_assert(K::PI == 64 && MB == 2, "layer-0 epilogue assumes 4 m-blocks per row and block pairs");
+            const int ly = m0 >> 2, lx0 = (m0 & 3) * 16 + g;
+            if (ly < K::R0) {
+                const bool rowin = (unsigned)(2 * oy0 - 1 + ly) < (unsigned)p.h;
+                const int sub0 = ((ly & 1) * 2 + (g & 1)) * K::SUB_PX + (ly >> 1) * K::WP + (lx0 >> 1);
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-                if (m0 + mb >= K::M0) break;
+                for (int mb = 0; mb < MB; ++mb) {
+                    if (m0 + mb >= K::M0) break;
 #pragma unroll
-                for (int rh = 0; rh < 2; ++rh) {
-                    const int q = (m0 + mb) * 16 + g + 8 * rh;
-                    const int ly = q / K::PI, lx = q - ly * K::PI;
-                    if (ly >= K::R0 || lx >= K::W0) continue;
-                    const bool inside = (unsigned)(2 * oy0 - 1 + ly) < (unsigned)p.h && (unsigned)(2 * ox0 - 1 + lx) < (unsigned)p.w;  // layer 1 zero-pads layer 0's OUTPUT
-                    uint32_t v[K::NB0];
+                    for (int rh = 0; rh < 2; ++rh) {
+                        const int lx = lx0 + mb * 16 + rh * 8;
+                        if (lx >= K::W0) continue;
+                        const bool inside = rowin && (unsigned)(2 * ox0 - 1 + lx) < (unsigned)p.w;  // layer 1 zero-pads layer 0's OUTPUT
+                        uint32_t v[K::NB0];
 #pragma unroll
-                    for (int j = 0; j < K::NB0; ++j)
-                        v[j] = inside ? pack2(silu_fast(acc[mb][j][2 * rh]), silu_fast(acc[mb][j][2 * rh + 1])) : 0u;
-                    const int sub = ((ly & 1) * 2 + (lx & 1)) * K::SUB_PX + (ly >> 1) * K::WP + (lx >> 1);
-                    planar_store<K::NB0>(sL0, K::PS0, sub, t, v);
+                        for (int j = 0; j < K::NB0; ++j)
+                            v[j] = inside ? pack2(silu_fast(acc[mb][j][2 * rh]), silu_fast(acc[mb][j][2 * rh + 1])) : 0u;
+                        planar_store<K::NB0>(sL0, K::PS0, sub0 + mb * 8 + rh * 4, t, v);
+                    }
                 }
             }
         }
@@ -743,6 +762,8 @@ extern "C" int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int 
     DBL_REQUIRE(x_nchw && w0 && w1_packed && valid_tensor(y), DBL_E_ARG, "dbl_stem_pair: null/invalid argument");
     DBL_REQUIRE(h % 2 == 0 && w % 2 == 0 && y->n == n && y->h == h / 2 && y->w == w / 2, DBL_E_ARG, "dbl_stem_pair: output shape mismatch");
     DBL_REQUIRE(vec8_ok(y), DBL_E_ARG, "dbl_stem_pair: y must be bf16 NHWC, 16-byte aligned");
+    DBL_REQUIRE((reinterpret_cast<uintptr_t>(x_nchw) & (x_is_u8 ? 1 : 7)) == 0, DBL_E_ARG, "dbl_stem_pair: x must be %d-byte aligned (pixel pairs are loaded at once)",
+                x_is_u8 ? 2 : 8);
     cudaStream_t st = as_stream(stream);
     const float scale = x_is_u8 ? 1.0f / 255.0f : 1.0f;
     // tile height 16 measured best (layer 0+1 at batch 64: 8 rows 349 us, 16 rows 337 us, 32 rows 503 us, 4 rows 420 us)
