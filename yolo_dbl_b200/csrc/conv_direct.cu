@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat1
     const int th = ty * R;
     const int ir = (th - 1) * S + (K - 1) * D + 1, ic = (tw - 1) * S + (K - 1) * D + 1;
     const int img = blockIdx.z, cb = blockIdx.y;
-    const int oy0 = (blockIdx.x / tiles_x) * th, ox0 = (blockIdx.x % tiles_x) * tw;
+    // small run-time divisions through exact float reciprocals ((q + 0.5) / d is never within float error of an integer for
+    // these magnitudes): the integer form costs ~25 instructions each, and this kernel's prologue was half of its instructions
+    const int tile_y = __float2int_rd(((float)blockIdx.x + 0.5f) * (1.0f / (float)tiles_x));
+    const int oy0 = tile_y * th, ox0 = ((int)blockIdx.x - tile_y * tiles_x) * tw;
     const int c0 = cb * G4 * 4;
     const int c_here = min(G4 * 4, c - c0);  // channels of this block (the last block may be short; a multiple of 8)
     float* sw = reinterpret_cast<float*>(dw_smem);                        // [K*K][G4*4]
@@ -350,7 +353,8 @@ __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat1
         asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const int g = threadIdx.x % G4, xi = (threadIdx.x / G4) % tw, ys = threadIdx.x / (G4 * tw);
+    const int g = threadIdx.x & (G4 - 1), rest = threadIdx.x >> (G4 == 4 ? 2 : 1);  // G4 is 2 or 4
+    const int ys = __float2int_rd(((float)rest + 0.5f) * (1.0f / (float)tw)), xi = rest - ys * tw;
     if (ys >= ty || g * 4 >= c_here) return;
     const int ox = ox0 + xi, oyb = oy0 + ys * R;
     if (ox >= wo || oyb >= ho) return;
