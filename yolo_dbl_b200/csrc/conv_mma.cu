@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
             float acc[MB][K::NB1][4];
 #pragma unroll
             for (int j = 0; j < K::NB1; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(sB1 + t * 2 * K::NB1 + 2 * j);
+                const float2 bb = lds_f2(sB1 + t * 2 * K::NB1 + 2 * j);
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
             }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NWARPS * 32) bottleneck_mma_kernel(const BnPar
             float acc[MB][K::NB2][4];
 #pragma unroll
             for (int j = 0; j < K::NB2; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(sB2 + t * 2 * K::NB2 + 2 * j);
+                const float2 bb = lds_f2(sB2 + t * 2 * K::NB2 + 2 * j);
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
             }
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(NWARPS * 32) conv3x3_mma_kernel(const CmParams
             float acc[MB][K::NB][4];
 #pragma unroll
             for (int j = 0; j < K::NB; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(sB + t * 2 * K::NB + 2 * j);
+                const float2 bb = lds_f2(sB + t * 2 * K::NB + 2 * j);
 #pragma unroll
                 for (int mb = 0; mb < MB; ++mb) acc[mb][j][0] = acc[mb][j][2] = bb.x, acc[mb][j][1] = acc[mb][j][3] = bb.y;
             }
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
             for (int j = 0; j < K::NB0; ++j) bw[ky][j] = lds64(sW0 + ((ky * K::NB0 + j) * 32 + lane) * 8);
         float2 bias[K::NB0];
 #pragma unroll
-        for (int j = 0; j < K::NB0; ++j) bias[j] = *reinterpret_cast<const float2*>(sB0 + t * 2 * K::NB0 + 2 * j);
+        for (int j = 0; j < K::NB0; ++j) bias[j] = lds_f2(sB0 + t * 2 * K::NB0 + 2 * j);
         constexpr int MB = 2;
         for (int m0 = warp * MB; m0 < K::M0; m0 += NWARPS * MB) {
             float acc[MB][K::NB0][4];
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
             float acc[MB][K::NB1][4];
 #pragma unroll
             for (int j = 0; j < K::NB1; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(sB1 + t * 2 * K::NB1 + 2 * j);
+                const float2 bb = lds_f2(sB1 + t * 2 * K::NB1 + 2 * j);
                 acc[0][j][0] = acc[0][j][2] = bb.x, acc[0][j][1] = acc[0][j][3] = bb.y;
             }
             conv_phase<C0, K::NB1, MB, K::PS0, OffS2<K::WP, K::PARB>>(acc, sL0 + a_lane + m0 * 256, sW1 + lane * 8, hi);

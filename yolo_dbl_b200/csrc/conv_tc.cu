@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
                         float f[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 bq = *reinterpret_cast<const float4*>(sBias + cg + 4 * q);
+                            const float4 bq = lds_f4(sBias + cg + 4 * q);
                             f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
                             f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
                             f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
                 float f[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 bq = *reinterpret_cast<const float4*>(sBias + cg + 4 * q);
+                    const float4 bq = lds_f4(sBias + cg + 4 * q);
                     f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
                     f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
                     f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);

@@ -17,7 +17,7 @@
 // channel chunk through the same pipeline.  Accumulators: fp32 in TMEM, double buffered; epilogue as in conv_tc.cu.
 #include <cstring>
 
-#include "tc_ptx.cuh"
+#include "mma_util.cuh"
 
 namespace dbl {
 
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const C3Param
                 float f[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 bq = *reinterpret_cast<const float4*>(sBias + cg + 4 * q);
+                    const float4 bq = lds_f4(sBias + cg + 4 * q);
                     f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
                     f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
                     f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);

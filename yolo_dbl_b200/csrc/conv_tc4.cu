@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                             float f[16];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const float4 bq = *reinterpret_cast<const float4*>(sBias + c0 + 4 * q);
+                                const float4 bq = lds_f4(sBias + c0 + 4 * q);
                                 f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
                                 f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
                                 f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                     float f[16];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 bq = *reinterpret_cast<const float4*>(sBias + c0 + 4 * q);
+                        const float4 bq = lds_f4(sBias + c0 + 4 * q);
                         f[4 * q + 0] = act_t<ACT>(__uint_as_float(v[4 * q + 0]) + bq.x);
                         f[4 * q + 1] = act_t<ACT>(__uint_as_float(v[4 * q + 1]) + bq.y);
                         f[4 * q + 2] = act_t<ACT>(__uint_as_float(v[4 * q + 2]) + bq.z);

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(512) dsconv_mma_kernel(const DsParams p) {
             float acc[C::NBC][4];
 #pragma unroll
             for (int j = 0; j < C::NBC; ++j) {
-                const float2 bb = *reinterpret_cast<const float2*>(sBp + t * 2 * C::NB + 2 * (ch * C::NBC + j));
+                const float2 bb = *reinterpret_cast<const float2*>(sBp + t * 2 * C::NB + 2 * (ch * C::NBC + j));  // generic load on purpose: the explicit (volatile) ld.shared form was measured 10 us slower here (8 loads pinned between the MMAs)
                 acc[j][0] = acc[j][2] = bb.x, acc[j][1] = acc[j][3] = bb.y;
             }
 #pragma unroll

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
     float acc3[K::NB3][4];
 #pragma unroll
     for (int j = 0; j < K::NB3; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(sB3 + t * 2 * K::NB3 + 2 * j);
+        const float2 bb = lds_f2(sB3 + t * 2 * K::NB3 + 2 * j);
         acc3[j][0] = acc3[j][2] = bb.x, acc3[j][1] = acc3[j][3] = bb.y;
     }
 #pragma unroll
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HfParams p) {
     float acc2[K::NB2][4];
 #pragma unroll
     for (int j = 0; j < K::NB2; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(sB2 + t * 16 + 2 * j);
+        const float2 bb = lds_f2(sB2 + t * 16 + 2 * j);
         acc2[j][0] = acc2[j][2] = bb.x, acc2[j][1] = acc2[j][3] = bb.y;
     }
 #pragma unroll

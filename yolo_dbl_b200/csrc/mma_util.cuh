@@ -26,6 +26,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
     asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+// float2 from a shared-memory float array through an explicit ld.shared (a `float*` carved out of the 128-byte-aligned dynamic
+// shared buffer has lost its address space: ptxas emits generic LD.E there)
+__device__ __forceinline__ float2 lds_f2(const float* p) {
+    const uint2 v = lds64(smem_u32(p));
+    return make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -149,5 +155,10 @@ __device__ __forceinline__ void global_load(const __nv_bfloat16* p, uint32_t* v)
     }
 }
 
+
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+    const uint4 v = lds128(smem_u32(p));
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
 
 }  // namespace dbl
