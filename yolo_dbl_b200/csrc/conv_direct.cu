@@ -404,8 +404,10 @@ __global__ void __launch_bounds__(256, 3) dwconv_tile3_kernel(const __nv_bfloat1
             float f[4];
             f32x2_split(acc[r][0], f[0], f[1]);
             f32x2_split(acc[r][1], f[2], f[3]);
+            if (act == DBL_ACT_SILU) {  // a (uniform) branch, not a select: DSConv's depthwise half has no activation
 #pragma unroll
-            for (int i = 0; i < 4; ++i) f[i] = act == DBL_ACT_SILU ? silu_fast(f[i]) : f[i];
+                for (int i = 0; i < 4; ++i) f[i] = silu_fast(f[i]);
+            }
             *reinterpret_cast<uint2*>(yp + (size_t)r * wo * ypitch) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
         }
     }
