@@ -1,3 +1,4 @@
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o ffma ffma.cu   (run on the GPU box: gpurun -- tools/ubench/ffma)
 // Micro-benchmark: 3-register FFMA vs packed FFMA2 (fma.rn.f32x2) issue rate on sm_100a.
 #include <cstdio>
 #include <cuda_runtime.h>

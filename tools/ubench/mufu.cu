@@ -1,3 +1,4 @@
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o mufu mufu.cu   (run on the GPU box: gpurun -- tools/ubench/mufu)
 // Micro-benchmark: MUFU.TANH f32 vs packed f16x2 throughput, and the accuracy of SiLU built on each.
 #include <cstdio>
 #include <cmath>
