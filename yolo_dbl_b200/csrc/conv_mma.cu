@@ -508,15 +508,17 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
             for (int j = 0; j < K::NB0; ++j) bw[ky][j] = lds64(sW0 + ((ky * K::NB0 + j) * 32 + lane) * 8);
         float2 bias[K::NB0];
 #pragma unroll
-        for (int j = 0; j < K::NB0; ++j) bias[j] = lds_f2(sB0 + t * 2 * K::NB0 + 2 * j);
+        for (int j = 0; j < K::NB0; ++j) {
+            bias[j] = lds_f2(sB0 + t * 2 * K::NB0 + 2 * j);
+            bias[j].x *= 0.5f, bias[j].y *= 0.5f;  // SiLU(z + b) = h + h * tanh(h) with h = 0.5 z + 0.5 b: the bias rides on the 0.5 scaling
+        }
         constexpr int MB = 2;
         for (int m0 = warp * MB; m0 < K::M0; m0 += NWARPS * MB) {
-            float acc[MB][K::NB0][4];
+            float acc[MB][K::NB0][4];  // zero accumulators: the first HMMA takes RZ, no per-iteration register set-up
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-                for (int j = 0; j < K::NB0; ++j)
-                    acc[mb][j][0] = acc[mb][j][2] = bias[j].x, acc[mb][j][1] = acc[mb][j][3] = bias[j].y;
+                for (int j = 0; j < K::NB0; ++j) acc[mb][j][0] = acc[mb][j][1] = acc[mb][j][2] = acc[mb][j][3] = 0.f;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
                         uint32_t v[K::NB0];
 #pragma unroll
                         for (int j = 0; j < K::NB0; ++j)
-                            v[j] = inside ? pack2(silu_fast(acc[mb][j][2 * rh]), silu_fast(acc[mb][j][2 * rh + 1])) : 0u;
+                            v[j] = inside ? pack2(silu_half_bias(acc[mb][j][2 * rh], bias[j].x), silu_half_bias(acc[mb][j][2 * rh + 1], bias[j].y)) : 0u;
                         planar_store<K::NB0>(sL0, K::PS0, sub0 + mb * 8 + rh * 4, t, v);
                     }
                 }

@@ -141,6 +141,13 @@ __device__ __forceinline__ float silu_fast(float v) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
     return fmaf(h, t, h);
 }
+// SiLU(z + b) with the bias pre-scaled by 0.5: h = 0.5 z + hb (one FMA), result h + h * tanh(h)
+__device__ __forceinline__ float silu_half_bias(float z, float hb) {
+    float t;
+    const float h = fmaf(z, 0.5f, hb);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 template <int ACT>
 __device__ __forceinline__ float act_t(float v) {
     if (ACT == DBL_ACT_SILU) return silu_fast(v);
