@@ -82,3 +82,44 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "dbl_oracle" not in src and "nms_oracle" not in src and "import oracle" not in src, f
+
+
+# ---- host-side mirrors of index arithmetic used inside the kernels (the GPU tests cover the kernels; these pin the maths) --------
+def test_fastdiv_multiply_high_is_exact_within_its_guard():
+    """dbl_common.cuh: q = umulhi(x, m), m = floor(2^32 / d) + 1 is exact while x * d < 2^32 (make_fastdiv leaves m = 0 otherwise)."""
+    import random
+
+    rng = random.Random(0)
+    for d in [2, 3, 5, 6, 7, 11, 20, 54, 120, 255, 256, 1000, 4097, 65535]:
+        m = (1 << 32) // d + 1
+        lim = ((1 << 32) - 1) // d  # largest x with x * d < 2^32
+        xs = [0, 1, d - 1, d, d + 1, lim - 1, lim] + [rng.randrange(0, lim + 1) for _ in range(2000)]
+        for x in xs:
+            if x < 0 or x * d >= (1 << 32):
+                continue
+            assert (x * m) >> 32 == x // d, (x, d)
+
+
+def test_row_walk_staging_covers_every_chunk_once():
+    """tc_ptx.cuh stage_tile16: threads keep a (column, group) and walk down the rows; every 16-byte chunk of the
+    [rows][cols][G8] tile must be written exactly once, whatever the CTA size."""
+    import math
+
+    for rows, cols, g8, nt in [(10, 29, 2, 216), (14, 16, 2, 160), (38, 28, 2, 200), (18, 42, 1, 96), (14, 26, 8, 320), (10, 12, 16, 320),
+                               (5, 70, 4, 128), (3, 300, 2, 256), (22, 22, 10, 416)]:
+        row_items = cols * g8
+        per_pass = min(row_items, nt)
+        rpp = nt // per_pass
+        seen = {}
+        for tid in range(nt):
+            r0 = math.floor((tid + 0.5) * (1.0 / per_pass))
+            e_in = tid - r0 * per_pass
+            if r0 >= rpp:
+                continue
+            e = e_in
+            while e < row_items:
+                for ly in range(r0, rows, rpp):
+                    key = ly * row_items + e
+                    seen[key] = seen.get(key, 0) + 1
+                e += per_pass
+        assert len(seen) == rows * row_items and set(seen.values()) == {1}, (rows, cols, g8, nt)
