@@ -152,8 +152,7 @@ __device__ __forceinline__ void ds_depthwise(uint32_t sX, uint32_t sA, const flo
 template <int K, int S, int CIN, int COUT, int DW_ACT>
 __global__ void __launch_bounds__(512) dsconv_mma_kernel(const DsParams p) {
     using C = DsCfg<K, S, CIN, COUT>;
-    constexpr int R = C::R, G = C::G, PAD = (K - 1) / 2;
-    constexpr int ROWS_T = (R - 1) * S + K;
+    constexpr int G = C::G, PAD = (K - 1) / 2;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int tw = p.tw, th = p.th, mpx = tw * th;
