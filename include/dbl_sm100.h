@@ -114,7 +114,8 @@ int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const float* bias
 /* Layers 0 and 1 of the graph fused (cfg/models/v13/yolov13_DBL.yaml:9-10: Conv [c0,3,1] then Conv [c1,3,2]) together
  * with the input cast / scale of BasePredictor.preprocess (engine/predictor.py:116-134).  x: NCHW (n,3,h,w), f32 in 0..1
  * (x_is_u8 = 0) or uint8 0..255 (x_is_u8 = 1; the /255 is folded into layer 0's weights).  w0: f32 [c0][3][3][3], w1:
- * packed (c1, c0, 9 taps).  y: bf16 NHWC (n, h/2, w/2, c1).  (c0,c1) in {(8,16), (16,32)}. */
+ * packed (c1, c0, 9 taps).  y: bf16 NHWC (n, h/2, w/2, c1).  (c0,c1) in {(8,16), (16,32)}.  h and w even; x aligned to 8 bytes
+ * (f32) / 2 bytes (u8): the kernel loads pixel pairs (DBL_E_ARG otherwise). */
 int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int w, const float* w0, const float* b0, int c0,
                   const void* w1_packed, const float* b1, const dbl_tensor* y, dbl_stream_t stream);
 
