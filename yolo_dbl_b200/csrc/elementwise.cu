@@ -253,17 +253,22 @@ static int launch_resample(int mode, const dbl_tensor* x, const dbl_tensor* y, c
 // LetterBox.__call__ (data/augment.py:1558-1600; auto=False, centre, pad 114) + the BGR->RGB / HWC->CHW of BasePredictor.preprocess
 // (engine/predictor.py:127-129) for a batch of uint8 images of DIFFERENT sizes in one launch.  The bilinear resize repeats the
 // fixed-point arithmetic of cv2.resize(INTER_LINEAR) for 8-bit images: 11-bit coefficients cvRound(f * 2048), horizontal pass in
-// int32, vertical pass (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.
+// int32, vertical pass (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2.  The two axes treat the image border
+// differently (imgproc/src/resize.cpp): along x a sample outside the image gets the weights (2048, 0) on the edge pixel; along y
+// the fractional weight is KEPT and only the row indices are clamped, so both taps read the edge row and truncate separately.
+template <bool VERTICAL>
 __device__ __forceinline__ void lb_coeff(int d, int n_out, int n_in, int& s0, int& s1, int& a0, int& a1) {
-    const double scale = (double)n_in / (double)n_out;
+    const double scale = 1.0 / ((double)n_out / (double)n_in);  // cv2: inv_scale = dsize / ssize, scale = 1 / inv_scale
     float f = (float)(((double)d + 0.5) * scale - 0.5);
     int s = (int)floorf(f);
     f -= (float)s;
-    if (s < 0) f = 0.f, s = 0;
-    if (s >= n_in - 1) f = 0.f, s = n_in - 1;
-    a1 = __float2int_rn(f * 2048.f);
-    a0 = __float2int_rn((1.f - f) * 2048.f);
-    s0 = s, s1 = min(s + 1, n_in - 1);
+    if (!VERTICAL) {
+        if (s < 0) f = 0.f, s = 0;
+        if (s >= n_in - 1) f = 0.f, s = n_in - 1;
+    }
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    s0 = min(max(s, 0), n_in - 1), s1 = min(max(s + 1, 0), n_in - 1);
 }
 
 __global__ void __launch_bounds__(256) letterbox_kernel(const dbl_lb_image* __restrict__ tab, uint8_t* __restrict__ dst, int H, int W, int pad) {
@@ -281,8 +286,8 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const dbl_lb_image* __re
             bl = px[0], g = px[1], r = px[2];
         } else {
             int x0, x1, ax0, ax1, y0, y1, ay0, ay1;
-            lb_coeff(rx, im.new_w, im.w, x0, x1, ax0, ax1);
-            lb_coeff(ry, im.new_h, im.h, y0, y1, ay0, ay1);
+            lb_coeff<false>(rx, im.new_w, im.w, x0, x1, ax0, ax1);
+            lb_coeff<true>(ry, im.new_h, im.h, y0, y1, ay0, ay1);
             const uint8_t* p00 = src + (size_t)y0 * im.pitch + x0 * 3;
             const uint8_t* p01 = src + (size_t)y0 * im.pitch + x1 * 3;
             const uint8_t* p10 = src + (size_t)y1 * im.pitch + x0 * 3;
