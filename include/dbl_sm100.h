@@ -244,6 +244,43 @@ size_t dbl_nms_sort_capacity(int cap);
 int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
             uint64_t* sort_keys, float* out_rows, int32_t* out_pos, int32_t* out_count, dbl_stream_t stream);
 
+
+/* Same, with DetectionPredictor.postprocess's tail fused into the epilogue: scale_boxes + clip_boxes
+ * (utils/ops.py:92-127, 319-338; called at models/yolo/detect/predict.py:38).  scale: DEVICE array of `batch` records, or NULL
+ * (= dbl_nms).  A kept box (x1,y1,x2,y2) leaves as clamp((x - pad_x) / gain, 0, w0), clamp((y - pad_y) / gain, 0, h0): the
+ * letterbox padding and gain of that image (pad = round((W - w0*gain)/2 - 0.1) etc., computed by the caller like the reference
+ * does in Python) and the original image size.  IEEE fp32 subtract / divide / clamp, bit-identical to the reference on CPU. */
+typedef struct dbl_box_scale {
+    float pad_x, pad_y, gain, w0, h0;
+} dbl_box_scale;
+int dbl_nms_scaled(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
+                   uint64_t* sort_keys, const dbl_box_scale* scale, float* out_rows, int32_t* out_pos, int32_t* out_count,
+                   dbl_stream_t stream);
+
+/* ---- validator path ----------------------------------------------------------------------------
+ * A-priori labels of non_max_suppression (utils/ops.py:255-261; DetectionValidator.postprocess passes labels=self.lb,
+ * models/yolo/detect/val.py:92-102): after a filter call (dbl_nms_filter / dbl_decode_filter / dbl_head_decode) has filled
+ * `cand`, append one candidate per ground-truth label: box = xywh2xyxy(label), score 1.0, class = label class, ordered after every
+ * prediction row like the reference's torch.cat.  labels: DEVICE f32 [L][5] = (cls, x, y, w, h) in network-input pixels, all
+ * images concatenated; label_offsets: DEVICE int32 [batch+1].  anchors / nc / multi_label / conf / classes as in the filter
+ * call.  cand->cap must leave room for the labels. */
+int dbl_nms_append_labels(const float* labels, const int32_t* label_offsets, int max_labels_per_image, int anchors, int nc,
+                          int multi_label, float conf_thres, const int32_t* classes, int num_classes_kept,
+                          const dbl_candidates* cand, dbl_stream_t stream);
+
+/* DetectionValidator._process_batch (models/yolo/detect/val.py:213-227) = box_iou (utils/metrics.py:52-71) + match_predictions
+ * (engine/validator.py:222-260, use_scipy=False) for a whole batch in one launch.
+ *   rows f32 [batch][max_det][6] + counts int32 [batch]: the NMS output (dbl_nms / dbl_nms_scaled);
+ *   gt_boxes f32 [G][4] xyxy (16-byte aligned), gt_cls f32 [G], gt_offsets int32 [batch+1]: ground truth, images concatenated;
+ *   iou_thresholds f32 [T], T <= 16 (the validator's iouv = linspace(0.5, 0.95, 10));
+ *   correct uint8 [batch][max_det][T]: 1 where detection d is a true positive at threshold t (rows >= counts[b] are 0).
+ * ws: scratch of dbl_match_workspace_bytes(batch, max_labels_per_image, T) bytes.  Pairs with exactly equal IoU resolve to
+ * the larger label index (the reference's argsort leaves that order unspecified). */
+size_t dbl_match_workspace_bytes(int batch, int max_labels_per_image, int num_thresholds);
+int dbl_match_predictions(const float* rows, const int32_t* counts, int batch, int max_det, const float* gt_boxes,
+                          const float* gt_cls, const int32_t* gt_offsets, int max_labels_per_image, const float* iou_thresholds,
+                          int num_thresholds, uint8_t* correct, void* ws, size_t ws_bytes, dbl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

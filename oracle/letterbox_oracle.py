@@ -20,13 +20,17 @@ from typing import Tuple
 import numpy as np
 
 
-def letterbox_params(h0: int, w0: int, H: int, W: int) -> Tuple[int, int, int, int, float]:
-    """augment.py:1564-1590 -> (new_h, new_w, top, left, r)"""
+def letterbox_params(h0: int, w0: int, H: int, W: int, auto: bool = False, stride: int = 32):
+    """augment.py:1564-1597 -> (new_h, new_w, top, left, r, H_out, W_out); auto = minimum rectangle (augment.py:1577-1578)"""
     r = min(H / h0, W / w0)
     new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
-    dw, dh = (W - new_w) / 2, (H - new_h) / 2
-    top, left = int(round(dh - 0.1)), int(round(dw - 0.1))
-    return new_h, new_w, top, left, r
+    dw, dh = W - new_w, H - new_h
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_h, new_w, top, left, r, new_h + top + bottom, new_w + left + right
 
 
 def _coeffs(n_out: int, n_in: int, vertical: bool = False):
@@ -66,19 +70,20 @@ def resize_linear_u8(src: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
-def letterbox(img: np.ndarray, shape: Tuple[int, int], pad_value: int = 114) -> np.ndarray:
-    """HWC uint8 -> HWC uint8 of `shape` (augment.py:1558-1600): resize to fit, centre, pad with 114"""
-    H, W = shape
-    new_h, new_w, top, left, _ = letterbox_params(img.shape[0], img.shape[1], H, W)
+def letterbox(img: np.ndarray, shape: Tuple[int, int], pad_value: int = 114, auto: bool = False, stride: int = 32) -> np.ndarray:
+    """HWC uint8 -> HWC uint8 of `shape` (augment.py:1558-1600): resize to fit, centre, pad with 114; auto: minimum rectangle"""
+    new_h, new_w, top, left, _, H, W = letterbox_params(img.shape[0], img.shape[1], shape[0], shape[1], auto, stride)
     out = np.full((H, W, img.shape[2]), pad_value, np.uint8)
     out[top:top + new_h, left:left + new_w] = resize_linear_u8(img, new_w, new_h)
     return out
 
 
-def preprocess(images, shape: Tuple[int, int]) -> np.ndarray:
-    """BasePredictor.preprocess for a list of HWC BGR uint8 images (engine/predictor.py:116-134) up to, not including, the
-    float cast: letterbox, BGR -> RGB, BHWC -> BCHW.  Returns uint8 [B,3,H,W]."""
-    return np.ascontiguousarray(np.stack([letterbox(im, shape) for im in images])[..., ::-1].transpose(0, 3, 1, 2))
+def preprocess(images, shape: Tuple[int, int], auto=None) -> np.ndarray:
+    """BasePredictor.preprocess for a list of HWC BGR uint8 images (engine/predictor.py:116-134, 145-161) up to, not including,
+    the float cast: letterbox (auto = all images share a shape, predictor.py:155-158), BGR -> RGB, BHWC -> BCHW.  uint8 [B,3,H,W]."""
+    if auto is None:
+        auto = len({im.shape for im in images}) == 1
+    return np.ascontiguousarray(np.stack([letterbox(im, shape, auto=auto) for im in images])[..., ::-1].transpose(0, 3, 1, 2))
 
 
 def scale_boxes(img1_shape, boxes: np.ndarray, img0_shape) -> np.ndarray:

@@ -58,9 +58,11 @@ def xywh2xyxy(x: np.ndarray) -> np.ndarray:
 
 
 def non_max_suppression(pred: np.ndarray, conf_thres=0.25, iou_thres=0.45, classes: Optional[Sequence[int]] = None,
-                        agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680
+                        agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680, labels=None
                         ) -> Tuple[List[np.ndarray], List[np.ndarray]]:
-    """pred: (B, 4+nc, A) fp32 (xywh px, scores).  Returns (rows per image [n_i,6], kept anchor index per image)."""
+    """pred: (B, 4+nc, A) fp32 (xywh px, scores).  Returns (rows per image [n_i,6], kept anchor index per image).
+    labels: per image (n_i, 5) = (cls, x, y, w, h): the validator's a-priori labels (ops.py:255-261); a kept label row has
+    index A + k (k = its position in the image's label list)."""
     pred = np.asarray(pred, np.float32)
     B, no, A = pred.shape
     nc = no - 4
@@ -72,6 +74,13 @@ def non_max_suppression(pred: np.ndarray, conf_thres=0.25, iou_thres=0.45, class
         cand = np.nonzero(x[:, 4:].max(1) > conf_thres)[0]  # ops.py:234 (xc) and :253
         box = xywh2xyxy(x[cand, :4])
         cls = x[cand, 4:]
+        if labels is not None and len(labels) and len(labels[b]):  # ops.py:255-261: rows appended after the filtered predictions
+            lb = np.asarray(labels[b], np.float32).reshape(-1, 5)
+            v = np.zeros((len(lb), nc), np.float32)
+            v[np.arange(len(lb)), lb[:, 0].astype(np.int64)] = 1.0
+            box = np.concatenate([box, xywh2xyxy(lb[:, 1:5])], 0)
+            cls = np.concatenate([cls, v], 0)
+            cand = np.concatenate([cand, A + np.arange(len(lb))])
         if multi_label:  # ops.py:270-272
             i, j = np.nonzero(cls > conf_thres)
             box, conf, cid, anchor = box[i], cls[i, j], j.astype(np.int64), cand[i]

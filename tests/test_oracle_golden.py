@@ -8,6 +8,7 @@ import torch
 
 import dbl_oracle as O
 import nms_oracle as N
+from yolo_dbl_b200.graph import param_shapes, resolve
 from yolo_dbl_b200.synth import synth_images, synth_state_dict
 
 from conftest import GOLDEN
@@ -128,7 +129,7 @@ def test_nms_kernel_matches_torchvision_random_and_ties():
 
 
 # ---- letterbox / scale_boxes (image-source pre/post-process): oracle vs the reference's LetterBox (cv2) and ops.scale_boxes
-LETTERBOX_CASES = ["down_wide", "up_tall", "same", "odd", "square_down", "up2x", "down2x", "up_both", "thin"]
+LETTERBOX_CASES = ["down_wide", "up_tall", "same", "odd", "square_down", "up2x", "down2x", "up_both", "thin", "auto_wide", "auto_tall"]
 
 
 @pytest.mark.parametrize("name", LETTERBOX_CASES)
@@ -137,13 +138,68 @@ def test_letterbox_oracle_matches_reference_cv2(name):
 
     g = _load(f"letterbox_{name}.npz")
     shape = tuple(int(v) for v in g["shape"])
-    got = LB.letterbox(g["img"], shape)
+    auto = name.startswith("auto_")  # minimum-rectangle mode of BasePredictor.pre_transform (same-shape batches)
+    got = LB.letterbox(g["img"], shape, auto=auto)
     assert got.shape == g["out"].shape
     # integer work: byte for byte what the reference's LetterBox (cv2.resize INTER_LINEAR + copyMakeBorder) produced
     np.testing.assert_array_equal(got, g["out"])
     # padding is exact
-    new_h, new_w, top, left, _ = LB.letterbox_params(g["img"].shape[0], g["img"].shape[1], *shape)
+    new_h, new_w, top, left = LB.letterbox_params(g["img"].shape[0], g["img"].shape[1], *shape, auto=auto)[:4]
     pad = np.ones(got.shape[:2], bool)
     pad[top:top + new_h, left:left + new_w] = False
     assert (got[pad] == 114).all() and (g["out"][pad] == 114).all()
-    np.testing.assert_allclose(LB.scale_boxes(shape, g["boxes"], g["img"].shape[:2]), g["scaled"], rtol=1e-6, atol=1e-4)
+    # scale_boxes + clip_boxes: fp32 arithmetic, bit for bit what the reference's ops.scale_boxes returned
+    np.testing.assert_array_equal(LB.scale_boxes(got.shape[:2], g["boxes"], g["img"].shape[:2]), g["scaled"])
+
+
+# ---- round 2: validator path (a-priori labels, match_predictions) and the benchmarked nc=80 instantiation ----------------
+@pytest.mark.parametrize("name", ["single", "multi"])
+def test_nms_oracle_labels_branch_matches_reference(name):
+    """ops.non_max_suppression(labels=lb) (utils/ops.py:255-261): rows identical to the reference's output, byte for byte"""
+    g = _load(f"nms_labels_{name}.npz")
+    lc = g["label_counts"].tolist()
+    labels, o = [], 0
+    for n in lc:
+        labels.append(g["labels"][o:o + n])
+        o += n
+    rows, idx = N.non_max_suppression(g["pred"], 0.4, 0.6, multi_label=bool(g["multi_label"]), labels=labels, max_det=300)
+    assert [len(r) for r in rows] == g["counts"].tolist()
+    assert np.concatenate(rows).tobytes() == g["rows"].tobytes()
+    # the case is only meaningful if label rows (score exactly 1, index >= A) survive
+    A = g["pred"].shape[2]
+    assert any((i >= A).any() for i in idx) and all(float(r[:, 4].max()) == 1.0 for r, n in zip(rows, lc) if n)
+
+
+@pytest.mark.parametrize("name", ["typical", "crowded", "empty", "one"])
+def test_match_oracle_matches_reference(name):
+    """box_iou + DetectionValidator.match_predictions of the reference vs the numpy restatement"""
+    import match_oracle as M
+
+    g = _load(f"match_{name}.npz")
+    if len(g["gt"]):
+        iou = M.box_iou(g["gt"], g["det"][:, :4])
+        assert iou.tobytes() == g["iou"].tobytes()  # strict fp32, same operation order
+    got = M.process_batch(g["det"], g["gt"], g["gt_cls"], g["iouv"])
+    np.testing.assert_array_equal(got, g["correct"])
+
+
+def test_oracle_forward_nc80_640_matches_reference_on_the_benchmarked_weights():
+    """The instantiation bench.py measures (n, nc=80, recipe seed 0 + calibration table, bench images): oracle vs the REAL
+    reference's fused forward and NMS."""
+    g = _load("fwd_n_nc80_640.npz")
+    spec = resolve(None, "n", 80)
+    sd = synth_state_dict(param_shapes(spec), 0)
+    x = synth_images(8, 640, 640, seed=100)[:2]
+    y, _ = O.forward(sd, x, "n")
+    # the oracle applies BatchNorm explicitly like the UNFUSED reference: same bound as test_forward_matches_reference_640
+    torch.testing.assert_close(y[0, :, ::4], torch.from_numpy(g["y0_unfused_s4"]), rtol=2e-4, atol=5e-3)
+    # against the fused model (what predict runs) the fp32 re-association of fuse() shows: <= 0.25 px / 5e-3 in score
+    d = (y[0] - torch.from_numpy(g["y0"])).abs()
+    assert float(d[:4].max()) <= 0.25 and float(d[4:].max()) <= 5e-3, (float(d[:4].max()), float(d[4:].max()))
+    d1 = (y[1, :4] - torch.from_numpy(g["y1_box"])).abs()
+    best, cls = y[1, 4:].max(0)
+    assert float(d1.max()) <= 0.25 and float((best - torch.from_numpy(g["y1_best"])).abs().max()) <= 5e-3
+    rows, _ = N.non_max_suppression(np.stack([g["y0"], y[1].numpy()]), 0.25, 0.7, max_det=300)
+    c = g["counts"].tolist()
+    assert len(rows[0]) == c[0] and rows[0].tobytes() == g["rows"][: c[0]].tobytes()  # image 0: the reference's own y -> identical rows
+    assert abs(len(rows[1]) - c[1]) <= 2  # image 1: the oracle's y (fp32 noise may flip a box at the threshold)

@@ -15,6 +15,10 @@ def __getattr__(name):  # backend / engine import torch.nn and touch the library
         from . import backend
 
         return getattr(backend, name)
+    if name in ("DBLValidator", "match_predictions"):
+        from . import validator
+
+        return getattr(validator, name)
     if name == "DBLEngine":
         from .engine import DBLEngine
 

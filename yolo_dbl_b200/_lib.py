@@ -55,6 +55,10 @@ class LbImage(C.Structure):
                 ("top", C.c_int32), ("left", C.c_int32), ("reserved", C.c_int32)]
 
 
+class BoxScale(C.Structure):
+    _fields_ = [("pad_x", C.c_float), ("pad_y", C.c_float), ("gain", C.c_float), ("w0", C.c_float), ("h0", C.c_float)]
+
+
 class Candidates(C.Structure):
     _fields_ = [("box", C.c_void_p), ("score", C.c_void_p), ("cls", C.c_void_p), ("pos", C.c_void_p),
                 ("count", C.c_void_p), ("cap", C.c_int32), ("batch", C.c_int32)]
@@ -98,6 +102,10 @@ _SIGNATURES = {
     "dbl_head_decode": (C.c_int, [C.POINTER(HeadFused), _P, C.c_float, C.c_int, _P, C.c_int, C.POINTER(Candidates), _P]),
     "dbl_nms_sort_capacity": (C.c_size_t, [C.c_int]),
     "dbl_nms": (C.c_int, [C.POINTER(Candidates), C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "dbl_nms_scaled": (C.c_int, [C.POINTER(Candidates), C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "dbl_nms_append_labels": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, C.c_int, C.POINTER(Candidates), _P]),
+    "dbl_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dbl_match_predictions": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -25,28 +25,28 @@ from .engine import DBLEngine
 from .synth import synth_state_dict
 
 
-def letterbox_params(h0: int, w0: int, H: int, W: int):
-    """LetterBox geometry (reference data/augment.py:1564-1590; auto=False, scaleup, centre): (new_h, new_w, top, left, gain)"""
+def letterbox_params(h0: int, w0: int, H: int, W: int, auto: bool = False, stride: int = 32):
+    """LetterBox geometry (reference data/augment.py:1564-1597; scaleup, centre): (new_h, new_w, top, left, gain, H_out, W_out).
+    auto=True is the minimum-rectangle mode (augment.py:1577-1578): only the padding modulo `stride` is kept, so the output is
+    the smallest stride-multiple rectangle around the resized image instead of the full H x W."""
     r = min(H / h0, W / w0)
     new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
-    dw, dh = (W - new_w) / 2, (H - new_h) / 2
-    return new_h, new_w, int(round(dh - 0.1)), int(round(dw - 0.1)), r
+    dw, dh = W - new_w, H - new_h
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_h, new_w, top, left, r, new_h + top + bottom, new_w + left + right
 
 
-def scale_boxes_(rows: torch.Tensor, img1_shape, img0_shape) -> torch.Tensor:
-    """ops.scale_boxes + clip_boxes (reference utils/ops.py:92-127, 319-338) on the xyxy columns of `rows`, in place, fp32"""
+def box_scale_record(img1_shape, img0_shape):
+    """(pad_x, pad_y, gain, w0, h0) of ops.scale_boxes / clip_boxes (reference utils/ops.py:92-127, 319-338; ratio_pad=None) for
+    one image: what the NMS epilogue (dbl_nms_scaled) applies to every kept box."""
     gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
-    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
-    rows[..., 0] -= pad[0]
-    rows[..., 1] -= pad[1]
-    rows[..., 2] -= pad[0]
-    rows[..., 3] -= pad[1]
-    rows[..., :4] /= gain
-    rows[..., 0].clamp_(0, img0_shape[1])
-    rows[..., 1].clamp_(0, img0_shape[0])
-    rows[..., 2].clamp_(0, img0_shape[1])
-    rows[..., 3].clamp_(0, img0_shape[0])
-    return rows
+    pad_x = round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1)
+    pad_y = round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1)
+    return [float(pad_x), float(pad_y), float(gain), float(img0_shape[1]), float(img0_shape[0])]
 
 
 class DBLBackend(nn.Module):
@@ -157,11 +157,15 @@ class DBLBackend(nn.Module):
 
     __call__ = forward
 
-    def preprocess(self, images, imgsz=(640, 640)) -> torch.Tensor:
+    def preprocess(self, images, imgsz=(640, 640), auto=None) -> torch.Tensor:
         """Image sources: a list of HWC BGR uint8 arrays (what cv2.imread returns, any sizes) -> uint8 [B,3,H,W] RGB on the device,
         letterboxed like BasePredictor.pre_transform / LetterBox (reference engine/predictor.py:145-161, data/augment.py:1558-1600).
         One pinned upload of the raw pixels + ONE kernel (dbl_letterbox_u8) for the whole batch; the float cast and /255 happen
-        inside the stem kernel."""
+        inside the stem kernel.
+
+        auto=None follows the reference's rule (predictor.py:155-158): ``LetterBox(auto=same_shapes and model.pt)`` -- when every
+        image has the same shape the batch is padded only to the next stride multiple (rectangular inference), otherwise to the
+        full imgsz square; True / False force a mode."""
         import numpy as np
 
         lib = L.require_device()
@@ -172,6 +176,13 @@ class DBLBackend(nn.Module):
         for a in arrs:
             if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
                 raise ValueError("expected HWC uint8 images with 3 channels (BGR)")
+        same_shapes = len({a.shape for a in arrs}) == 1
+        if auto is None:
+            auto = same_shapes
+        if auto and not same_shapes:
+            raise ValueError("auto (minimum-rectangle) letterboxing needs images of one shape")
+        if auto:  # the rectangle every image of the batch lands in
+            H, W = letterbox_params(arrs[0].shape[0], arrs[0].shape[1], H, W, True, int(max(self.spec.strides)))[5:]
         sizes = [a.size for a in arrs]
         offs = [0]
         for n in sizes:
@@ -184,7 +195,7 @@ class DBLBackend(nn.Module):
             tab = (L.LbImage * len(arrs))()
             for k, (a, o) in enumerate(zip(arrs, offs)):
                 h0, w0 = a.shape[:2]
-                new_h, new_w, top, left, _ = letterbox_params(h0, w0, H, W)
+                new_h, new_w, top, left = letterbox_params(h0, w0, H, W)[:4]
                 tab[k] = L.LbImage(raw.data_ptr() + o, h0, w0, w0 * 3, new_h, new_w, top, left, 0)
             tab_host = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).pin_memory()
             tab_dev = tab_host.to(self._device, non_blocking=True)
@@ -194,11 +205,27 @@ class DBLBackend(nn.Module):
         return out
 
     def detect(self, x, conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None,
-               max_nms=30000):
-        """Fused forward + decode + NMS.  Returns (rows [B,max_det,6], counts [B]) living in engine-owned buffers."""
+               max_nms=30000, orig_shapes=None, labels=None, labels_cap=0):
+        """Fused forward + decode + NMS.  Returns (rows [B,max_det,6], counts [B]) living in engine-owned buffers.
+
+        orig_shapes: per image (h0, w0) -- the kept boxes leave the NMS kernel already mapped back to the original images
+        (scale_boxes + clip_boxes in the epilogue, reference models/yolo/detect/predict.py:38).
+        labels: per image an (n_i, 5) tensor (cls, x, y, w, h): the validator's a-priori labels (reference utils/ops.py:255-261);
+        labels_cap bounds n_i (default: the next multiple of 64 above the largest n_i)."""
         x = self._prep(x)
-        rows, counts, _ = self.engine(x.shape[0], x.shape[2], x.shape[3]).detect(
-            x, conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms)
+        eng = self.engine(x.shape[0], x.shape[2], x.shape[3])
+        if labels is not None and not labels_cap:
+            labels_cap = max(64, -(-max((len(l) for l in labels), default=0) // 64) * 64)
+        kw = dict(conf=conf, iou=iou, agnostic=agnostic, multi_label=multi_label, max_det=max_det, classes=classes, max_nms=max_nms,
+                  scaled=orig_shapes is not None, labels_cap=labels_cap if labels is not None else 0)
+        key = eng.post_key(**kw)
+        with torch.cuda.device(self._device):
+            if orig_shapes is not None:
+                rec = torch.tensor([box_scale_record(tuple(x.shape[2:]), tuple(o)) for o in orig_shapes], dtype=torch.float32)
+                eng.set_scale(key, rec.pin_memory())
+            if labels is not None:
+                eng.set_labels(key, labels)
+        rows, counts, _ = eng.detect(x, **kw)
         return rows, counts
 
     def detect_stream(self, batches, with_event: bool = False, in_flight: Optional[int] = None, **nms):
@@ -306,7 +333,7 @@ class _NmsWorkspace:
 
 
 def nms_raw(prediction: torch.Tensor, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-            max_det=300, max_nms=30000, max_wh=7680):
+            max_det=300, max_nms=30000, max_wh=7680, labels=None):
     """Device-side result of the two NMS kernels: (rows [B,max_det,6], counts [B] int32, positions [B,max_det] int32).
 
     ``positions`` is the index each kept box had in the reference's filtered list ordering: the anchor index (or
@@ -319,13 +346,26 @@ def nms_raw(prediction: torch.Tensor, conf_thres=0.25, iou_thres=0.45, classes=N
     B, no, A = pred.shape
     nc = no - 4
     ml = bool(multi_label) and nc > 1
-    ws = _NmsWorkspace.get(pred.device, B, A * (nc if ml else 1), int(max_det))
+    lab = None
+    if labels is not None and len(labels) and any(len(l) for l in labels):  # a-priori labels (utils/ops.py:255-261)
+        if len(labels) != B:
+            raise ValueError(f"labels must hold one (n_i, 5) tensor per image ({B}), got {len(labels)}")
+        parts = [torch.as_tensor(l, dtype=torch.float32).reshape(-1, 5).to(pred.device) for l in labels]
+        offs = [0]
+        for t in parts:
+            offs.append(offs[-1] + t.shape[0])
+        lab = (torch.cat(parts).contiguous(), torch.tensor(offs, dtype=torch.int32, device=pred.device), max(t.shape[0] for t in parts))
+    lab_cap = -(-lab[2] // 64) * 64 if lab else 0
+    ws = _NmsWorkspace.get(pred.device, B, (A + lab_cap) * (nc if ml else 1), int(max_det))
     cls_t = torch.tensor(list(classes), dtype=torch.int32, device=pred.device) if classes is not None else None
     with torch.cuda.device(pred.device):
         s = L.current_stream()
         sb, sc, sa = pred.stride()
         L.check(lib.dbl_nms_filter(pred.data_ptr(), B, nc, A, sb, sc, sa, C.c_float(conf_thres), int(ml), L.ptr(cls_t),
                                    0 if cls_t is None else cls_t.numel(), C.byref(ws.cand), s), "dbl_nms_filter")
+        if lab:
+            L.check(lib.dbl_nms_append_labels(lab[0].data_ptr(), lab[1].data_ptr(), lab[2], A, nc, int(ml), C.c_float(conf_thres), L.ptr(cls_t),
+                                              0 if cls_t is None else cls_t.numel(), C.byref(ws.cand), s), "dbl_nms_append_labels")
         L.check(lib.dbl_nms(C.byref(ws.cand), C.c_float(iou_thres), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
                             ws.keys.data_ptr(), ws.rows.data_ptr(), ws.out_pos.data_ptr(), ws.out_count.data_ptr(), s), "dbl_nms")
     return ws.rows, ws.out_count, ws.out_pos
@@ -337,19 +377,21 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     """Drop-in for ``ultralytics.utils.ops.non_max_suppression`` (reference ``utils/ops.py:167-316``).
 
     Same arguments, same return type: a list of ``(n_i, 6)`` tensors ``(x1, y1, x2, y2, conf, cls)`` in descending score
-    order.  Differences, all deliberate: the input is never modified (``in_place`` is accepted and ignored), there is
-    no wall-clock abort (``max_time_img`` ignored; reference ops.py:312-314 silently drops images), and the paths the
-    YOLO-DBL head never takes (``rotated``, mask channels ``nc < C-4``, a-priori ``labels``) raise NotImplementedError.
+    order.  ``labels`` (the validator's a-priori labels, ops.py:255-261) is a list of ``(n_i, 5)`` tensors
+    ``(cls, x, y, w, h)``.  Differences, all deliberate: the input is never modified (``in_place`` is accepted and ignored),
+    there is no wall-clock abort (``max_time_img`` ignored; reference ops.py:312-314 silently drops images), and the paths the
+    YOLO-DBL head never takes (``rotated``, mask channels ``nc < C-4``) raise NotImplementedError.
     """
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]
-    if rotated or (labels and any(len(l) for l in labels)) or (nc and nc != prediction.shape[1] - 4):
-        raise NotImplementedError("rotated boxes, a-priori labels and mask channels are outside the YOLO-DBL hot path")
+    if rotated or (nc and nc != prediction.shape[1] - 4):
+        raise NotImplementedError("rotated boxes and mask channels are outside the YOLO-DBL hot path")
     if prediction.shape[-1] == 6:  # end2end models (not YOLO-DBL): pass through like the reference
         return [p[p[:, 4] > conf_thres][:max_det] for p in prediction]
-    rows, counts, _ = nms_raw(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    rows, counts, _ = nms_raw(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh,
+                              labels=labels if labels is not None and len(labels) else None)
     counts = counts.tolist()  # the one host sync: callers of this API want variable-length tensors
     return [rows[i, : counts[i]].clone() for i in range(len(counts))]
 
@@ -415,39 +457,60 @@ class YOLO:
         self.names = self.model.names
         self.overrides = {"conf": 0.25, "iou": 0.7, "max_det": 300, "agnostic_nms": False, "classes": None}  # cfg/default.yaml:51-65
 
-    def predict(self, source, conf=None, iou=None, max_det=None, agnostic_nms=None, classes=None, **kw) -> List[Results]:
+    def _nms_args(self, conf, iou, max_det, agnostic_nms, classes):
         o = self.overrides
+        return dict(conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
+                    agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
+                    max_det=o["max_det"] if max_det is None else max_det, classes=classes if classes is not None else o["classes"])
+
+    def _tick(self):
+        """ops.Profile (reference utils/ops.py:24-69): device-synchronised wall clock"""
+        import time
+
+        torch.cuda.synchronize(self.model.device)
+        return time.perf_counter()
+
+    def predict(self, source, conf=None, iou=None, max_det=None, agnostic_nms=None, classes=None, **kw) -> List[Results]:
         if not isinstance(source, torch.Tensor):
             return self._predict_images(source, conf, iou, max_det, agnostic_nms, classes, kw.get("imgsz", 640))
-        rows, counts = self.model.detect(
-            source, conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
-            agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
-            max_det=o["max_det"] if max_det is None else max_det, classes=classes if classes is not None else o["classes"])
+        t0 = self._tick()
+        x = self.model._prep(source)
+        t1 = self._tick()
+        rows, counts = self.model.detect(x, **self._nms_args(conf, iou, max_det, agnostic_nms, classes))
+        t2 = self._tick()
         counts = counts.tolist()
         shape = tuple(source.shape[2:])
-        return [Results(rows[i, : counts[i]].clone(), shape, self.names, path=f"image{i}.jpg") for i in range(len(counts))]
+        res = [Results(rows[i, : counts[i]].clone(), shape, self.names, path=f"image{i}.jpg") for i in range(len(counts))]
+        return self._stamp(res, t0, t1, t2)
+
+    def _stamp(self, res, t0, t1, t2):
+        """Results.speed: per-image milliseconds of the three phases (reference engine/predictor.py:266-272).  Decode + NMS run
+        inside the same captured graph as the forward pass, so they are counted under "inference"; "postprocess" is what is left
+        of DetectionPredictor.postprocess on the host: reading the counts and wrapping the rows."""
+        t3 = self._tick()
+        n = max(1, len(res))
+        speed = {"preprocess": (t1 - t0) * 1e3 / n, "inference": (t2 - t1) * 1e3 / n, "postprocess": (t3 - t2) * 1e3 / n}
+        for r in res:
+            r.speed = dict(speed)
+        return res
 
     def _predict_images(self, source, conf, iou, max_det, agnostic_nms, classes, imgsz) -> List[Results]:
-        """Image sources (one HWC BGR uint8 array or a list of them): GPU letterbox -> detect -> boxes scaled back to each original
-        image (DetectionPredictor.postprocess, reference models/yolo/detect/predict.py:23-41)."""
+        """Image sources (one HWC BGR uint8 array or a list of them): GPU letterbox (minimum rectangle when all images share a
+        shape, like the reference) -> detect, with the boxes mapped back to each original image inside the NMS epilogue
+        (DetectionPredictor.postprocess, reference models/yolo/detect/predict.py:23-41)."""
         import numpy as np
 
         images = [source] if isinstance(source, np.ndarray) else list(source)
         if not images or not all(isinstance(im, np.ndarray) for im in images):
             raise NotImplementedError("pass a BCHW tensor, one HWC uint8 image or a list of HWC uint8 images")
-        o = self.overrides
         H, W = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        t0 = self._tick()
         x = self.model.preprocess(images, (H, W))
-        rows, counts = self.model.detect(
-            x, conf=o["conf"] if conf is None else conf, iou=o["iou"] if iou is None else iou,
-            agnostic=o["agnostic_nms"] if agnostic_nms is None else agnostic_nms,
-            max_det=o["max_det"] if max_det is None else max_det, classes=classes if classes is not None else o["classes"])
+        t1 = self._tick()
+        rows, counts = self.model.detect(x, orig_shapes=[im.shape[:2] for im in images], **self._nms_args(conf, iou, max_det, agnostic_nms, classes))
+        t2 = self._tick()
         counts = counts.tolist()
-        out = []
-        for i, im in enumerate(images):
-            r = rows[i, : counts[i]].clone()
-            scale_boxes_(r, (H, W), im.shape[:2])
-            out.append(Results(r, tuple(im.shape[:2]), self.names, path=f"image{i}.jpg"))
-        return out
+        res = [Results(rows[i, : counts[i]].clone(), tuple(im.shape[:2]), self.names, path=f"image{i}.jpg") for i, im in enumerate(images)]
+        return self._stamp(res, t0, t1, t2)
 
     __call__ = predict

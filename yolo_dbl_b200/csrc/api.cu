@@ -2,6 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "dbl_common.cuh"
 
@@ -19,6 +22,38 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+const DevInfo& dev_info() {
+    static DevInfo table[64];
+    static std::atomic<unsigned long long> known{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) cudaGetLastError(), dev = 0;
+    DevInfo& d = table[dev & 63];
+    if (!((known.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+        DevInfo t{dev, 0, 0};
+        cudaDeviceGetAttribute(&t.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&t.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        d = t;  // racing writers store identical values
+        known.fetch_or(1ull << (dev & 63), std::memory_order_release);
+    }
+    return d;
+}
+
+static std::mutex g_cfg_mu;
+static std::map<std::pair<const void*, int>, int> g_cfg;
+
+int func_config(const void* fn) {
+    const int dev = dev_info().ordinal;
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    auto it = g_cfg.find({fn, dev});
+    return it == g_cfg.end() ? -1 : it->second;
+}
+
+void func_set_config(const void* fn, int value) {
+    const int dev = dev_info().ordinal;
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    g_cfg[{fn, dev}] = value;
+}
 
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();

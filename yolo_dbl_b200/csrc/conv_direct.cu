@@ -573,16 +573,12 @@ extern "C" int dbl_dwconv2d(const dbl_tensor* x, const float* w, const float* bi
             if (dbg) fprintf(stderr, "dw k%d s%d d%d c%d %dx%d: R=%d G4=%d tw=%d ty=%d smem=%zu\n", k, stride, dil, x->c, ho, wo, R, G4, tw, ty, smem);
         }
         if (have_tile) {
-            static thread_local const void* configured[16];
-            static thread_local int nconf = 0;
-            bool have = false;
-            for (int i = 0; i < nconf; ++i) have = have || configured[i] == reinterpret_cast<const void*>(kern);
-            if (!have) {
+            if (func_config(reinterpret_cast<const void*>(kern)) < 0) {
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) {
                     set_error("dbl_dwconv2d: cannot opt in to 100 KB of shared memory: %s", cudaGetErrorString(cudaGetLastError()));
                     return DBL_E_CUDA;
                 }
-                if (nconf < 16) configured[nconf++] = reinterpret_cast<const void*>(kern);
+                func_set_config(reinterpret_cast<const void*>(kern), 1);
             }
             const int tiles_x = cdiv(wo, tw), tiles_y = cdiv(ho, ty * R);
             dim3 grid(tiles_x * tiles_y, cdiv(x->c, G4 * 4), x->n);

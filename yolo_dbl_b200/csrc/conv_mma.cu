@@ -588,25 +588,10 @@ __global__ void __launch_bounds__(NWARPS * 32) stem_pair_kernel(const StemParams
     }
 }
 
-static int g_sms = 0;
-static int sm_count() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_sms;
-}
-
 template <class Kern>
 static int launch_persistent(Kern kern, size_t smem, int threads, int ntiles, cudaStream_t st, const char* what, int* grid_out) {
-    static thread_local const void* configured[32];
-    static thread_local int blocks_per_sm[32];
-    static thread_local int nconf = 0;
-    int occ = 0;
-    for (int i = 0; i < nconf; ++i)
-        if (configured[i] == reinterpret_cast<const void*>(kern)) occ = blocks_per_sm[i];
-    if (!occ) {
+    int occ = func_config(reinterpret_cast<const void*>(kern));  // resident CTAs per SM on the current device, -1 = not configured there yet
+    if (occ < 1) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
         if (e != cudaSuccess || occ < 1) {
@@ -614,9 +599,9 @@ static int launch_persistent(Kern kern, size_t smem, int threads, int ntiles, cu
             set_error("%s: cannot configure kernel (%zu bytes of shared memory): %s", what, smem, cudaGetErrorString(e));
             return DBL_E_CUDA;
         }
-        if (nconf < 32) configured[nconf] = reinterpret_cast<const void*>(kern), blocks_per_sm[nconf] = occ, ++nconf;
+        func_set_config(reinterpret_cast<const void*>(kern), occ);
     }
-    const int cap = sm_count() * occ;
+    const int cap = dev_info().sms * occ;
     *grid_out = ntiles < cap ? ntiles : cap;
     return DBL_OK;
 }
@@ -672,15 +657,15 @@ static int launch_stem_pair(const void* x, int n, int h, int w, const float* w0,
     p.n = n, p.h = h, p.w = w, p.ho = y->h, p.wo = y->w, p.ypitch = y->pitch, p.in_scale = scale;
     p.tiles_x = cdiv(y->w, TW), p.tiles_y = cdiv(y->h, TH);
     auto kern = stem_pair_kernel<C0, C1, TH, TW, NWARPS, TIN>;
-    static thread_local bool configured = false;  // one flag per template instantiation
-    if (!configured) {
+    static DevOnce once;  // one per template instantiation, one bit per device
+    if (once.need()) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
         if (e != cudaSuccess) {
             cudaGetLastError();
             set_error("dbl_stem_pair: cannot opt in to %d bytes of shared memory: %s", (int)K::SMEM, cudaGetErrorString(e));
             return DBL_E_CUDA;
         }
-        configured = true;
+        once.mark();
     }
     DBL_REQUIRE(n <= 65535 && p.tiles_y <= 65535, DBL_E_UNSUPPORTED, "dbl_stem_pair: grid too large");
     launch_k(kern, dim3(p.tiles_x, p.tiles_y, n), NWARPS * 32, K::SMEM, st, p);

@@ -337,20 +337,17 @@ bool conv3x3_tc3_preferred(const dbl_tensor* x, const dbl_tensor* y, int stride)
 
 int conv3x3_tc3(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int stride, int act,
                 int epi, cudaStream_t st) {
-    static int num_sms = 0, max_smem = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int num_sms = dev_info().sms, max_smem = dev_info().max_smem;
+    static DevOnce once;  // shared-memory opt-in is per device
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) {
             set_error("conv3x3_tc3: cannot opt in to %d bytes of shared memory: %s", max_smem, cudaGetErrorString(e));
-            num_sms = 0;
             return DBL_E_CUDA;
         }
+        once.mark();
     }
     DBL_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, DBL_E_ARG, "conv3x3_tc3: weights must be 16-byte aligned");
     C3Params p;

@@ -448,12 +448,9 @@ bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y) {
 }
 
 int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int act, int epi, cudaStream_t st) {
-    static int num_sms = 0, max_smem = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int num_sms = dev_info().sms, max_smem = dev_info().max_smem;
+    static DevOnce once;  // shared-memory opt-in is per device
+    if (once.need()) {
         cudaError_t e = cudaSuccess;
 #define DBL_T4_ATTR(A, K) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc4_kernel<A, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
@@ -463,9 +460,9 @@ int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl
 #undef DBL_T4_ATTR
         if (e != cudaSuccess) {
             set_error("conv3x3_tc4: cannot opt in to %d bytes of shared memory: %s", max_smem, cudaGetErrorString(e));
-            num_sms = 0;
             return DBL_E_CUDA;
         }
+        once.mark();
     }
     DBL_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, DBL_E_ARG, "conv3x3_tc4: weights must be 16-byte aligned");
     T4Params p;

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/dbl_sm100.h"
 
 namespace dbl {
@@ -21,6 +23,26 @@ int check_launch(const char* what);  // cudaGetLastError -> DBL_E_CUDA
             return (code);                \
         }                                 \
     } while (0)
+
+// ---- per-device state ---------------------------------------------------------------------------------------------
+// SM count / shared-memory limit and every cudaFuncSetAttribute opt-in are properties of ONE device: a process that drives
+// several GPUs (DBLBackend.to('cuda:1')) needs them per ordinal, never in a process-wide static.
+struct DevInfo {
+    int ordinal, sms, max_smem;
+};
+const DevInfo& dev_info();  // of the CURRENT device, cached per ordinal (api.cu)
+// "has this kernel been configured on the current device": one bit per device ordinal.  Usage:
+//   static DevOnce once;  if (once.need()) { cudaFuncSetAttribute(...); once.mark(); }
+struct DevOnce {
+    std::atomic<unsigned long long> done{0};
+    bool need() const { return !((done.load(std::memory_order_acquire) >> (dev_info().ordinal & 63)) & 1ull); }
+    void mark() { done.fetch_or(1ull << (dev_info().ordinal & 63), std::memory_order_release); }
+};
+
+// Table keyed by (kernel function, current device) for launchers that configure many instantiations through one code path:
+// func_config() returns -1 until func_set_config(fn, value >= 0) has been called on the current device (value: e.g. occupancy).
+int func_config(const void* fn);
+void func_set_config(const void* fn, int value);
 
 // ---- launches: programmatic dependent launch (PDL) ----------------------------------------------------------------
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute: the next kernel of the

@@ -150,9 +150,24 @@ __host__ __device__ inline size_t next_pow2(size_t v) {
 }
 
 // Scratch per image (in uint64 units): keys[P] | payload u32[P] (P/2 u64) | boxes float4[P] (2P u64)
+// Epilogue of the NMS: one output row.  With a scale record (pad_x, pad_y, gain, w0, h0) the kept box leaves in the ORIGINAL image's
+// coordinates: scale_boxes + clip_boxes (utils/ops.py:92-127, 319-338) -- subtract the letterbox padding, divide by the gain (an
+// IEEE division like the reference's fp32 tensor / scalar), clamp to the image -- so no separate pass touches the rows again.
+__device__ __forceinline__ void emit_row(float* __restrict__ ro, float4 bx, float score, int cls, const float* __restrict__ sc) {
+    if (sc) {
+        const float px = sc[0], py = sc[1], g = sc[2], w0 = sc[3], h0 = sc[4];
+        bx.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, px), g), 0.f), w0);
+        bx.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, py), g), 0.f), h0);
+        bx.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, px), g), 0.f), w0);
+        bx.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, py), g), 0.f), h0);
+    }
+    ro[0] = bx.x, ro[1] = bx.y, ro[2] = bx.z, ro[3] = bx.w, ro[4] = score, ro[5] = (float)cls;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd, float iou_thr, float cls_scale, int max_nms, int max_det,
-                                                               uint64_t* __restrict__ scratch, size_t per_image, float* __restrict__ out_rows,
-                                                               int32_t* __restrict__ out_pos, int32_t* __restrict__ out_count) {
+                                                               uint64_t* __restrict__ scratch, size_t per_image, const float* __restrict__ scale,
+                                                               float* __restrict__ out_rows, int32_t* __restrict__ out_pos,
+                                                               int32_t* __restrict__ out_count) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) unsigned char nms_smem[];
@@ -161,6 +176,7 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
     __shared__ int s_keep[1024];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = min(cd.count[b], cd.cap);
+    const float* sc = scale ? scale + 5 * (size_t)b : nullptr;
     if (n <= NMS_FAST_N) {
         // ---------------- fast path (the usual case): everything stays in shared memory --------------------------------
         // stable sort -> class-offset boxes -> full suppression bit-matrix in parallel -> one warp walks it greedily.
@@ -242,8 +258,7 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
             float* ro = out_rows + ((size_t)b * max_det + k) * 6;
             if (k < kept) {
                 const size_t sidx = cb + fslot[s_keep[k]];
-                const float4 bx = reinterpret_cast<const float4*>(cd.box)[sidx];
-                ro[0] = bx.x, ro[1] = bx.y, ro[2] = bx.z, ro[3] = bx.w, ro[4] = cd.score[sidx], ro[5] = (float)cd.cls[sidx];
+                emit_row(ro, reinterpret_cast<const float4*>(cd.box)[sidx], cd.score[sidx], cd.cls[sidx], sc);
                 out_pos[(size_t)b * max_det + k] = cd.pos[sidx];
             } else {
                 ro[0] = ro[1] = ro[2] = ro[3] = ro[4] = ro[5] = 0.f;
@@ -442,8 +457,7 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
         float* ro = out_rows + ((size_t)b * max_det + k) * 6;
         if (k < kept) {
             const size_t s = cbase + slot_of[s_keep[k]];
-            const float4 bx = reinterpret_cast<const float4*>(cd.box)[s];
-            ro[0] = bx.x, ro[1] = bx.y, ro[2] = bx.z, ro[3] = bx.w, ro[4] = cd.score[s], ro[5] = (float)cd.cls[s];
+            emit_row(ro, reinterpret_cast<const float4*>(cd.box)[s], cd.score[s], cd.cls[s], sc);
             out_pos[(size_t)b * max_det + k] = cd.pos[s];
         } else {
             ro[0] = ro[1] = ro[2] = ro[3] = ro[4] = ro[5] = 0.f;
@@ -451,6 +465,91 @@ __global__ void __launch_bounds__(NMS_THREADS) sort_nms_kernel(dbl_candidates cd
         }
     }
     if (tid == 0) out_count[b] = kept;
+}
+
+// ---- validator path: a-priori labels (utils/ops.py:255-261) -------------------------------------------------------------
+// The reference appends, per image, one row per ground-truth label AFTER the rows that passed the confidence filter: box =
+// xywh2xyxy(label box), score 1.0 on the label's class.  Here: one extra candidate per label with the position key of that row
+// (anchors + k, or (anchors + k) * nc + cls with multi_label), so the stable sort orders it exactly like the reference does.
+// grid (ceil(max_labels/128), B)
+__global__ void __launch_bounds__(128) append_labels_kernel(const float* __restrict__ labels, const int32_t* __restrict__ offs, int anchors,
+                                                            int nc, int multi_label, float conf, const int32_t* __restrict__ classes, int ncls,
+                                                            dbl_candidates cd) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = offs[b + 1] - offs[b];
+    const bool live = k < n;
+    float4 box = make_float4(0, 0, 0, 0);
+    int c = 0;
+    if (live) {
+        const float* lb = labels + 5 * (size_t)(offs[b] + k);
+        c = (int)lb[0];  // lb[:, 0].long()
+        box = xywh_to_xyxy(make_float4(lb[1], lb[2], lb[3], lb[4]));
+    }
+    const bool ok = live && c >= 0 && c < nc && 1.0f > conf && class_allowed(c, classes, ncls);
+    push_candidate(ok, cd, b, box, 1.0f, c, multi_label ? (anchors + k) * nc + c : anchors + k);
+}
+
+// ---- validator path: DetectionValidator._process_batch = box_iou + match_predictions ----------------------------------------
+// box_iou (utils/metrics.py:52-71): inter / ((area_a + area_b - inter) + eps), strict fp32; match_predictions
+// (engine/validator.py:222-260, use_scipy=False) for every IoU threshold t: keep the pairs (label l, detection d) of equal class with
+// iou >= thr_t, order them by descending IoU, keep the first pair of every detection, then (in detection order) the first pair of
+// every label.  Equivalent closed form: best(d) = arg max_l iou(l, d) over the admissible labels; label l is won by the SMALLEST d
+// with best(d) == l; correct[d, t] = (d won best(d)).  Pairs of exactly equal IoU (the reference's unstable argsort leaves their order
+// unspecified) resolve to the larger label index.  One CTA per image.
+constexpr int MATCH_MAX_THR = 16;
+__global__ void __launch_bounds__(256) match_predictions_kernel(const float* __restrict__ rows, const int32_t* __restrict__ counts, int max_det,
+                                                                const float* __restrict__ gt_box, const float* __restrict__ gt_cls,
+                                                                const int32_t* __restrict__ gt_offs, const float* __restrict__ iouv, int T,
+                                                                uint8_t* __restrict__ correct, int32_t* __restrict__ winner_ws, int max_labels) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nd = min(counts[b], max_det), g0 = gt_offs[b], nl = min(gt_offs[b + 1] - g0, max_labels);
+    int32_t* winner = winner_ws + (size_t)b * max_labels * T;  // [T][max_labels]
+    for (int i = tid; i < nl * T; i += blockDim.x) winner[(i / nl) * max_labels + (i % nl)] = 0x7fffffff;
+    for (int i = tid; i < max_det * T; i += blockDim.x) correct[(size_t)b * max_det * T + i] = 0;
+    __syncthreads();
+    float thr[MATCH_MAX_THR];
+#pragma unroll
+    for (int t = 0; t < MATCH_MAX_THR; ++t) thr[t] = t < T ? iouv[t] : CUDART_INF_F;
+    for (int d0 = 0; d0 < nd; d0 += blockDim.x) {  // block-uniform trip count: the barriers below are reached by every thread
+        const int d = d0 + tid;
+        int best[MATCH_MAX_THR];
+        float biou[MATCH_MAX_THR];
+#pragma unroll
+        for (int t = 0; t < MATCH_MAX_THR; ++t) best[t] = -1, biou[t] = 0.f;
+        if (d < nd) {
+            const float* r = rows + ((size_t)b * max_det + d) * 6;
+            const float bx1 = r[0], by1 = r[1], bx2 = r[2], by2 = r[3], bc = r[5];
+            const float area_b = __fmul_rn(__fsub_rn(bx2, bx1), __fsub_rn(by2, by1));
+            for (int l = 0; l < nl; ++l) {
+                const float4 a = reinterpret_cast<const float4*>(gt_box)[g0 + l];
+                const float w = fmaxf(__fsub_rn(fminf(a.z, bx2), fmaxf(a.x, bx1)), 0.f);
+                const float h = fmaxf(__fsub_rn(fminf(a.w, by2), fmaxf(a.y, by1)), 0.f);
+                const float inter = __fmul_rn(w, h);
+                const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+                float iou = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-7f));
+                iou = gt_cls[g0 + l] == bc ? iou : __fmul_rn(iou, 0.f);  // iou * correct_class
+#pragma unroll
+                for (int t = 0; t < MATCH_MAX_THR; ++t)
+                    if (iou >= thr[t] && iou >= biou[t]) best[t] = l, biou[t] = iou;
+            }
+#pragma unroll
+            for (int t = 0; t < MATCH_MAX_THR; ++t)
+                if (t < T && best[t] >= 0) atomicMin(winner + t * max_labels + best[t], d);
+        }
+        __syncthreads();  // all detections of this image vote before anyone reads: process chunks in order, smaller d first
+        // a later chunk can never take a label from an earlier one (atomicMin keeps the smallest d), so reading now is final
+        // for every d of this chunk only if no EARLIER d is still to come -- chunks are processed in ascending order.
+        if (d < nd) {
+#pragma unroll
+            for (int t = 0; t < MATCH_MAX_THR; ++t)
+                if (t < T && best[t] >= 0 && winner[t * max_labels + best[t]] == d) correct[((size_t)b * max_det + d) * T + t] = 1;
+        }
+        __syncthreads();
+    }
 }
 
 static bool valid_cand(const dbl_candidates* c) {
@@ -510,21 +609,63 @@ extern "C" size_t dbl_nms_sort_capacity(int cap) {
 
 extern "C" int dbl_nms(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
                        uint64_t* sort_keys, float* out_rows, int32_t* out_pos, int32_t* out_count, dbl_stream_t stream) {
+    return dbl_nms_scaled(cand, iou_thres, agnostic, max_wh, max_nms, max_det, sort_keys, nullptr, out_rows, out_pos, out_count, stream);
+}
+
+extern "C" int dbl_nms_scaled(const dbl_candidates* cand, float iou_thres, int agnostic, float max_wh, int max_nms, int max_det,
+                              uint64_t* sort_keys, const dbl_box_scale* scale, float* out_rows, int32_t* out_pos, int32_t* out_count,
+                              dbl_stream_t stream) {
     DBL_REQUIRE(valid_cand(cand) && sort_keys && out_rows && out_pos && out_count, DBL_E_ARG, "dbl_nms: invalid argument");
     DBL_REQUIRE(max_det >= 1 && max_det <= 1024, DBL_E_UNSUPPORTED, "dbl_nms: max_det %d not in [1,1024]", max_det);
     DBL_REQUIRE(max_nms >= 1, DBL_E_ARG, "dbl_nms: max_nms");
     DBL_REQUIRE(std::min(cand->cap, max_nms) <= NMS_FLAG_CAP, DBL_E_UNSUPPORTED,
                 "dbl_nms: min(cap,max_nms)=%d exceeds the %d candidates one image may hold", std::min(cand->cap, max_nms), NMS_FLAG_CAP);
     DBL_REQUIRE((reinterpret_cast<uintptr_t>(sort_keys) & 15) == 0, DBL_E_ARG, "dbl_nms: scratch must be 16-byte aligned");
-    static bool smem_ok = false;
-    if (!smem_ok) {
+    static DevOnce once;
+    if (once.need()) {
         cudaError_t e = cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM);
         DBL_REQUIRE(e == cudaSuccess, DBL_E_CUDA, "dbl_nms: shared memory opt-in failed: %s", cudaGetErrorString(e));
-        smem_ok = true;
+        once.mark();
     }
     launch_k(sort_nms_kernel, cand->batch, NMS_THREADS, NMS_SMEM, as_stream(stream), *cand, iou_thres, agnostic ? 0.f : max_wh, max_nms, max_det,
-                                                                        sort_keys, dbl_nms_sort_capacity(cand->cap), out_rows, out_pos,
-                                                                        out_count);
+             sort_keys, dbl_nms_sort_capacity(cand->cap), reinterpret_cast<const float*>(scale), out_rows, out_pos, out_count);
     count_launch();
     return check_launch("dbl_nms");
+}
+
+extern "C" int dbl_nms_append_labels(const float* labels, const int32_t* label_offsets, int max_labels_per_image, int anchors, int nc,
+                                     int multi_label, float conf_thres, const int32_t* classes, int num_classes_kept,
+                                     const dbl_candidates* cand, dbl_stream_t stream) {
+    DBL_REQUIRE(labels && label_offsets && valid_cand(cand) && anchors > 0 && nc > 0 && max_labels_per_image >= 0, DBL_E_ARG,
+                "dbl_nms_append_labels: invalid argument");
+    if (max_labels_per_image == 0) return DBL_OK;
+    const int ml = (multi_label && nc > 1) ? 1 : 0;
+    DBL_REQUIRE((long long)(anchors + max_labels_per_image) * (ml ? nc : 1) < (1ll << 31), DBL_E_UNSUPPORTED,
+                "dbl_nms_append_labels: position keys exceed 31 bits");
+    DBL_REQUIRE(cand->batch <= 65535, DBL_E_UNSUPPORTED, "dbl_nms_append_labels: batch too large");
+    launch_k(append_labels_kernel, dim3(cdiv(max_labels_per_image, 128), cand->batch), 128, 0, as_stream(stream), labels, label_offsets, anchors, nc,
+             ml, conf_thres, classes, num_classes_kept, *cand);
+    count_launch();
+    return check_launch("dbl_nms_append_labels");
+}
+
+extern "C" size_t dbl_match_workspace_bytes(int batch, int max_labels_per_image, int num_thresholds) {
+    if (batch <= 0 || max_labels_per_image <= 0 || num_thresholds <= 0) return 0;
+    return sizeof(int32_t) * (size_t)batch * max_labels_per_image * num_thresholds;
+}
+
+extern "C" int dbl_match_predictions(const float* rows, const int32_t* counts, int batch, int max_det, const float* gt_boxes,
+                                     const float* gt_cls, const int32_t* gt_offsets, int max_labels_per_image, const float* iou_thresholds,
+                                     int num_thresholds, uint8_t* correct, void* ws, size_t ws_bytes, dbl_stream_t stream) {
+    DBL_REQUIRE(rows && counts && gt_offsets && iou_thresholds && correct && batch > 0 && max_det > 0, DBL_E_ARG,
+                "dbl_match_predictions: invalid argument");
+    DBL_REQUIRE(num_thresholds >= 1 && num_thresholds <= MATCH_MAX_THR, DBL_E_UNSUPPORTED, "dbl_match_predictions: 1..%d thresholds", MATCH_MAX_THR);
+    DBL_REQUIRE(max_labels_per_image >= 0 && (max_labels_per_image == 0 || (gt_boxes && gt_cls)), DBL_E_ARG, "dbl_match_predictions: labels");
+    DBL_REQUIRE((reinterpret_cast<uintptr_t>(gt_boxes) & 15) == 0, DBL_E_ARG, "dbl_match_predictions: gt_boxes must be 16-byte aligned");
+    const int ml = max_labels_per_image > 0 ? max_labels_per_image : 1;
+    DBL_REQUIRE(ws && ws_bytes >= dbl_match_workspace_bytes(batch, ml, num_thresholds), DBL_E_WORKSPACE, "dbl_match_predictions: workspace too small");
+    launch_k(match_predictions_kernel, batch, 256, 0, as_stream(stream), rows, counts, max_det, gt_boxes, gt_cls, gt_offsets, iou_thresholds,
+             num_thresholds, correct, reinterpret_cast<int32_t*>(ws), ml);
+    count_launch();
+    return check_launch("dbl_match_predictions");
 }

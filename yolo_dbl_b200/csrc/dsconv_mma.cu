@@ -278,16 +278,14 @@ static bool ds_pick_tile(int k, int s, int cin, int cout, int ho, int wo, int ma
 template <int K, int S, int CIN, int COUT, int DW_ACT>
 static int launch_ds(const dbl_tensor* x, const float* wdw, const float* bdw, const void* wpw, const float* bpw, const dbl_tensor* r,
                      const dbl_tensor* y, int epi, cudaStream_t st) {
-    static int max_smem = 0;
-    if (!max_smem) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int max_smem = dev_info().max_smem;
+    static DevOnce once;  // one per template instantiation, one bit per device
+    if (once.need()) {
         if (cudaFuncSetAttribute(dsconv_mma_kernel<K, S, CIN, COUT, DW_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
             set_error("dbl_dsconv: cannot opt in to %d bytes of shared memory: %s", max_smem, cudaGetErrorString(cudaGetLastError()));
-            max_smem = 0;
             return DBL_E_CUDA;
         }
+        once.mark();
     }
     DsParams p;
     memset(&p, 0, sizeof(p));

@@ -246,15 +246,15 @@ template <int C3, int NCP>
 static int launch_head(const HfParams& p, cudaStream_t st) {
     using K = HfCfg<C3, NCP>;
     auto kern = head_decode_kernel<C3, NCP>;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DevOnce once;  // one per template instantiation, one bit per device
+    if (once.need()) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
         if (e != cudaSuccess) {
             cudaGetLastError();
             set_error("dbl_head_decode: cannot opt in to %d bytes of shared memory: %s", (int)K::SMEM, cudaGetErrorString(e));
             return DBL_E_CUDA;
         }
-        configured = true;
+        once.mark();
     }
     launch_k(kern, p.batch * p.blocks_per_img, 256, (size_t)K::SMEM, st, p);
     count_launch();

@@ -640,9 +640,9 @@ class DBLEngine:
 
     def _post(self, key: tuple) -> dict:
         if key not in self._post_bufs:
-            conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = key
+            conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh, scaled, labels_cap = key
             ml = bool(multi_label) and self.spec.nc > 1
-            cap = self.A * (self.spec.nc if ml else 1)
+            cap = (self.A + labels_cap) * (self.spec.nc if ml else 1)  # a-priori labels (validator path) are appended to the candidates
             dev, B = self.dev, self.B
             d = dict(
                 box=torch.zeros(B, cap, 4, device=dev), score=torch.zeros(B, cap, device=dev),
@@ -652,25 +652,42 @@ class DBLEngine:
                 rows=torch.zeros(B, max_det, 6, device=dev), out_pos=torch.zeros(B, max_det, dtype=torch.int32, device=dev),
                 out_count=torch.zeros(B, dtype=torch.int32, device=dev),
                 classes=torch.tensor(list(classes), dtype=torch.int32, device=dev) if classes else None,
+                # per-image (pad_x, pad_y, gain, w0, h0) of scale_boxes / clip_boxes, read by the NMS epilogue; identity until set_scale()
+                scale=torch.tensor([[0.0, 0.0, 1.0, float(self.W), float(self.H)]] * B, dtype=torch.float32, device=dev) if scaled else None,
+                labels=torch.zeros(max(1, B * labels_cap), 5, device=dev) if labels_cap else None,
+                label_offs=torch.zeros(B + 1, dtype=torch.int32, device=dev) if labels_cap else None,
             )
             d["cand"] = L.Candidates(d["box"].data_ptr(), d["score"].data_ptr(), d["cls"].data_ptr(), d["pos"].data_ptr(),
                                      d["count"].data_ptr(), cap, B)
             self._post_bufs[key] = d
         return self._post_bufs[key]
 
-    def _launch_post(self, key: tuple, stream: int):
-        conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = key
-        d = self._post(key)
+    def _launch_filter(self, key: tuple, d: dict, stream: int):
+        conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh, scaled, labels_cap = key
         ncls = len(classes) if classes else 0
         if self.head_fused is not None:
-            L.check(self.lib.dbl_head_decode(C.byref(self.head_fused_nolog), None, C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]),
-                                             ncls, C.byref(d["cand"]), stream), "dbl_head_decode")
+            rc = self.lib.dbl_head_decode(C.byref(self.head_fused_nolog), None, C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]),
+                                          ncls, C.byref(d["cand"]), stream)
+            L.check(rc, "dbl_head_decode")
         else:
-            L.check(self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]), ncls,
-                                               C.byref(d["cand"]), stream), "dbl_decode_filter")
-        L.check(self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
-                                 d["keys"].data_ptr(), d["rows"].data_ptr(), d["out_pos"].data_ptr(), d["out_count"].data_ptr(), stream),
-                "dbl_nms")
+            rc = self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(bool(multi_label)), L.ptr(d["classes"]), ncls,
+                                            C.byref(d["cand"]), stream)
+            L.check(rc, "dbl_decode_filter")
+        if labels_cap:  # validator path: non_max_suppression(labels=...) (utils/ops.py:255-261)
+            L.check(self.lib.dbl_nms_append_labels(d["labels"].data_ptr(), d["label_offs"].data_ptr(), labels_cap, self.A, self.spec.nc,
+                                                   int(bool(multi_label)), C.c_float(conf), L.ptr(d["classes"]), ncls, C.byref(d["cand"]), stream),
+                    "dbl_nms_append_labels")
+
+    def _launch_nms(self, key: tuple, d: dict, stream: int):
+        conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh, scaled, labels_cap = key
+        L.check(self.lib.dbl_nms_scaled(C.byref(d["cand"]), C.c_float(iou), int(bool(agnostic)), C.c_float(max_wh), int(max_nms), int(max_det),
+                                        d["keys"].data_ptr(), L.ptr(d["scale"]), d["rows"].data_ptr(), d["out_pos"].data_ptr(),
+                                        d["out_count"].data_ptr(), stream), "dbl_nms")
+
+    def _launch_post(self, key: tuple, stream: int):
+        d = self._post(key)
+        self._launch_filter(key, d, stream)
+        self._launch_nms(key, d, stream)
 
     def _run(self, key: Optional[tuple], want_y: bool):
         """Launch forward (+decode) (+post-process) on the current stream, through a cached CUDA graph when enabled."""
@@ -708,9 +725,34 @@ class DBLEngine:
         g.replay()
 
     @staticmethod
-    def post_key(conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None, max_nms=30000, max_wh=7680):
+    def post_key(conf=0.25, iou=0.45, agnostic=False, multi_label=False, max_det=300, classes=None, max_nms=30000, max_wh=7680,
+                 scaled=False, labels_cap=0):
+        """scaled: the NMS epilogue applies scale_boxes + clip_boxes with the per-image records of set_scale();
+        labels_cap > 0: up to that many a-priori labels per image (set_labels()) join the candidates (validator path)."""
         return (float(conf), float(iou), bool(agnostic), bool(multi_label), int(max_det), tuple(classes) if classes else (),
-                int(max_nms), float(max_wh))
+                int(max_nms), float(max_wh), bool(scaled), int(labels_cap))
+
+    def set_scale(self, key: tuple, records: torch.Tensor):
+        """records [B,5] f32 = (pad_x, pad_y, gain, w0, h0) per image (host or device); stream-ordered copy into the table the
+        captured NMS launch reads."""
+        self._post(key)["scale"].copy_(records.to(torch.float32).reshape(self.B, 5), non_blocking=True)
+
+    def set_labels(self, key: tuple, labels: Sequence[torch.Tensor]):
+        """labels: per image an (n_i, 5) tensor (cls, x, y, w, h) in network-input pixels -- DetectionValidator.lb
+        (models/yolo/detect/val.py:60-65).  Packed into the fixed-capacity device buffers the captured launch reads."""
+        d, cap = self._post(key), key[9]
+        if len(labels) != self.B:
+            raise ValueError(f"expected {self.B} label tensors")
+        offs, parts = [0], []
+        for lb in labels:
+            lb = torch.as_tensor(lb, dtype=torch.float32).reshape(-1, 5)
+            if lb.shape[0] > cap:
+                raise ValueError(f"{lb.shape[0]} labels in one image exceed labels_cap={cap}")
+            parts.append(lb.cpu())
+            offs.append(offs[-1] + lb.shape[0])
+        if offs[-1]:
+            d["labels"][: offs[-1]].copy_(torch.cat(parts), non_blocking=False)
+        d["label_offs"].copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=False)
 
     def set_input(self, im: torch.Tensor):
         """Stage one batch: float BCHW in 0..1 (LoadTensor sources) or uint8 BCHW in 0..255 (image sources); `im` may
@@ -758,20 +800,13 @@ class DBLEngine:
                     fn(*args, st)
                     ev[i][1].record()
                 if post_key is not None:
-                    conf, iou, agnostic, multi_label, max_det, classes, max_nms, max_wh = post_key
                     d = self._post(post_key)
                     n = len(self.ops)
                     ev[n][0].record()
-                    if self.head_fused is not None:
-                        self.lib.dbl_head_decode(C.byref(self.head_fused_nolog), None, C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
-                                                 len(classes), C.byref(d["cand"]), st)
-                    else:
-                        self.lib.dbl_decode_filter(C.byref(self.levels), C.c_float(conf), int(multi_label), L.ptr(d["classes"]),
-                                                   len(classes), C.byref(d["cand"]), st)
+                    self._launch_filter(post_key, d, st)
                     ev[n][1].record()
                     ev[n + 1][0].record()
-                    self.lib.dbl_nms(C.byref(d["cand"]), C.c_float(iou), int(agnostic), C.c_float(max_wh), int(max_nms), int(max_det),
-                                     d["keys"].data_ptr(), d["rows"].data_ptr(), d["out_pos"].data_ptr(), d["out_count"].data_ptr(), st)
+                    self._launch_nms(post_key, d, st)
                     ev[n + 1][1].record()
                 torch.cuda.synchronize(self.dev)
                 for i in range(len(acc)):
