@@ -1,14 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the YOLO-DBL inference hot path on B200 (BASELINE.json metric: images/sec, 640^2, batch 64 per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]               # the B200 path (this repo)
+    python bench.py [--gpus N] [--steps K] [--warmup W]               # the B200 path (this repo), BASELINE config 3
     python bench.py --impl reference [--steps K] [--warmup W]         # the reference's algorithm on the host CPU
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU
+    python bench.py --workload decode_nms [--regime typical|dense]    # BASELINE config 2 (Detect decode + NMS microbench)
+    python bench.py --scale l --batch 32                              # BASELINE config 4
+    python bench.py --imgsz 1280 --batch 16 --conf 0.001              # BASELINE config 5
 
 A step = forward + Detect decode + NMS over one batch of 64 synthetic 640x640 images per GPU (weak scaling: images are
-independent, ranks never exchange data on the path; the only collective is the timing reduction).  One JSON line is
-printed by rank 0.  `value` is timed with inputs resident in HBM (CUDA-graph replays); `e2e` goes through the public
-API with pinned HOST input and a device->host read of the detections inside the timed region.
+independent, ranks never exchange data on the path; the only collectives are the timing reduction and, in the end-to-end leg, the
+final gather of the detections).  One JSON line is printed by rank 0.  `value` is timed with inputs resident in HBM (CUDA-graph
+replays); `e2e` goes through the public API with pinned HOST input and a device->host read of the detections inside the timed
+region.  With N > 1 the line also carries a `strong` block: the SAME global batch of 64 images sharded 64/N per GPU, gather included.
 """
 import argparse
 import json
@@ -24,9 +28,17 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "images_per_sec_yolo_dbl_n_640_b64_forward_decode_nms"
 PEAKS_FALLBACK = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-NMS = dict(conf=0.25, iou=0.7, max_det=300)  # predict defaults: cfg/default.yaml:51-53 of the reference
+
+
+def nms_args(args):
+    return dict(conf=args.conf, iou=0.7, max_det=300)  # predict defaults: cfg/default.yaml:51-53 of the reference
+
+
+def metric_name(args):
+    if args.workload == "decode_nms":
+        return f"candidates_per_sec_detect_decode_nms_b{args.batch}_a8400_nc{args.nc}_{args.regime}"
+    return f"images_per_sec_yolo_dbl_{args.scale}_{args.imgsz}_b{args.batch}_forward_decode_nms"
 
 
 def load_peaks():
@@ -72,25 +84,35 @@ class ClockSampler:
                 "power_w_max": max((float(r[3]) for r in rows if len(r) >= 8), default=None), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bench_images(args, rank=0):
+    """The batch every arm measures: 8 distinct synthetic images tiled to the batch (CPU synthesis is slow)."""
+    from yolo_dbl_b200 import synth_images
+
+    small = synth_images(8, args.imgsz, args.imgsz, seed=100 + rank)
+    return small, small.repeat((args.batch + 7) // 8, 1, 1, 1)[: args.batch].contiguous()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle (a port of the reference's algorithm; the reference itself is pure Python that
 # cannot travel to the GPU box) on all host threads
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_port_run(scale, nc, hw, images_per_step, steps, warmup):
+def cpu_port_run(args, images_per_step, steps, warmup):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import dbl_oracle as O  # the only place bench.py touches oracle/: as the measured CPU implementation
+    import dbl_oracle as O  # bench.py touches oracle/ only here and in parity_check(): as the measured CPU implementation / the checker
     import nms_oracle as N
-    from yolo_dbl_b200 import param_shapes, resolve, synth_images, synth_state_dict
+    from yolo_dbl_b200 import param_shapes, resolve, synth_state_dict
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    spec = resolve(None, scale, nc)
+    spec = resolve(None, args.scale, args.nc)
     sd = synth_state_dict(param_shapes(spec), 0)
-    x = synth_images(images_per_step, hw, hw, seed=11)
+    _, x = bench_images(args)
+    x = x[:images_per_step]
+    kw = nms_args(args)
 
     def step():
-        y, _ = O.forward(sd, x, scale)
-        N.non_max_suppression(y.numpy(), NMS["conf"], NMS["iou"], max_det=NMS["max_det"])
+        y, _ = O.forward(sd, x, args.scale)
+        N.non_max_suppression(y.numpy(), kw["conf"], kw["iou"], max_det=kw["max_det"])
 
     for _ in range(warmup):
         step()
@@ -102,17 +124,24 @@ def cpu_port_run(scale, nc, hw, images_per_step, steps, warmup):
 
 
 def run_reference(args):
+    """--impl reference: the CPU implementation of the same workload, SAME config dict, the full batch per step.  Calibration of
+    the port against the real reference (this container, B=8, 8 threads): port 15.2 img/s vs reference 16.3 img/s -- the port is
+    ~7 % SLOWER than the reference's own code, so GPU/CPU ratios computed from this arm are ~7 % flattering."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 32  # bounded sample of the 64-image step: ~0.8 s of CPU work per step on 16 threads
+    if args.workload != "model":
+        emit({"impl": "reference", "unavailable": "the CPU arm is defined for the whole-model workload only"})
+        return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, per_step, steps, warmup)
-    sample = f"{per_step} images/step of the {args.batch}-image workload, {steps} steps after {warmup} warm-up, oracle port (torch CPU fp32 + C NMS)"
+    per_step = args.batch
+    ips, ms, cores = cpu_port_run(args, per_step, steps, warmup)
+    sample = (f"{per_step} images/step = the full {args.batch}-image step, {steps} steps after {warmup} warm-up; oracle port (torch CPU fp32 forward + C NMS) "
+              f"on {cores} host threads; port-vs-real-reference calibration 0.93x (BASELINE.md)")
     emit({
-        "impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric_name(args), "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(args, 1),
+        "data": "synthetic", "config": config_dict(args, max(1, args.gpus)),
         "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -120,10 +149,34 @@ def run_reference(args):
 
 
 def config_dict(args, world):
+    kw = nms_args(args)
     return {"workload": f"YOLO-DBL-{args.scale} (yolov13_DBL.yaml, nc={args.nc}) {args.imgsz}x{args.imgsz}, batch {args.batch} per GPU, "
-                        f"forward + Detect decode + NMS (conf {NMS['conf']}, iou {NMS['iou']}, max_det {NMS['max_det']})",
+                        f"forward + Detect decode + NMS (conf {kw['conf']}, iou {kw['iou']}, max_det {kw['max_det']})",
             "global_batch": args.batch * world, "per_gpu_batch": args.batch, "imgsz": args.imgsz, "parallelism": f"dp{world} (images sharded, no data-path collective)",
-            "weights": "synthetic recipe seed 0 (+BN calibration table)", "l2": "inputs 315 MB/step > 126 MB L2; activations stream through HBM"}
+            "weights": "synthetic recipe seed 0 (+BN calibration table)",
+            "l2": f"inputs {args.batch * 3 * args.imgsz * args.imgsz * 4 / 1e6:.0f} MB/step > 126 MB L2; activations stream through HBM",
+            "steps_in_flight": max(1, args.inflight)}
+
+
+def parity_check(model, eng, x_host, args):
+    """One step of the benchmarked engine against the CPU oracle (the checker, never the thing measured): the detections of
+    detect() must equal the oracle's non_max_suppression of the engine's own decoded y, bit for bit, for every image of the batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nms_oracle as N
+
+    kw = nms_args(args)
+    y, _ = eng.forward(x_host)
+    y = y.cpu().numpy()
+    rows, counts, _ = eng.detect(x_host, **kw)
+    torch.cuda.synchronize()
+    rows, counts = rows.cpu().numpy(), counts.tolist()
+    want, _ = N.non_max_suppression(y, kw["conf"], kw["iou"], max_det=kw["max_det"])
+    exact = all(counts[i] == len(w) and rows[i, : counts[i]].tobytes() == w.tobytes() for i, w in enumerate(want))
+    out = {"detections_oracle": int(sum(len(w) for w in want)), "detections_cuda": int(sum(counts)), "rows_bit_exact": bool(exact),
+           "what": "detect() rows vs oracle non_max_suppression of the engine's decoded y, all images of one step"}
+    if not exact:
+        raise SystemExit(f"bench.py: parity check failed: {out}")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -144,9 +197,33 @@ def kernel_table(rows, peaks):
         f["gbs"] = f["bytes"] / s / 1e9 if s else 0.0
         f["tflops"] = f["flops"] / s / 1e12 if s else 0.0
         f["hbm_frac"] = f["gbs"] / peaks["hbm_gbs"]
-        f["tensor_frac"] = f["tflops"] / peaks["bf16_tflops_sustained"]
+        f["tensor_frac"] = f["tflops"] / peaks["bf16_tflops"]  # kernels are timed alone: the burst peak is the denominator
         out.append(f)
     return sorted(out, key=lambda f: -f["ms"])
+
+
+def roofline_block(table, peaks):
+    top = table[0]  # the kernel (family) with the largest share of the step; per-launch averages below
+    t_tensor, t_hbm = top["flops"] / (peaks["bf16_tflops"] * 1e12), top["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_tensor > t_hbm else "hbm"
+    ach, peak, unit = (top["tflops"], peaks["bf16_tflops"], "TFLOP/s") if bound == "tensor" else (top["gbs"], peaks["hbm_gbs"], "GB/s")
+    traffic = None  # DRAM bytes per launch from the committed ncu capture of the same command
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top["kern"], {}).get("dram_bytes_per_launch")
+            if traffic is not None:
+                break
+    n = max(1, top["launches"])
+    return {"kernel": top["kern"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+            "peak_kind": "burst (the kernel is timed alone between its own CUDA events; MEASURED_PEAKS.json bf16_tflops / hbm_gbs)",
+            "frac_of_sustained_tensor_peak": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4),
+            "traffic": traffic, "launches_per_step": top["launches"], "share_of_step": round(top["share"], 3),
+            "avg_launch_us": round(top["ms"] * 1e3 / n, 2), "algorithmic_bytes_per_launch": round(top["bytes"] / n),
+            "algorithmic_flops_per_launch": round(top["flops"] / n), "peak_source": peaks["source"],
+            "tensor_frac": round(top["tflops"] / peaks["bf16_tflops"], 4), "hbm_frac": round(top["gbs"] / peaks["hbm_gbs"], 4),
+            "note": "achieved = sum of algorithmic bytes (or flops) of this kernel's launches in one step / sum of their CUDA-event times; "
+                    "per-launch rows: --kernel-table"}
 
 
 _STDOUT = sys.stdout
@@ -157,6 +234,91 @@ def emit(line: dict):
     print(json.dumps(line), file=_STDOUT, flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE config 2: Detect-head decode + NMS microbench (8400 anchors x nc classes, batch 64, one GPU)
+# ----------------------------------------------------------------------------------------------------------------------
+def run_decode_nms(args, dev):
+    """Head logits (B, 64+nc, 8400) fp32 -> dbl_decode_filter -> dbl_nms, SURVEY.md §8d config 2: box logits ~ N(0,2) (seed 2), class
+    logits ~ N(mu,1.5); `typical` = mu chosen so ~2 % of the anchors pass conf 0.25, `dense` = conf 0.001 with every anchor a candidate."""
+    import ctypes as C
+
+    from yolo_dbl_b200 import _lib as L
+
+    lib = L.require_device()
+    B, nc, hw = args.batch, args.nc, [(80, 80), (40, 40), (20, 20)]
+    A = sum(h * w for h, w in hw)
+    conf = 0.25 if args.regime == "typical" else 0.001
+    g = torch.Generator().manual_seed(2)
+    # P(max of nc logits > logit(0.25)) ~ 2 %  ->  per-class tail 0.02/nc
+    import math
+    from statistics import NormalDist
+
+    mu = math.log(0.25 / 0.75) - 1.5 * NormalDist().inv_cdf(1 - 0.02 / nc) if args.regime == "typical" else 0.0
+    pitch = (64 + nc + 3) // 4 * 4
+    lv = L.HeadLevels()
+    keep = []
+    for i, (h, w) in enumerate(hw):
+        t = torch.zeros(B, h, w, pitch)
+        t[..., :64] = torch.randn(B, h, w, 64, generator=g) * 2.0
+        t[..., 64:64 + nc] = torch.randn(B, h, w, nc, generator=g) * 1.5 + mu
+        t = t.to(dev)
+        keep.append(t)
+        lv.data[i], lv.h[i], lv.w[i], lv.stride[i] = t.data_ptr(), h, w, float(640 // h)
+    lv.num_levels, lv.batch, lv.nc, lv.pitch = 3, B, nc, pitch
+    cap = A
+    box, score = torch.zeros(B, cap, 4, device=dev), torch.zeros(B, cap, device=dev)
+    cls, pos = torch.zeros(B, cap, dtype=torch.int32, device=dev), torch.zeros(B, cap, dtype=torch.int32, device=dev)
+    count = torch.zeros(B, dtype=torch.int32, device=dev)
+    keys = torch.zeros(B * lib.dbl_nms_sort_capacity(cap), dtype=torch.int64, device=dev)
+    rows, out_pos, out_count = torch.zeros(B, 300, 6, device=dev), torch.zeros(B, 300, dtype=torch.int32, device=dev), torch.zeros(B, dtype=torch.int32, device=dev)
+    cand = L.Candidates(box.data_ptr(), score.data_ptr(), cls.data_ptr(), pos.data_ptr(), count.data_ptr(), cap, B)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        L.check(lib.dbl_decode_filter(C.byref(lv), C.c_float(conf), 0, None, 0, C.byref(cand), st), "dbl_decode_filter")
+        L.check(lib.dbl_nms(C.byref(cand), C.c_float(0.7), 0, C.c_float(7680.0), 30000, 300, keys.data_ptr(), rows.data_ptr(), out_pos.data_ptr(),
+                            out_count.data_ptr(), st), "dbl_nms")
+
+    n0 = lib.dbl_launch_count()
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    kps = (lib.dbl_launch_count() - n0) // max(3, args.warmup)
+    ncand = count.clone()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_f = t_n = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    for _ in range(5):  # the two kernels separately
+        ev[0].record()
+        lib.dbl_decode_filter(C.byref(lv), C.c_float(conf), 0, None, 0, C.byref(cand), st)
+        ev[1].record()
+        lib.dbl_nms(C.byref(cand), C.c_float(0.7), 0, C.c_float(7680.0), 30000, 300, keys.data_ptr(), rows.data_ptr(), out_pos.data_ptr(), out_count.data_ptr(), st)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_f += ev[0].elapsed_time(ev[1]) / 5
+        t_n += ev[1].elapsed_time(ev[2]) / 5
+    peaks = load_peaks()
+    in_bytes = B * A * (64 + nc) * 4
+    total_cand = int(ncand.sum())
+    emit({"metric": metric_name(args), "value": round(total_cand / (ms * 1e-3), 1), "unit": "candidates/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+          "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"Detect decode + NMS microbench (BASELINE config 2): head logits ({B}, {64 + nc}, {A}) fp32, {args.regime} regime (conf {conf}, iou 0.7, max_det 300)",
+                     "candidates_per_image": {"min": int(ncand.min()), "mean": round(total_cand / B, 1), "max": int(ncand.max())},
+                     "kept_per_image_mean": round(float(out_count.float().mean()), 1), "l2": f"logits {in_bytes / 1e6:.0f} MB/step > 126 MB L2"},
+          "images_per_sec": round(B / (ms * 1e-3), 1), "gpu_launches": int(kps * args.steps),
+          "roofline": {"kernel": "decode_filter", "bound": "hbm", "achieved": round(in_bytes / (t_f * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": round(in_bytes / (t_f * 1e-3) / 1e9 / peaks["hbm_gbs"], 4), "traffic": None, "avg_launch_us": round(t_f * 1e3, 1),
+                       "algorithmic_bytes_per_launch": in_bytes, "peak_source": peaks["source"]},
+          "nms": {"ms": round(t_n, 4), "candidates_per_sec": round(total_cand / (t_n * 1e-3), 1), "note": "sort + greedy suppression: O(n * kept) ALU / latency bound, reported in ms and candidates/s, not as a roofline fraction (SURVEY.md §8d)"}})
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     global _STDOUT
     _STDOUT = os.fdopen(os.dup(1), "w")
@@ -166,11 +328,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="model", choices=["model", "decode_nms"])
+    ap.add_argument("--regime", default="typical", choices=["typical", "dense"])
     ap.add_argument("--scale", default="n")
     ap.add_argument("--nc", type=int, default=80)
     ap.add_argument("--imgsz", type=int, default=640)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--conf", type=float, default=0.25)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: e2e leg without the final NCCL gather (N > 1)")
     ap.add_argument("--inflight", type=int, default=2, help="whole 64-image steps in flight per GPU (engine replicas on their own streams)")
     ap.add_argument("--kernel-table", default="", help="write the per-launch timing table (json) here")
     ap.add_argument("--quick", action="store_true", help="device-resident leg only (for runs under ncu): prints a reduced line, never a bench value")
@@ -182,17 +349,23 @@ def main():
     import torch.distributed as dist
 
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.workload == "decode_nms":
+        if rank == 0:
+            run_decode_nms(args, dev)
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from yolo_dbl_b200 import DBLBackend, _lib, synth_images
+    from yolo_dbl_b200 import DBLBackend
     from yolo_dbl_b200.engine import DBLEngine
+    from yolo_dbl_b200.parallel import DetectionGatherer
 
+    NMS = nms_args(args)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    dev = torch.device("cuda", local)
     model = DBLBackend.synthetic(args.scale, args.nc, seed=0, device=dev)
     eng: DBLEngine = model.engine(args.batch, args.imgsz, args.imgsz)
-    small = synth_images(8, args.imgsz, args.imgsz, seed=100 + rank)  # tile 8 distinct images to the batch (CPU synthesis is slow)
-    x_host = small.repeat((args.batch + 7) // 8, 1, 1, 1)[: args.batch].contiguous().pin_memory()
+    _, x_host = bench_images(args, rank)
+    x_host = x_host.pin_memory()
     eng.set_input(x_host.to(dev))
     key = eng.post_key(**NMS)
 
@@ -225,15 +398,16 @@ def main():
     side = [torch.cuda.Stream(device=dev) for _ in range(P)]
     step = lambda: eng.detect(None, **NMS)  # noqa: E731
 
-    def run_steps(k):
-        main = torch.cuda.current_stream(dev)
+    def run_steps(k, group=None):
+        group = group or engs
+        main_s = torch.cuda.current_stream(dev)
         for s in side:
-            s.wait_stream(main)
+            s.wait_stream(main_s)
         for i in range(k):
-            with torch.cuda.stream(side[i % P]):
-                engs[i % P].detect(None, **NMS)
+            with torch.cuda.stream(side[i % len(group)]):
+                group[i % len(group)].detect(None, **NMS)
         for s in side:
-            main.wait_stream(s)
+            main_s.wait_stream(s)
 
     clk = ClockSampler(local) if rank == 0 and not args.quick else None  # samples SM clocks / throttle reasons every 100 ms until the e2e legs are done
     run_steps(max(warmup, P))
@@ -244,46 +418,86 @@ def main():
 
     if args.quick:
         if rank == 0:
-            emit({"metric": METRIC, "quick": True, "value": round(value, 1), "ms_per_step": round(ms_total / steps, 4), "gpu_launches": launches})
+            emit({"metric": metric_name(args), "quick": True, "value": round(value, 1), "ms_per_step": round(ms_total / steps, 4), "gpu_launches": launches})
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # latency of ONE step on an otherwise idle GPU (one replica, nothing else in flight): what a caller of predict() waits for
+    run_steps(3, [eng])
+    lat = sorted(timed(lambda: run_steps(1, [eng]), 1) for _ in range(7))[3]
+
     # ---- end to end through the public API: pinned host batches -> H2D -> predict -> D2H of the detections, every step.
     # Image sources reach the reference as uint8 and are scaled on the device (engine/predictor.py:116-134); the same
     # here: uint8 NCHW crosses PCIe, the /255 is fused into the stem kernel.  detect_stream() overlaps the copy of batch
-    # i+1 with the compute of batch i (the reference's predict(stream=True) generator).
-    out_rows = torch.empty(args.batch, NMS["max_det"], 6, pin_memory=True)
-    out_cnt = torch.empty(args.batch, dtype=torch.int32, pin_memory=True)
+    # i+1 with the compute of batch i (the reference's predict(stream=True) generator).  With N > 1 the path's one collective, the
+    # final gather of the fixed-capacity detections, runs every step: ONE packed all-gather into preallocated, double-buffered
+    # storage; the host reads step i's gathered result while step i+1 is already running (one step of slack between the ranks).
     x_u8 = [(x_host * 255.0).round().to(torch.uint8).pin_memory() for _ in range(2)]
-
-    from yolo_dbl_b200.parallel import gather_detections
-
     d2h = torch.cuda.Stream(device=dev)
+    use_gather = world > 1 and not args.no_gather
 
-    def e2e_run(k, src):
-        n = 0
-        for rows, counts, ev in model.detect_stream((src[i & 1] for i in range(k)), with_event=True, in_flight=P, **NMS):
-            d2h.wait_event(ev)  # this batch's result is complete; the next batch is already queued on the compute stream
-            with torch.cuda.stream(d2h):
-                if world > 1:  # the path's one collective: final gather of the fixed-capacity detections (NCCL all-gather)
-                    g_rows, g_cnt = gather_detections(rows, counts, args.batch * world)
-                    rows, counts = g_rows[rank * args.batch:(rank + 1) * args.batch], g_cnt[rank * args.batch:(rank + 1) * args.batch]
-                out_rows.copy_(rows, non_blocking=True)
-                out_cnt.copy_(counts, non_blocking=True)
-            d2h.synchronize()  # the caller reads the result on the host every step
-            n += 1
-        return n
+    def make_e2e(batch, mdl):
+        gat = DetectionGatherer(batch, NMS["max_det"], dev, slots=3) if use_gather else None
+        n_img = batch * world if use_gather else batch
+        out_rows = [torch.empty(n_img, NMS["max_det"], 6).pin_memory() for _ in range(3)]
+        out_cnt = [torch.empty(n_img, dtype=torch.int32).pin_memory() for _ in range(3)]
+        state = {"det": 0}
 
+        def run(k, src):
+            pending = []  # (event, slot): results whose D2H copy has been queued but not yet read by the host
+            n = 0
+            for rows, counts, ev in mdl.detect_stream((src[i & 1] for i in range(k)), with_event=True, in_flight=P, **NMS):
+                slot = n % 3
+                d2h.wait_event(ev)  # this batch's result is complete; the next batch is already queued on the compute stream
+                with torch.cuda.stream(d2h):
+                    if gat is not None:
+                        rows, counts = gat.gather(rows, counts, slot)
+                    out_rows[slot].copy_(rows, non_blocking=True)
+                    out_cnt[slot].copy_(counts, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(d2h)
+                pending.append((done, slot))
+                if len(pending) > 1:  # the host reads step i-1's detections while step i's gather/copy is in flight
+                    e, s = pending.pop(0)
+                    e.synchronize()
+                    state["det"] = int(out_cnt[s][: batch].sum()) if gat is None else int(out_cnt[s][rank * batch:(rank + 1) * batch].sum())
+                n += 1
+            for e, s in pending:
+                e.synchronize()
+                state["det"] = int(out_cnt[s][: batch].sum()) if gat is None else int(out_cnt[s][rank * batch:(rank + 1) * batch].sum())
+            return n
+
+        return run, state, out_rows, out_cnt
+
+    e2e_run, e2e_state, out_rows, out_cnt = make_e2e(args.batch, model)
     e2e_steps = max(3, steps)
     e2e_run(3, x_u8)
     e2e_ms = timed(lambda: e2e_run(e2e_steps, x_u8), 1)
     e2e_value = args.batch * world * e2e_steps / (e2e_ms * 1e-3)
-    detections = int(out_cnt.sum())
+    detections = e2e_state["det"]
     x_f32 = [x_host, x_host.clone().pin_memory()]
     e2e_run(2, x_f32)
     e2e_f32_ms = timed(lambda: e2e_run(e2e_steps, x_f32), 1)
     e2e_f32_value = args.batch * world * e2e_steps / (e2e_f32_ms * 1e-3)
+
+    # ---- strong scaling (N > 1): BASELINE's "batch 64 sharded across 1/2/4/8 B200" -- the SAME 64 images, 64/N per GPU, gather included
+    strong = None
+    if world > 1 and not args.no_strong and args.batch % world == 0:
+        sb = args.batch // world
+        s_engs = [model.engine(sb, args.imgsz, args.imgsz, replica=r) for r in range(P)]
+        for e in s_engs:
+            e.set_input(x_host[:sb].to(dev))
+        run_steps(max(warmup, P), s_engs)
+        s_ms = timed(lambda: run_steps(steps, s_engs), 1)
+        xs_u8 = [x_u8[0][:sb].clone().pin_memory(), x_u8[1][:sb].clone().pin_memory()]
+        s_run, _, _, _ = make_e2e(sb, model)
+        s_run(3, xs_u8)
+        s_e2e_ms = timed(lambda: s_run(e2e_steps, xs_u8), 1)
+        strong = {"scaling": "strong", "global_batch": args.batch, "per_gpu_batch": sb, "value": round(args.batch * steps / (s_ms * 1e-3), 1),
+                  "ms_per_step": round(s_ms / steps, 4), "e2e": {"value": round(args.batch * e2e_steps / (s_e2e_ms * 1e-3), 1), "ms_per_step": round(s_e2e_ms / e2e_steps, 4),
+                                                                 "gather": "one packed NCCL all-gather per step" if use_gather else "off"},
+                  "unit": "images/s", "note": "the same 64-image global batch sharded by image; with 8 images per GPU a step is ~0.5 ms of small-grid kernels"}
 
     if clk is not None:  # keep the GPU under the same load until nvidia-smi has a handful of samples (the timed legs last < 0.5 s)
         t_end = time.perf_counter() + 1.0
@@ -298,47 +512,36 @@ def main():
     if rank == 0:
         rows = eng.profile_ops(reps=5, post_key=key)
         table = kernel_table(rows, peaks)
-        top = table[0]  # the kernel (family) with the largest share of the step; per-launch averages below
-        t_tensor, t_hbm = top["flops"] / (peaks["bf16_tflops_sustained"] * 1e12), top["bytes"] / (peaks["hbm_gbs"] * 1e9)
-        bound = "tensor" if t_tensor > t_hbm else "hbm"
-        ach, peak, unit = (top["tflops"], peaks["bf16_tflops_sustained"], "TFLOP/s") if bound == "tensor" else (top["gbs"], peaks["hbm_gbs"], "GB/s")
-        traffic = None  # DRAM bytes per launch from the committed ncu capture of the same command (profiles/r01_ncu_traffic.json)
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top["kern"], {}).get("dram_bytes_per_launch")
-        n = max(1, top["launches"])
-        roof = {"kernel": top["kern"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
-                "traffic": traffic, "launches_per_step": top["launches"], "share_of_step": round(top["share"], 3),
-                "avg_launch_us": round(top["ms"] * 1e3 / n, 2), "algorithmic_bytes_per_launch": round(top["bytes"] / n),
-                "algorithmic_flops_per_launch": round(top["flops"] / n), "peak_source": peaks["source"],
-                "tensor_frac": round(top["tflops"] / peaks["bf16_tflops_sustained"], 4), "hbm_frac": round(top["gbs"] / peaks["hbm_gbs"], 4),
-                "note": "achieved = sum of algorithmic bytes (or flops) of this kernel's launches in one step / sum of their CUDA-event times; "
-                        "per-launch rows: --kernel-table"}
+        roof = roofline_block(table, peaks)
         if args.kernel_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             json.dump({"families": table, "launches": rows, "peaks": peaks}, open(args.kernel_table, "w"), indent=1)
 
-    # ---- CPU baseline (rank 0, N == 1 only): the oracle port on all host threads, bounded sample
-    cpu = None
+    # ---- CPU baseline + parity check (rank 0, N == 1 only): the oracle port on all host threads, bounded sample
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, ms, cores = cpu_port_run(args.scale, args.nc, args.imgsz, 64, 6, 1)
+        parity = parity_check(model, eng, x_host, args)
+        n_cpu_steps = 6 if args.scale == "n" and args.imgsz <= 640 else 1
+        ips, ms, cores = cpu_port_run(args, min(args.batch, 64), n_cpu_steps, 1)
         cpu = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"384 images (6 steps x 64 = the full {args.batch}-image step) after 1 warm-up step, ~10 s of CPU work; oracle port: "
-                         "torch CPU fp32 forward + C NMS on all host threads"}
+               "sample": f"{n_cpu_steps} steps x {min(args.batch, 64)} images (the full step) after 1 warm-up step, ~10-30 s of CPU work; oracle port: "
+                         "torch CPU fp32 forward + C NMS on all host threads (0.93x the speed of the reference's own code, BASELINE.md)"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": metric_name(args), "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": dict(config_dict(args, world), steps_in_flight=P), "clocks": clocks,
+            "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": x_u8[0].numel(),
-                    "d2h_bytes_per_step": out_rows.numel() * 4 + out_cnt.numel() * 4, "ms_per_step": round(e2e_ms / e2e_steps, 4),
+                    "d2h_bytes_per_step": out_rows[0].numel() * 4 + out_cnt[0].numel() * 4, "ms_per_step": round(e2e_ms / e2e_steps, 4),
                     "input": "uint8 NCHW in pinned host memory (image source; /255 fused into the stem kernel), copy of batch i+1 "
-                             "overlapped with compute of batch i, detections read back to pinned host memory every step",
+                             "overlapped with compute of batch i, detections (gathered over all ranks when N > 1) read back to pinned host memory every step",
+                    "gather": ("one packed NCCL all-gather per step, double-buffered" if use_gather else ("disabled (--no-gather)" if world > 1 else "n/a (N = 1)")),
                     "fp32_input": {"value": round(e2e_f32_value, 1), "h2d_bytes_per_step": x_host.numel() * 4,
                                    "ms_per_step": round(e2e_f32_ms / e2e_steps, 4)}},
             "gpu_launches": launches, "kernels_per_step": kps, "detections_per_step": detections,
-            "roofline": roof, "cpu_baseline": cpu,
+            "latency_single_step_ms": round(lat, 4), "strong": strong,
+            "roofline": roof, "cpu_baseline": cpu, "parity": parity,
             "kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in f.items() if k in ("kern", "launches", "ms", "share", "gbs", "tflops", "hbm_frac", "tensor_frac")}
                         for f in table[:8]],
         }

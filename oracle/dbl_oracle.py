@@ -314,8 +314,37 @@ def detect_decode(x_cat: Tensor, hw, strides, reg_max=16) -> Tensor:
 # --------------------------------------------------------------------------------------
 # whole graph  (BaseModel._predict_once nn/tasks.py:145-172)
 # --------------------------------------------------------------------------------------
-def forward(sd: Dict[str, Tensor], x: Tensor, scale: str = "n", collect: bool = False):
-    """Returns (y, head_feats[, per-layer outputs]).  x: (B,3,H,W) fp32 in 0..1, H,W % 32 == 0."""
+# bf16 emulation (tests only): with ROUND_BF16 set, every leaf block's output is rounded to bf16 -- the reference's own network run
+# with bf16 activation storage.  |forward(round_bf16=True) - forward()| is the drift ANY bf16-activation implementation shows
+# on these weights at this shape; the GPU tests derive their free-running bounds from it instead of stating a constant.
+ROUND_BF16 = False
+
+
+def _rounded(fn):
+    def wrapped(*a, **k):
+        o = fn(*a, **k)
+        return o.to(torch.bfloat16).float() if (ROUND_BF16 and isinstance(o, Tensor)) else o
+
+    wrapped.__doc__, wrapped.__name__ = fn.__doc__, fn.__name__
+    return wrapped
+
+
+conv_bn_silu, dsconv, bottleneck, ds_bottleneck = _rounded(conv_bn_silu), _rounded(dsconv), _rounded(bottleneck), _rounded(ds_bottleneck)
+lskblock, c3ah, dysample, downsample_conv, fullpad = _rounded(lskblock), _rounded(c3ah), _rounded(dysample), _rounded(downsample_conv), _rounded(fullpad)
+
+
+def forward(sd: Dict[str, Tensor], x: Tensor, scale: str = "n", collect: bool = False, round_bf16: bool = False):
+    """Returns (y, head_feats[, per-layer outputs]).  x: (B,3,H,W) fp32 in 0..1, H,W % 32 == 0.
+    round_bf16: emulate bf16 activation storage (see ROUND_BF16); the head's last 1x1 convs and the decode stay fp32."""
+    global ROUND_BF16
+    ROUND_BF16 = bool(round_bf16)
+    try:
+        return _forward(sd, x.to(torch.bfloat16).float() if round_bf16 else x, scale, collect)
+    finally:
+        ROUND_BF16 = False
+
+
+def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool):
     layers = build_layers(scale)
     outs: List[Tensor] = []
     with torch.inference_mode():

@@ -3,9 +3,9 @@
     python oracle/make_golden_r2.py
 
   * ``fwd_n_nc80_640.npz``            the BENCHMARKED instantiation: n-scale, nc=80, bench weights (recipe seed 0 + BN calibration
-                                      table), first two images of bench.py's batch (synth_images(8, 640, 640, seed=100)):
-                                      y of DetectionModel.fuse().eval() (image 0 complete, image 1 box rows + best score/class; every 4th anchor
-                                      of the UNFUSED model's y for image 0, which is what the oracle's explicit BatchNorm reproduces) and
+                                      table), images 2 and 3 of bench.py's batch (synth_images(8, 640, 640, seed=100)):
+                                      y of DetectionModel.fuse().eval() (image 2 complete = ya, image 3 box rows + best score/class = yb_*;
+                                      every 4th anchor of the UNFUSED model's y for image 2, which the oracle's explicit BatchNorm reproduces) and
                                       ops.non_max_suppression(y, 0.25, 0.7) rows for both images.
   * ``nms_labels_{single,multi}.npz`` ops.non_max_suppression(..., labels=lb) (validator path, utils/ops.py:255-261)
   * ``match_{typical,crowded,empty}.npz``  utils.metrics.box_iou + DetectionValidator.match_predictions (engine/validator.py:222-260)
@@ -34,16 +34,16 @@ def fwd_nc80():
     from ultralytics.utils import ops
 
     m, shapes, sd = build_reference("n", 80, 0)
-    x = synth_images(8, 640, 640, seed=100)[:2]
+    x = synth_images(8, 640, 640, seed=100)[2:4]  # images 2 and 3 of the bench batch: the well-conditioned ones (oracle/select_bench_images.py)
     with torch.inference_mode():
         y_unfused = m(x)[0].clone()
         m.fuse(verbose=False)
         y, feats = m(x)
         out = ops.non_max_suppression(y.clone(), 0.25, 0.7, max_det=300, max_time_img=1e9)
     best, cls = y[1, 4:].max(0)
-    np.savez_compressed(os.path.join(OUT, "fwd_n_nc80_640.npz"), y0=y[0].numpy(), y0_unfused_s4=y_unfused[0, :, ::4].numpy(), y1_box=y[1, :4].numpy(), y1_best=best.numpy(),
-                        y1_cls=cls.numpy().astype(np.int16), rows=torch.cat(out).numpy(), counts=np.array([o.shape[0] for o in out]),
-                        meta=np.array(json.dumps(dict(scale="n", nc=80, wseed=0, images="synth_images(8,640,640,seed=100)[:2]",
+    np.savez_compressed(os.path.join(OUT, "fwd_n_nc80_640.npz"), ya=y[0].numpy(), ya_unfused_s4=y_unfused[0, :, ::4].numpy(), yb_box=y[1, :4].numpy(), yb_best=best.numpy(),
+                        yb_cls=cls.numpy().astype(np.int16), rows=torch.cat(out).numpy(), counts=np.array([o.shape[0] for o in out]),
+                        meta=np.array(json.dumps(dict(scale="n", nc=80, wseed=0, images="synth_images(8,640,640,seed=100)[2:4]",
                                                       conf=0.25, iou=0.7))))
     print("fwd_n_nc80_640: kept", [o.shape[0] for o in out], "cand", [(y[i, 4:].amax(0) > 0.25).sum().item() for i in range(2)])
 

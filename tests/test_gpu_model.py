@@ -277,35 +277,13 @@ def test_letterbox_kernel_bit_exact_vs_oracle_and_reference_golden():
     sizes = [(150, 260), (50, 37), (96, 128), (97, 131), (301, 299), (480, 640), (1080, 1920), (17, 400), (3, 5)]
     imgs = [_synth_bgr(h, w, 100 + i) for i, (h, w) in enumerate(sizes)]
     for shape in [(96, 128), (160, 160), (640, 640)]:
-        got = m.preprocess(imgs, shape).cpu().numpy()
+        got = m.preprocess(imgs, shape).cpu().numpy()  # ragged batch -> full-size letterbox (auto off), like the reference
         want = LB.preprocess(imgs, shape)
         assert got.shape == want.shape and got.dtype == np.uint8
         np.testing.assert_array_equal(got, want)
-    for name in ["down_wide", "up_tall", "same", "odd", "square_down", "up2x", "down2x", "up_both", "thin"]:
+    for name in ["down_wide", "up_tall", "same", "odd", "square_down", "up2x", "down2x", "up_both", "thin", "auto_wide", "auto_tall"]:
         g = np.load(os.path.join(GOLDEN, f"letterbox_{name}.npz"))
         shape = tuple(int(v) for v in g["shape"])
-        got = m.preprocess([g["img"]], shape).cpu().numpy()[0]
+        got = m.preprocess([g["img"]], shape, auto=name.startswith("auto_")).cpu().numpy()[0]
         ref = np.ascontiguousarray(g["out"][..., ::-1].transpose(2, 0, 1))
         np.testing.assert_array_equal(got, ref)
-
-
-def test_predict_on_image_sources_scales_boxes_back_like_the_reference():
-    """YOLO.predict(list of HWC BGR uint8 images): GPU letterbox -> detect -> scale_boxes, vs the same steps through the oracle."""
-    import letterbox_oracle as LB
-
-    yolo = YOLO("yolov13n_DBL.yaml", nc=3)
-    imgs = [_synth_bgr(h, w, 7 + i) for i, (h, w) in enumerate([(240, 320), (500, 375), (128, 96)])]
-    res = yolo.predict(imgs, conf=0.05, imgsz=(128, 160))
-    x = torch.from_numpy(LB.preprocess(imgs, (128, 160)))
-    rows, counts = yolo.model.detect(x.pin_memory(), conf=0.05, iou=0.7)
-    rows, counts = rows.cpu().numpy(), counts.tolist()
-    assert len(res) == 3 and sum(counts) > 0
-    for i, (r, im) in enumerate(zip(res, imgs)):
-        assert r.orig_shape == im.shape[:2] and len(r) == counts[i]
-        want = rows[i, : counts[i]].copy()
-        want[:, :4] = LB.scale_boxes((128, 160), want[:, :4], im.shape[:2])
-        np.testing.assert_allclose(r.boxes.data.cpu().numpy(), want, rtol=1e-6, atol=1e-4)
-        b = r.boxes.xyxy.cpu().numpy()
-        assert (b[:, [0, 2]] >= 0).all() and (b[:, [0, 2]] <= im.shape[1]).all() and (b[:, [1, 3]] <= im.shape[0]).all()
-    one = yolo.predict(imgs[0], conf=0.05, imgsz=(128, 160))
-    assert len(one) == 1 and torch.equal(one[0].boxes.data, res[0].boxes.data)

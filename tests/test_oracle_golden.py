@@ -189,17 +189,17 @@ def test_oracle_forward_nc80_640_matches_reference_on_the_benchmarked_weights():
     g = _load("fwd_n_nc80_640.npz")
     spec = resolve(None, "n", 80)
     sd = synth_state_dict(param_shapes(spec), 0)
-    x = synth_images(8, 640, 640, seed=100)[:2]
+    x = synth_images(8, 640, 640, seed=100)[2:4]
     y, _ = O.forward(sd, x, "n")
     # the oracle applies BatchNorm explicitly like the UNFUSED reference: same bound as test_forward_matches_reference_640
-    torch.testing.assert_close(y[0, :, ::4], torch.from_numpy(g["y0_unfused_s4"]), rtol=2e-4, atol=5e-3)
+    torch.testing.assert_close(y[0, :, ::4], torch.from_numpy(g["ya_unfused_s4"]), rtol=2e-4, atol=5e-3)
     # against the fused model (what predict runs) the fp32 re-association of fuse() shows: <= 0.25 px / 5e-3 in score
-    d = (y[0] - torch.from_numpy(g["y0"])).abs()
+    d = (y[0] - torch.from_numpy(g["ya"])).abs()
     assert float(d[:4].max()) <= 0.25 and float(d[4:].max()) <= 5e-3, (float(d[:4].max()), float(d[4:].max()))
-    d1 = (y[1, :4] - torch.from_numpy(g["y1_box"])).abs()
+    d1 = (y[1, :4] - torch.from_numpy(g["yb_box"])).abs()
     best, cls = y[1, 4:].max(0)
-    assert float(d1.max()) <= 0.25 and float((best - torch.from_numpy(g["y1_best"])).abs().max()) <= 5e-3
-    rows, _ = N.non_max_suppression(np.stack([g["y0"], y[1].numpy()]), 0.25, 0.7, max_det=300)
+    assert float(d1.max()) <= 0.25 and float((best - torch.from_numpy(g["yb_best"])).abs().max()) <= 5e-3
+    rows, _ = N.non_max_suppression(np.stack([g["ya"], y[1].numpy()]), 0.25, 0.7, max_det=300)
     c = g["counts"].tolist()
     assert len(rows[0]) == c[0] and rows[0].tobytes() == g["rows"][: c[0]].tobytes()  # image 0: the reference's own y -> identical rows
     assert abs(len(rows[1]) - c[1]) <= 2  # image 1: the oracle's y (fp32 noise may flip a box at the threshold)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import nms_oracle as N
-from yolo_dbl_b200.parallel import detect_sharded, gather_detections, max_shard, shard_range
+from yolo_dbl_b200.parallel import DetectionGatherer, detect_sharded, gather_detections, max_shard, shard_range
 
 MAX_DET = 20
 
@@ -55,6 +55,17 @@ def _worker(rank, world, port, n_total, q):
         lo, hi = shard_range(n_total, rank, world)
         r2, c2 = gather_detections(*_detect_cpu(pred[lo:hi]), n_total)
         assert torch.equal(rows, r2) and torch.equal(counts, c2)
+        # the persistent gatherer bench.py / serving loops keep: preallocated, packed, double-buffered -- three steps over two slots,
+        # step 1 with different data so a stale slot would show
+        g = DetectionGatherer(hi - lo, MAX_DET, "cpu", slots=2, n_total=n_total)
+        mine = _detect_cpu(pred[lo:hi])
+        other = (mine[0] * 0.5, mine[1])
+        packed = [g.gather_packed(*(other if i == 1 else mine), slot=i % 2).clone() for i in range(3)]
+        for i in (0, 2):
+            r3, c3 = g.unpack(packed[i])
+            assert torch.equal(r3, rows) and torch.equal(c3, counts)
+        r3, c3 = g.unpack(packed[1])
+        assert torch.equal(r3, rows * 0.5) and torch.equal(c3, counts)
         q.put((rank, rows.numpy(), counts.numpy()))
     finally:
         dist.destroy_process_group()

@@ -15,6 +15,7 @@ namespace dbl {
 constexpr int HG_MAX_E = 16;
 constexpr int HG_CTX_SPLIT = 32;   // token splits for the mean/max context
 constexpr int HG_TOK_BLOCK = 128;  // tokens per block in the per-token kernels
+constexpr int HG_EDGE_SPLIT = 32;  // token slices per image in the A^T X kernel: short, latency-bound loops -> more CTAs and more loads in flight
 
 struct HgLayout {  // float offsets into the caller's workspace
     size_t ctx_part, P, cvec, logits, stat_part, stats, Q, He, total;
@@ -31,7 +32,7 @@ static HgLayout hg_layout(int B, int N, int D, int E) {
     L.stat_part = o, o += (size_t)B * L.nblk * E * 2;
     L.stats = o, o += (size_t)B * E * 2;
     L.Q = o, o += (size_t)B * E * D;
-    L.He = o, o += (size_t)B * E * D;
+    L.He = o, o += (size_t)B * HG_EDGE_SPLIT * E * D;  // per-slice partials, reduced in a fixed order (bitwise reproducible)
     L.total = o;
     return L;
 }
@@ -168,7 +169,6 @@ __global__ void __launch_bounds__(HG_TOK_BLOCK) hg_logits_kernel(const __nv_bflo
 }
 
 // K4a: softmax normalisation in place + partial He = A^T X over a token slice.  grid (HG_EDGE_SPLIT, B), block 256.
-constexpr int HG_EDGE_SPLIT = 32;  // token slices per image: short, latency-bound loops -> more CTAs and more loads in flight
 __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ logits,
                                                                const float* __restrict__ stat_part, float* __restrict__ He, int N, int D,
                                                                int E, int nblk, int pitch) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) hg_edges_partial_kernel(const __nv_bfloat
     for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
         float s = 0.f;
         for (int rr = 0; rr < R; ++rr) s += red[(size_t)rr * E * D + i];
-        atomicAdd(He + (size_t)b * E * D + i, s);
+        He[((size_t)b * HG_EDGE_SPLIT + blockIdx.x) * E * D + i] = s;  // no atomics: the final kernel adds the slices in order
     }
 }
 
@@ -232,7 +232,12 @@ __global__ void __launch_bounds__(1024) hg_edges_final_kernel(const float* __res
     const int b = blockIdx.x, E = wt.num_edges;
     float* he = sm;
     float* he2 = sm + E * D;
-    for (int i = threadIdx.x; i < E * D; i += blockDim.x) he[i] = He[(size_t)b * E * D + i];
+    for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < HG_EDGE_SPLIT; ++k) s += He[((size_t)b * HG_EDGE_SPLIT + k) * E * D + i];
+        he[i] = s;
+    }
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x & 31, nwarp = blockDim.x / 32;
     for (int row = warp; row < E * D; row += nwarp) {  // He2[e,j] = GELU(sum_d He[e,d] We[j,d] + be[j])
@@ -323,8 +328,6 @@ extern "C" int dbl_hypergraph(const dbl_tensor* x, const dbl_hypergraph_weights*
                                                                  x->pitch);
     const int R = 256 / D;
     const size_t sm4 = (2 * HG_MAX_E + (size_t)R * E * D) * sizeof(float);
-    cudaError_t me = cudaMemsetAsync(f + L.He, 0, (size_t)B * E * D * sizeof(float), st);
-    DBL_REQUIRE(me == cudaSuccess, DBL_E_CUDA, "dbl_hypergraph: memset failed: %s", cudaGetErrorString(me));
     launch_k(hg_edges_partial_kernel, dim3(HG_EDGE_SPLIT, B), 256, sm4, st, xp, f + L.logits, f + L.stat_part, f + L.He, N, D, E, L.nblk, x->pitch);
     launch_k(hg_edges_final_kernel, B, 1024, (size_t)2 * E * D * sizeof(float), st, f + L.He, *wt, f + L.Q, D);
     launch_k(hg_nodes_kernel, dim3(L.nblk, B), HG_TOK_BLOCK, ((size_t)E * D + D) * sizeof(float), st, 

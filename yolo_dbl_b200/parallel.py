@@ -29,8 +29,52 @@ def max_shard(n: int, world: int) -> int:
     return (n + world - 1) // world
 
 
+class DetectionGatherer:
+    """The path's one collective, made cheap: ONE packed all-gather per step into preallocated storage.
+
+    Per rank the message is ``[cap * max_det * 6 floats of rows | cap int32 counts]`` (cap = largest shard), so a step costs one
+    copy kernel pair + one ``all_gather_into_tensor`` -- no per-step allocation, zero-fill, ``arange`` / ``cat`` / ``index_select``.
+    ``slots`` independent send/receive buffers let the gather of step i overlap step i+1 (the caller reads slot i one step later).
+    """
+
+    def __init__(self, b_local: int, max_det: int, device, slots: int = 2, n_total: Optional[int] = None, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = int(n_total) if n_total is not None else b_local * self.world
+        self.cap = max_shard(self.n_total, self.world) if n_total is not None else b_local
+        self.max_det, self.R = max_det, self.cap * max_det * 6
+        self.send = [torch.zeros(self.R + self.cap, dtype=torch.float32, device=device) for _ in range(slots)]
+        self.recv = [torch.zeros(self.world, self.R + self.cap, dtype=torch.float32, device=device) for _ in range(slots)]
+        self.even = all(shard_range(self.n_total, r, self.world)[1] - shard_range(self.n_total, r, self.world)[0] == self.cap for r in range(self.world))
+
+    def gather_packed(self, rows: torch.Tensor, counts: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """rows [b, max_det, 6] f32, counts [b] i32 (b <= cap) of this rank -> packed [world, R + cap] on every rank."""
+        b = rows.shape[0]
+        s = self.send[slot]
+        s[: b * self.max_det * 6].copy_(rows.reshape(-1))
+        s[self.R: self.R + b].view(torch.int32).copy_(counts)
+        if self.world == 1:
+            self.recv[slot][0].copy_(s)
+        else:
+            dist.all_gather_into_tensor(self.recv[slot].view(-1), s, group=self.group)
+        return self.recv[slot]
+
+    def unpack(self, packed: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """packed (device or host copy) -> (rows [n_total, max_det, 6], counts [n_total]) in batch order; views when shards are even."""
+        rows = packed[:, : self.R].view(self.world, self.cap, self.max_det, 6)
+        cnt = packed[:, self.R:].view(torch.int32)
+        if self.even:
+            return rows.reshape(self.world * self.cap, self.max_det, 6), cnt.reshape(-1)
+        sizes = [shard_range(self.n_total, r, self.world) for r in range(self.world)]
+        return torch.cat([rows[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)]), torch.cat([cnt[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)])
+
+    def gather(self, rows: torch.Tensor, counts: torch.Tensor, slot: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.unpack(self.gather_packed(rows, counts, slot))
+
+
 def gather_detections(rows: torch.Tensor, counts: torch.Tensor, n_total: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather the per-rank detections into batch order.
+    """All-gather the per-rank detections into batch order (functional form; loops should keep a DetectionGatherer).
 
     rows [B_local, max_det, 6] f32 and counts [B_local] i32 of THIS rank's shard -> rows [n_total, max_det, 6], counts [n_total]
     on every rank.  Shards are padded to the largest shard so one fixed-shape collective serves uneven splits.
@@ -38,21 +82,8 @@ def gather_detections(rows: torch.Tensor, counts: torch.Tensor, n_total: int, gr
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return rows[:n_total], counts[:n_total]
-    cap = max_shard(n_total, world)
-    b, max_det, six = rows.shape
-    pad_rows = rows.new_zeros(cap, max_det, six)
-    pad_cnt = counts.new_zeros(cap)
-    pad_rows[:b], pad_cnt[:b] = rows, counts
-    all_rows = rows.new_empty(world * cap, max_det, six)
-    all_cnt = counts.new_empty(world * cap)
-    dist.all_gather_into_tensor(all_rows, pad_rows, group=group)
-    dist.all_gather_into_tensor(all_cnt, pad_cnt, group=group)
-    keep = []
-    for r in range(world):
-        lo, hi = shard_range(n_total, r, world)
-        keep.append(torch.arange(r * cap, r * cap + (hi - lo), device=rows.device))
-    idx = torch.cat(keep)
-    return all_rows.index_select(0, idx), all_cnt.index_select(0, idx)
+    g = DetectionGatherer(rows.shape[0], rows.shape[1], rows.device, slots=1, n_total=n_total, group=group)
+    return g.gather(rows, counts.to(torch.int32))
 
 
 def detect_sharded(detect: Callable[[torch.Tensor], Tuple[torch.Tensor, torch.Tensor]], images: torch.Tensor, group=None,

@@ -38,7 +38,7 @@ def _init_pos(groups: int = 4, scale: int = 2) -> torch.Tensor:
     return out.view(1, -1, 1, 1)
 
 
-def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=()) -> torch.Tensor:
+def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=(), recipe: str = "calibrated") -> torch.Tensor:
     g = _gen(seed, key)
     shape = tuple(shape)
     leaf = key.rsplit(".", 1)[-1]
@@ -67,6 +67,8 @@ def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=()) -> 
     if parent.endswith(".bn"):
         # small gammas keep SiLU near its linear range: a random deep stack with gamma ~ 1 is chaotic (it amplifies
         # bf16 rounding noise ~1.1x per layer, 50x end to end), which no trained detector is.
+        if recipe == "survey":  # SURVEY.md §8d as written: weight ~ U(.5, 1.5), bias ~ N(0, .1)
+            return uniform(0.5, 1.5) if leaf == "weight" else normal(0.1)
         return uniform(0.2, 0.5) if leaf == "weight" else normal(0.1)
     is_cls_out = ".cv3." in key and parent.endswith(".2")  # Detect.cv3[i][-1]
     is_box_out = ".cv2." in key and parent.endswith(".2") and len(parent.split(".")) == 5  # Detect.cv2[i][-1]
@@ -95,15 +97,24 @@ def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=()) -> 
     raise KeyError(f"synth_tensor: no rule for {key} {shape}")
 
 
-def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, calib="auto") -> Dict[str, torch.Tensor]:
+def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0, calib="auto", recipe: str = "calibrated") -> Dict[str, torch.Tensor]:
     """shapes: {state_dict key: shape}.  Returns fp32 tensors (int64 for num_batches_tracked).
 
     ``calib``: BatchNorm running statistics measured on a seeded calibration batch (the analogue of what training
     would have left in the buffers; without it a random deep stack either dies out or blows up, differently at every
     width/depth).  "auto" loads ``data/bn_calib_c<C0>_nc<nc>_seed<seed>.npz`` when it exists (written by
     ``oracle/calibrate_bn.py``); a dict overrides keys directly; None keeps the recipe's N(0,.1)/U(.5,1.5) statistics.
+    ``recipe="survey"`` is SURVEY.md §8d's parity recipe as written (gamma ~ U(.5,1.5), no calibration): a chaotic stack, used by
+    the teacher-forced per-layer tests only.
     """
-    sd = {k: synth_tensor(k, s, seed, shapes) for k, s in shapes.items()}
+    if recipe not in ("calibrated", "survey"):
+        raise ValueError(recipe)
+    sd = {k: synth_tensor(k, s, seed, shapes, recipe) for k, s in shapes.items()}
+    if recipe == "survey":  # the parity weight recipe of SURVEY.md §8d verbatim: BN gamma ~ U(.5,1.5), N(0,.1)/U(.5,1.5) statistics, cls bias -3
+        for k in sd:
+            if ".cv3." in k and k.endswith(".2.bias"):
+                sd[k] = torch.full_like(sd[k], -3.0)
+        return sd
     if calib == "auto":
         path = calib_path(shapes, seed)
         calib = dict(np_load(path)) if os.path.exists(path) else None
