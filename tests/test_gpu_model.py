@@ -2,12 +2,13 @@
 
 Stated tolerance for the bf16 backbone (north star: "bf16 backbone within a stated tolerance"):
   * teacher-forced, every top-level layer (inputs = the oracle's outputs rounded to bf16): relative L2 error of the
-    layer's output <= 3e-2 (bf16 rounding of every intermediate inside the block, fp32 accumulation); head logits <= 3e-2;
-  * free-running at 640x640 (n scale): every layer <= 5e-2 relative L2; decoded boxes median |d| <= 0.25 px,
-    p99 <= 1.5 px, max <= 6 px; scores p99 <= 1e-2, max <= 5e-2 -- the same size as the drift of the reference run
-    with its activations rounded to bf16 (measured with the oracle: p99 0.2 px / 2e-3, see DESIGN.md);
-  * wider scales (s, l) are held to the teacher-forced bound; their free-running drift is only required to stay
-    finite and <= 0.25 relative L2 because the synthetic s/l weights amplify rounding noise.
+    layer's output <= 2e-2 (bf16 rounding of every intermediate inside the block, fp32 accumulation); head logits <= 2e-2;
+    also run with SURVEY.md §8d's weight recipe exactly as written (BN gamma ~ U(.5, 1.5), uncalibrated);
+  * free-running: every layer's relative L2 error is bounded by a multiple of what bf16 ACTIVATION STORAGE costs the reference
+    itself on the same weights, input and shape -- the oracle run with every block output rounded to bf16
+    (O.forward(round_bf16=True)) against its fp32 run: err_cuda(layer) <= 3 * err_bf16_oracle(layer) + 5e-3.  No constant is
+    invented per scale: a chaotic synthetic stack gets a loose bound exactly as far as the reference's own bf16 run is loose;
+  * decoded outputs at 640x640 (n scale): the bounds in test_full_640_* are MEASURED values x 2 (printed by the test).
 The fp32 post-process on identical inputs is held to 1e-3 / bit-exactness in test_gpu_nms.py.
 """
 import json
@@ -26,17 +27,21 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
+# decoded-output bounds of the n-scale 640x640 free-running case = 2 x the values measured on B200 (printed by the test)
+BOX_MED_640, BOX_P99_640, BOX_MAX_640, SCORE_P99_640, SCORE_MAX_640 = 0.06, 1.0, 4.0, 4e-3, 3e-2
+
 
 def _rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, free_tol=5e-2, forced_tol=3e-2):
+def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, forced_tol=2e-2, recipe="calibrated", free=True):
     spec = resolve(None, scale, nc)
-    sd = synth_state_dict(param_shapes(spec), seed)
+    sd = synth_state_dict(param_shapes(spec), seed, recipe=recipe)
     x = synth_images(b, h, w, xseed)
     eng = DBLEngine(spec, sd, b, h, w, device="cuda:0", conv_impl=conv_impl, use_graph=False, keep_layers=True)
     y_ref, feats_ref, outs_ref = O.forward(sd, x, scale, collect=True)
+    _, _, outs_b16 = O.forward(sd, x, scale, collect=True, round_bf16=True)  # the reference's own cost of bf16 activation storage
     head_ref = torch.cat([f.reshape(b, f.shape[1], -1) for f in feats_ref], 2)
     # --- teacher-forced: each layer on the oracle's inputs
     forced = eng.debug_layers_forced(x.cuda(), outs_ref)
@@ -48,12 +53,13 @@ def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, free_tol=5e-2, f
     print(f"[{scale} {h}x{w} impl={conv_impl}] teacher-forced rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in errs))
     for e, i, kind in errs:
         assert e <= forced_tol, f"teacher-forced layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
-    # --- free-running
+    # --- free-running: bounded by the reference's own bf16 drift at the same layer
     outs = eng.debug_layers(x.cuda())
-    free = [(_rel_l2(o, r), i, spec.layers[i].kind) for i, (o, r) in enumerate(zip(outs, outs_ref)) if o is not None]
-    print(f"[{scale} {h}x{w} impl={conv_impl}] free-running  rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in free))
-    for e, i, kind in free:
-        assert e <= free_tol, f"free-running layer {i} ({kind}) relative L2 error {e:.3g} (conv_impl={conv_impl})"
+    fr = [(_rel_l2(o, r), _rel_l2(q, r), i, spec.layers[i].kind) for i, (o, r, q) in enumerate(zip(outs, outs_ref, outs_b16)) if o is not None]
+    print(f"[{scale} {h}x{w} impl={conv_impl}] free-running  rel-L2 (ours/oracle-bf16):", " ".join(f"{i}:{e:.3g}/{q:.3g}" for e, q, i, _ in fr))
+    for e, q, i, kind in fr:
+        if free:
+            assert e <= 3.0 * q + 5e-3, f"free-running layer {i} ({kind}): error {e:.3g} vs the reference's own bf16 drift {q:.3g} (conv_impl={conv_impl})"
     y, feats = eng.forward(x.cuda())
     torch.cuda.synchronize()
     return eng, sd, x, y.cpu(), y_ref
@@ -69,11 +75,17 @@ def test_layers_n_scale_nc80():
 
 
 def test_layers_s_scale():
-    _check_layers("s", 3, 5, 1, 96, 96, L.IMPL_AUTO, free_tol=0.25)
+    _check_layers("s", 3, 5, 1, 96, 96, L.IMPL_AUTO)
 
 
 def test_layers_l_scale():
-    _check_layers("l", 3, 7, 1, 64, 64, L.IMPL_AUTO, free_tol=0.25)
+    _check_layers("l", 3, 7, 1, 64, 64, L.IMPL_AUTO)
+
+
+def test_layers_survey_recipe_as_written():
+    """SURVEY.md §8d's parity weight recipe verbatim (BN gamma ~ U(.5, 1.5), N(0,.1) / U(.5,1.5) statistics, no calibration table)"""
+    _check_layers("n", 3, 11, 2, 128, 160, L.IMPL_AUTO, recipe="survey")
+    _check_layers("s", 3, 12, 1, 96, 128, L.IMPL_AUTO, recipe="survey")
 
 
 def test_full_640_vs_oracle_and_reference_golden():
@@ -85,8 +97,9 @@ def test_full_640_vs_oracle_and_reference_golden():
         dsc = (y[:, 4:] - ref[:, 4:]).abs().flatten()
         print(f"vs {name}: box median {dbox.median():.3f} p99 {dbox.quantile(0.99):.3f} max {dbox.max():.3f} px | "
               f"score p99 {dsc.quantile(0.99):.4f} max {dsc.max():.4f}")
-        assert float(dbox.median()) <= 0.25 and float(dbox.quantile(0.99)) <= 1.5 and float(dbox.max()) <= 6.0
-        assert float(dsc.quantile(0.99)) <= 1e-2 and float(dsc.max()) <= 5e-2
+        # MEASURED x 2 (B200, round 2)
+        assert float(dbox.median()) <= BOX_MED_640 and float(dbox.quantile(0.99)) <= BOX_P99_640 and float(dbox.max()) <= BOX_MAX_640
+        assert float(dsc.quantile(0.99)) <= SCORE_P99_640 and float(dsc.max()) <= SCORE_MAX_640
     # detections vs the reference's own NMS output: nearly every reference box has a twin (IoU > 0.9, same class)
     rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
     ref_rows = torch.from_numpy(np.load(os.path.join(GOLDEN, "nms_model640_conf0.25.npz"))["rows"])
@@ -225,14 +238,14 @@ def test_config5_1280_dense_nms_through_the_production_engine():
     y = y.clone()
     torch.cuda.synchronize()
     assert tuple(y.shape) == (1, 7, 33600) and bool(torch.isfinite(y).all())
-    # The synthetic weights are calibrated for ~640^2 statistics; at 1280^2 the oracle's own activations grow to |x| ~ 60, so
-    # bf16 rounding noise is amplified like in the wide scales (teacher-forced per-layer error stays <= 2e-2, identical on the
-    # CUDA-core and tensor-core paths: tools/diag_res.py).  Free-running drift is held to the wide-scale bound; what this
-    # config is about -- 33 600 anchors, max_nms truncation, dense NMS -- is checked bit-exactly below.
+    # free-running bound: a multiple of the reference's own bf16 drift on this input (at 1280^2 the synthetic network is in its
+    # high-gain regime, |x| ~ 60: the oracle's bf16 run itself moves); what this config is about -- 33 600 anchors, max_nms
+    # truncation, dense NMS -- is checked bit-exactly below.
     y_ref, _ = O.forward(sd, x, "n")
-    rel = float((y.cpu() - y_ref).norm() / y_ref.norm())
-    print(f"1280^2: rel-L2 of y {rel:.4f}")
-    assert rel <= 0.25
+    y_b16, _ = O.forward(sd, x, "n", round_bf16=True)
+    rel, rel_b16 = _rel_l2(y.cpu(), y_ref), _rel_l2(y_b16, y_ref)
+    print(f"1280^2: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f})")
+    assert rel <= 3.0 * rel_b16 + 5e-3
     for kw in (dict(conf=0.001, iou=0.7), dict(conf=0.001, iou=0.7, multi_label=True)):
         rows, counts, _ = eng.detect(x.cuda(), **kw)
         torch.cuda.synchronize()
@@ -252,9 +265,10 @@ def test_config4_l_scale_production_engine():
     torch.cuda.synchronize()
     y_ref, _ = O.forward(sd, x, "l")
     assert bool(torch.isfinite(y).all())
-    rel = float((y.cpu() - y_ref).norm() / y_ref.norm())
-    print(f"l scale 192x256: rel-L2 of y {rel:.4f}")
-    assert rel <= 0.25  # free-running drift bound used for the wide scales (see module docstring)
+    y_b16, _ = O.forward(sd, x, "l", round_bf16=True)
+    rel, rel_b16 = _rel_l2(y.cpu(), y_ref), _rel_l2(y_b16, y_ref)
+    print(f"l scale 192x256: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f})")
+    assert rel <= 3.0 * rel_b16 + 5e-3
     rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
     want, _ = N.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
     assert counts.tolist() == [len(w) for w in want]
@@ -287,3 +301,32 @@ def test_letterbox_kernel_bit_exact_vs_oracle_and_reference_golden():
         got = m.preprocess([g["img"]], shape, auto=name.startswith("auto_")).cpu().numpy()[0]
         ref = np.ascontiguousarray(g["out"][..., ::-1].transpose(2, 0, 1))
         np.testing.assert_array_equal(got, ref)
+
+
+def test_config4_l_scale_640_batch_and_config5_1280_batch16():
+    """BASELINE configs 4 and 5 at their own shapes: l width/depth at 640x640 (B = 4; the bench runs B = 32 of the same engine
+    shape class) and n at 1280x1280 with B = 16, conf 0.001.  y against the oracle on the distinct images, bounded by the
+    reference's own bf16 drift; detections bit-exact against the oracle's NMS of the CUDA y."""
+    for scale, seed, b, hw, xseed, conf in (("l", 7, 4, 640, 8, 0.25), ("n", 0, 16, 1280, 6, 0.001)):
+        spec = resolve(None, scale, 3)
+        sd = synth_state_dict(param_shapes(spec), seed)
+        small = synth_images(2, hw, hw, xseed)
+        x = small.repeat(b // 2, 1, 1, 1).contiguous()
+        eng = DBLEngine(spec, sd, b, hw, hw)
+        y = eng.forward(x.pin_memory())[0].clone()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(y).all()) and torch.equal(y[:2], y[b - 2:])
+        y_ref, _ = O.forward(sd, small, scale)
+        y_b16, _ = O.forward(sd, small, scale, round_bf16=True)
+        rel, rel_b16 = _rel_l2(y[:2].cpu(), y_ref), _rel_l2(y_b16, y_ref)
+        d = (y[:2].cpu() - y_ref).abs()
+        print(f"{scale} {hw}^2 B={b}: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f}); box p99 {float(d[:, :4].flatten().quantile(.99)):.3f} px")
+        assert rel <= 3.0 * rel_b16 + 5e-3
+        rows, counts, _ = eng.detect(x.pin_memory(), conf=conf, iou=0.7)
+        torch.cuda.synchronize()
+        want, _ = N.non_max_suppression(y[:2].cpu().numpy(), conf, 0.7, max_det=300)
+        for i, w in enumerate(want):
+            for j in (i, b - 2 + i):
+                assert int(counts[j]) == len(w) and rows[j, : len(w)].cpu().numpy().tobytes() == w.tobytes(), (scale, j)
+        del eng
+        torch.cuda.empty_cache()
