@@ -2,11 +2,12 @@
 
 Stated tolerance for the bf16 backbone (north star: "bf16 backbone within a stated tolerance"):
   * teacher-forced, every top-level layer (inputs = the oracle's outputs rounded to bf16): relative L2 error of the
-    layer's output <= 2e-2 (bf16 rounding of every intermediate inside the block, fp32 accumulation); head logits <= 2e-2;
+    layer's output <= 1.5e-2 (2 x the largest measured value, 0.007 at the DSC3k2 layer; bf16 rounding of every intermediate inside
+    the block, fp32 accumulation); head logits <= 1.5e-2;
     also run with SURVEY.md §8d's weight recipe exactly as written (BN gamma ~ U(.5, 1.5), uncalibrated);
   * free-running: every layer's relative L2 error is bounded by a multiple of what bf16 ACTIVATION STORAGE costs the reference
     itself on the same weights, input and shape -- the oracle run with every block output rounded to bf16
-    (O.forward(round_bf16=True)) against its fp32 run: err_cuda(layer) <= 3 * err_bf16_oracle(layer) + 5e-3.  No constant is
+    (O.forward(round_bf16=True)) against its fp32 run: err_cuda(layer) <= 2 * err_bf16_oracle(layer) + 3e-3 (measured ratio <= 1.65).  No constant is
     invented per scale: a chaotic synthetic stack gets a loose bound exactly as far as the reference's own bf16 run is loose;
   * decoded outputs at 640x640 (n scale): the bounds in test_full_640_* are MEASURED values x 2 (printed by the test).
 The fp32 post-process on identical inputs is held to 1e-3 / bit-exactness in test_gpu_nms.py.
@@ -28,14 +29,14 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 # decoded-output bounds of the n-scale 640x640 free-running case = 2 x the values measured on B200 (printed by the test)
-BOX_MED_640, BOX_P99_640, BOX_MAX_640, SCORE_P99_640, SCORE_MAX_640 = 0.06, 1.0, 4.0, 4e-3, 3e-2
+BOX_MED_640, BOX_P99_640, BOX_MAX_640, SCORE_P99_640, SCORE_MAX_640 = 0.022, 0.22, 1.4, 4e-3, 4.7e-2  # measured 0.011 / 0.108 / 0.700 px, 0.0020 / 0.0232
 
 
 def _rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, forced_tol=2e-2, recipe="calibrated", free=True):
+def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, forced_tol=1.5e-2, recipe="calibrated", free=True):
     spec = resolve(None, scale, nc)
     sd = synth_state_dict(param_shapes(spec), seed, recipe=recipe)
     x = synth_images(b, h, w, xseed)
@@ -59,7 +60,7 @@ def _check_layers(scale, nc, seed, b, h, w, conv_impl, xseed=3, forced_tol=2e-2,
     print(f"[{scale} {h}x{w} impl={conv_impl}] free-running  rel-L2 (ours/oracle-bf16):", " ".join(f"{i}:{e:.3g}/{q:.3g}" for e, q, i, _ in fr))
     for e, q, i, kind in fr:
         if free:
-            assert e <= 3.0 * q + 5e-3, f"free-running layer {i} ({kind}): error {e:.3g} vs the reference's own bf16 drift {q:.3g} (conv_impl={conv_impl})"
+            assert e <= 2.0 * q + 3e-3, f"free-running layer {i} ({kind}): error {e:.3g} vs the reference's own bf16 drift {q:.3g} (conv_impl={conv_impl})"
     y, feats = eng.forward(x.cuda())
     torch.cuda.synchronize()
     return eng, sd, x, y.cpu(), y_ref
@@ -245,7 +246,7 @@ def test_config5_1280_dense_nms_through_the_production_engine():
     y_b16, _ = O.forward(sd, x, "n", round_bf16=True)
     rel, rel_b16 = _rel_l2(y.cpu(), y_ref), _rel_l2(y_b16, y_ref)
     print(f"1280^2: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f})")
-    assert rel <= 3.0 * rel_b16 + 5e-3
+    assert rel <= 2.0 * rel_b16 + 3e-3
     for kw in (dict(conf=0.001, iou=0.7), dict(conf=0.001, iou=0.7, multi_label=True)):
         rows, counts, _ = eng.detect(x.cuda(), **kw)
         torch.cuda.synchronize()
@@ -268,7 +269,7 @@ def test_config4_l_scale_production_engine():
     y_b16, _ = O.forward(sd, x, "l", round_bf16=True)
     rel, rel_b16 = _rel_l2(y.cpu(), y_ref), _rel_l2(y_b16, y_ref)
     print(f"l scale 192x256: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f})")
-    assert rel <= 3.0 * rel_b16 + 5e-3
+    assert rel <= 2.0 * rel_b16 + 3e-3
     rows, counts, _ = eng.detect(x.cuda(), conf=0.25, iou=0.7)
     want, _ = N.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
     assert counts.tolist() == [len(w) for w in want]
@@ -321,7 +322,7 @@ def test_config4_l_scale_640_batch_and_config5_1280_batch16():
         rel, rel_b16 = _rel_l2(y[:2].cpu(), y_ref), _rel_l2(y_b16, y_ref)
         d = (y[:2].cpu() - y_ref).abs()
         print(f"{scale} {hw}^2 B={b}: rel-L2 of y {rel:.4f} (oracle bf16 drift {rel_b16:.4f}); box p99 {float(d[:, :4].flatten().quantile(.99)):.3f} px")
-        assert rel <= 3.0 * rel_b16 + 5e-3
+        assert rel <= 2.0 * rel_b16 + 3e-3
         rows, counts, _ = eng.detect(x.pin_memory(), conf=conf, iou=0.7)
         torch.cuda.synchronize()
         want, _ = N.non_max_suppression(y[:2].cpu().numpy(), conf, 0.7, max_det=300)
