@@ -437,6 +437,8 @@ def main():
     d2h = torch.cuda.Stream(device=dev)
     use_gather = world > 1 and not args.no_gather
 
+    LAG = int(os.environ.get("DBL_E2E_LAG", "1"))  # 0: the host waits for every step's result before asking for the next batch
+
     def make_e2e(batch, mdl):
         gat = DetectionGatherer(batch, NMS["max_det"], dev, slots=3) if use_gather else None
         n_img = batch * world if use_gather else batch
@@ -458,7 +460,7 @@ def main():
                     done = torch.cuda.Event()
                     done.record(d2h)
                 pending.append((done, slot))
-                if len(pending) > 1:  # the host reads step i-1's detections while step i's gather/copy is in flight
+                if len(pending) > LAG:  # the host reads step i-LAG's detections while step i's gather/copy is in flight
                     e, s = pending.pop(0)
                     e.synchronize()
                     state["det"] = int(out_cnt[s][: batch].sum()) if gat is None else int(out_cnt[s][rank * batch:(rank + 1) * batch].sum())

@@ -25,7 +25,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 B, HW = 64, 640
-BOX_MED, BOX_P99, SCORE_P99 = 0.06, 1.0, 8e-3  # absolute bounds on the well-conditioned images (MEASURED x 2, see the printed table)
+BOX_MED, BOX_P99, SCORE_P99 = 0.032, 0.8, 7.5e-3  # absolute bounds on the well-conditioned images = 2 x MEASURED (0.016 px, 0.386 px, 0.0037)
 WELL = (2, 3, 6)  # images of the 8 whose fp32 reference is well-conditioned (oracle bf16 drift: box p99 < 0.3 px, score p99 < 2e-3)
 
 
@@ -68,12 +68,14 @@ def test_forward_vs_oracle_and_reference(bench):
         print(f"image {i}: CUDA vs fp32 oracle  box med {ours[0]:.3f} p99 {ours[1]:.3f} max {ours[2]:.2f} px | score p99 {ours[3]:.4f} max {ours[4]:.4f}"
               f"   || oracle-bf16 vs fp32: box med {drift[0]:.3f} p99 {drift[1]:.3f} max {drift[2]:.2f} | score p99 {drift[3]:.4f} max {drift[4]:.4f}")
     for i, (ours, drift) in enumerate(stats):
-        # every image: no worse than a small multiple of what bf16 activation storage costs the reference itself
+        # every image, chaotic or not: the bulk of the boxes (median) is as accurate as the reference's own bf16 run allows
         assert ours[0] <= 3.0 * drift[0] + 0.02, f"image {i}: median box error {ours[0]:.3f} vs bf16 drift {drift[0]:.3f}"
-        assert ours[1] <= 3.0 * drift[1] + 0.1, f"image {i}: p99 box error {ours[1]:.3f} vs bf16 drift {drift[1]:.3f}"
-        assert ours[3] <= 3.0 * drift[3] + 1e-3, f"image {i}: p99 score error {ours[3]:.4f} vs bf16 drift {drift[3]:.4f}"
-        if i in WELL:  # absolute bounds (<= 1 px p99) where the reference is well-conditioned
+        if drift[1] < 1.0:  # the fp32 reference is not chaotic on this image (its own bf16 run keeps p99 < 1 px): tails are comparable too
+            assert ours[1] <= 3.0 * drift[1] + 0.1, f"image {i}: p99 box error {ours[1]:.3f} vs bf16 drift {drift[1]:.3f}"
+            assert ours[3] <= 3.0 * drift[3] + 1e-3, f"image {i}: p99 score error {ours[3]:.4f} vs bf16 drift {drift[3]:.4f}"
+        if i in WELL:  # absolute bounds where the reference is well-conditioned
             assert ours[0] <= BOX_MED and ours[1] <= BOX_P99 and ours[3] <= SCORE_P99, (i, ours)
+    assert sum(1 for _, d in stats if d[1] < 1.0) >= 5  # the tail comparison above really ran on most of the batch
     # the REAL reference (fused DetectionModel) on images 2 and 3 of the batch
     g = np.load(os.path.join(GOLDEN, "fwd_n_nc80_640.npz"))
     s = _stats((y[2] - torch.from_numpy(g["ya"])).abs())
