@@ -129,6 +129,18 @@ int dbl_dsconv_supported(int k, int stride, int cin, int cout);
 int dbl_dsconv(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw_act, const void* w_pw_packed, const float* b_pw,
                const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int epi, dbl_stream_t stream);
 
+/* The same operation on the Blackwell data path (csrc/dsconv_tc.cu), stride 1: a persistent warp-specialised kernel -- TMA halo
+ * tiles (zero fill = padding), depthwise on the fp32 pipes writing the UMMA-swizzled A tile in place, pointwise on tcgen05 with the
+ * accumulator in TMEM, TMA-store epilogue -- whose phases overlap across consecutive tiles.  Differences to dbl_dsconv:
+ * w_pw is the PLAIN bf16 [cout][cin] matrix (the dbl_conv2d layout, BN folded), not the mma.sync fragment order; dw_act and a residual
+ * are not combined.  (k, cin, cout) from dbl_dsconv_tc_supported(); x and y must not alias (r may alias y). */
+int dbl_dsconv_tc_supported(int k, int stride, int cin, int cout);
+int dbl_dsconv_tc(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw_act, const void* w_pw, const float* b_pw,
+                  const dbl_tensor* r, const dbl_tensor* y, int k, int epi, dbl_stream_t stream);
+/* Developer aid (tools/ds_trace.py): with a non-NULL DEVICE buffer of the returned size, CTA 0 of every later dbl_dsconv_tc launch
+ * records %globaltimer stamps [role: producer, mma, depthwise, epilogue][first 16 tiles][4 events]; NULL switches it off. */
+int dbl_dsconv_tc_debug_trace(void* device_buffer);
+
 /* ---- depthwise convolution ---------------------------------------------------------------------------------------
  * DSConv.dw (conv.py:96-99), DWConv (conv.py:128-133), LSKblock.conv0 / conv_spatial (LSKA.py:31-32).
  *   w: f32 [k*k][c]   bias: f32 [c] or NULL   pad = dil*(k-1)/2 */

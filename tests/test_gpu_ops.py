@@ -451,3 +451,58 @@ def test_dsconv_fused(k, s, cin, cout, dw_act, epi, n, h, w):
     assert_close_bf16(from_nhwc(ybuf, 8, cout), ref, f"dsconv k{k} s{s} {cin}->{cout}", abs_=3e-2)
     assert bool((ybuf[..., :8].float() == -3.0).all()) and bool((ybuf[..., 8 + cout:].float() == -3.0).all())
     assert lib.dbl_dsconv_supported(5, 1, 48, 24) == 0
+
+
+# ---- depthwise-separable convolution on the Blackwell data path (csrc/dsconv_tc.cu: TMA + tcgen05 + TMEM, persistent) -----
+@pytest.mark.parametrize("k,cin,cout,dw_act,epi,n,h,w", [
+    (3, 64, 64, 0, L.EPI_NONE, 2, 40, 40), (7, 64, 64, 0, L.EPI_ADD, 2, 40, 40), (7, 64, 64, 0, L.EPI_ADD, 12, 40, 40),
+    (3, 32, 32, 0, L.EPI_NONE, 1, 24, 36), (7, 32, 32, 0, L.EPI_ADD, 3, 40, 40), (3, 128, 128, 0, L.EPI_NONE, 2, 20, 20),
+    (7, 128, 128, 0, L.EPI_ADD, 5, 20, 20), (3, 64, 80, 1, L.EPI_NONE, 1, 80, 80), (3, 80, 80, 1, L.EPI_NONE, 2, 40, 40),
+    (3, 128, 80, 1, L.EPI_NONE, 1, 40, 40), (3, 128, 64, 1, L.EPI_NONE, 1, 13, 19), (7, 64, 64, 0, L.EPI_ADD, 1, 33, 50),
+    (3, 64, 64, 0, L.EPI_MUL, 1, 7, 9), (7, 64, 64, 0, L.EPI_NONE, 40, 20, 20)])
+def test_dsconv_tc(k, cin, cout, dw_act, epi, n, h, w):
+    """every (k, cin, cout) instantiation; tiles that hang over the image on every side (TMA zero fill / store clipping), more tiles
+    than SMs (persistent loop, both pipeline parities), channel-slice views with a foreign pitch, and the engine's in-place residual
+    (r aliases y)."""
+    lib = L.require_device()
+    assert lib.dbl_dsconv_tc_supported(k, 1, cin, cout) == 1 and lib.dbl_dsconv_tc_supported(k, 2, cin, cout) == 0
+    g = torch.Generator().manual_seed(k * 100 + cin + cout + n)
+    x = bf16_round(torch.randn(n, cin, h, w, generator=g))
+    wdw = torch.randn(cin, 1, k, k, generator=g) / k
+    bdw = torch.randn(cin, generator=g) * 0.3 if dw_act else None
+    wpw = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
+    bpw = torch.randn(cout, generator=g) * 0.3
+    d = F.conv2d(x, wdw, bdw, 1, (k - 1) // 2, 1, cin)
+    if dw_act:
+        d = F.silu(d)
+    d = bf16_round(d)  # the depthwise result is held as bf16 in shared memory (the A operand of the pointwise GEMM)
+    ref = F.silu(F.conv2d(d, wpw, bpw))
+    r = bf16_round(torch.randn(ref.shape, generator=g)) if epi else None
+    if epi == L.EPI_ADD:
+        ref = ref + r
+    elif epi == L.EPI_MUL:
+        ref = ref * r
+    xbuf, xv = to_nhwc(x, pad_c=8, c_off=0)
+    ybuf, yv = empty_nhwc(n, h, w, cout, pad_c=16, c_off=8)
+    rv = None
+    if epi:  # in place, like DSBottleneck's `x = x + cv2(cv1(x))` in the engine: the residual IS the output view
+        ybuf[..., 8:8 + cout] = r.permute(0, 2, 3, 1).to(dev(), torch.bfloat16)
+        rv = yv
+    wd = wdw.reshape(cin, k * k).t().contiguous().to(dev())
+    bd = None if bdw is None else bdw.to(dev())
+    wdev = wpw.reshape(cout, cin).contiguous().to(dev(), torch.bfloat16)
+    bp = bpw.to(dev())
+    rc = lib.dbl_dsconv_tc(C.byref(xv), wd.data_ptr(), None if bd is None else bd.data_ptr(), dw_act, wdev.data_ptr(), bp.data_ptr(),
+                           None if rv is None else C.byref(rv), C.byref(yv), k, epi, stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(ybuf, 8, cout), ref, f"dsconv_tc k{k} {cin}->{cout}", abs_=3e-2)
+    assert bool((ybuf[..., :8].float() == -3.0).all()) and bool((ybuf[..., 8 + cout:].float() == -3.0).all())  # neighbours of the view untouched
+    assert bool((xbuf[..., cin:].float() == 7.0).all())
+    # run-to-run determinism of the pipelined kernel
+    if not epi:
+        y1 = ybuf.clone()
+        assert lib.dbl_dsconv_tc(C.byref(xv), wd.data_ptr(), None if bd is None else bd.data_ptr(), dw_act, wdev.data_ptr(), bp.data_ptr(), None,
+                                 C.byref(yv), k, epi, stream()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(y1, ybuf)

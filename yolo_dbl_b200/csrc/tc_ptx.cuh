@@ -35,6 +35,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > SPIN_LIMIT) __trap();  // a protocol bug must fail loudly, never hang the GPU
     }
 }
+// Same wait for roles that expect to sleep (a producer waiting for a free stage, an epilogue waiting for the next accumulator): the
+// suspend-time hint lets the hardware park the warp until the phase completes or the hint expires, instead of re-issuing
+// try_wait / compare / branch every ~80 cycles.  ncu on dsconv_tc_kernel: ten such warps per CTA spent 23 % of all issued
+// instructions in this loop, slots the depthwise warps needed.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 4000) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 20)) __trap();  // a protocol bug must fail loudly, never hang the GPU
+    }
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
