@@ -82,6 +82,7 @@ class DBLEngine:
         # cost.  Larger maps stay unfused: the fused CTA serialises fill -> depthwise -> pointwise at low occupancy
         # (Detect P3 64->80 @80^2: 108 us fused vs 89 us as two launches).  "1" = wherever supported, "0" = never.
         self.fuse_ds = os.environ.get("DBL_FUSE_DS", "auto")
+        self.ds_impl = os.environ.get("DBL_DS_IMPL", "auto")  # "mma": keep the warp-MMA kernel (A/B aid); "auto": tcgen05 kernel where instantiated
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
@@ -208,6 +209,19 @@ class DBLEngine:
         """dw k x k (+bias+SiLU when bdw is given) -> pw 1x1 + bias + SiLU (+ residual) in one kernel (csrc/dsconv_mma.cu);
         False when no instantiation exists or fusion is off -> the caller emits the two-kernel form"""
         k, cin, cout = wdw.shape[-1], wdw.shape[0], wpw.shape[0]
+        # Blackwell data path first (csrc/dsconv_tc.cu: TMA + tcgen05 + TMEM, persistent, phases of consecutive tiles overlap): faster
+        # than both the warp-MMA kernel and the two-launch form on every shape measured (tools/ds_bench.py, 1.2x .. 2.3x)
+        if (self.fuse_thin and self.ds_impl != "mma" and self.fuse_ds != "0" and s == 1 and x.buf.data_ptr() != y.buf.data_ptr()
+                and not (bdw is not None and r is not None) and self.lib.dbl_dsconv_tc_supported(k, s, cin, cout)):
+            wd = self._dev(wdw.reshape(cin, k * k).t(), torch.float32)
+            bd = self._dev(bdw, torch.float32) if bdw is not None else None
+            wp, bp = self._pack_w(wpw), self._dev(bpw, torch.float32)
+            npix = self.B * y.h * y.w
+            args = (C.byref(x.desc), L.ptr(wd), L.ptr(bd), 1 if bdw is not None else 0, L.ptr(wp), L.ptr(bp),
+                    C.byref(r.desc) if r is not None else None, C.byref(y.desc), k, epi if r is not None else L.EPI_NONE)
+            nbytes = 2 * self.B * x.h * x.w * cin + 2 * npix * cout * (2 if r is not None else 1) + 4 * k * k * cin + 2 * cin * cout
+            self._emit(self.lib.dbl_dsconv_tc, args, what, "dsconv_tc", 2.0 * npix * cin * (k * k + cout), nbytes)
+            return True
         want = self.fuse_ds == "1" or (self.fuse_ds == "auto" and s == 1 and x.h * x.w * cin <= 131072)
         if not (self.fuse_thin and want and self.lib.dbl_dsconv_supported(k, s, cin, cout)) or x.buf.data_ptr() == y.buf.data_ptr():
             return False

@@ -16,6 +16,45 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> dict:
+    """Pin this process (and, by first touch, the pinned host buffers it allocates afterwards) to the CPUs of the NUMA node the
+    GPU hangs off.  One process per GPU: without it the staging buffers of a rank may land on the other socket and every H2D copy
+    crosses the inter-socket link (measured on this pool: 78.6 MB uint8 batches at 11 GB/s instead of 55 GB/s).  Best effort: returns
+    what was done; a missing sysfs entry (containers) or a denied affinity call leaves the process untouched."""
+    import os
+
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bdf}/local_cpulist"
+        info["pci"] = bdf
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        target = (cpus & allowed) or None
+        info["local_cpulist"] = spec
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+        info["cpus"] = len(target or allowed)
+        try:
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+        except OSError:
+            pass
+    except (OSError, AttributeError, ValueError) as e:
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """[begin, end) of the images rank `rank` owns: contiguous, sizes differ by at most one, earlier ranks get the extra."""
     if world <= 0 or not 0 <= rank < world:
