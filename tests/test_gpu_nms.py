@@ -104,11 +104,11 @@ def test_nms_full_size_batch64_matches_oracle():
             assert bool((s[:-1] >= s[1:]).all()) and bool((s > conf).all())
 
 
-def test_decode_vs_oracle_and_fused_filter_consistency():
+@pytest.mark.parametrize("nc,hw", [(5, [(16, 24), (8, 12), (4, 6)]), (80, [(40, 40), (20, 20), (10, 10)]), (3, [(12, 20), (6, 10), (3, 5)])])
+def test_decode_vs_oracle_and_fused_filter_consistency(nc, hw):
     lib = L.require_device()
     g = torch.Generator().manual_seed(7)
-    B, nc = 3, 5
-    hw = [(16, 24), (8, 12), (4, 6)]
+    B = 3
     strides = [8.0, 16.0, 32.0]
     pitch = (64 + nc + 3) // 4 * 4
     feats = [torch.cat([torch.randn(B, 64, h, w, generator=g) * 2, torch.randn(B, nc, h, w, generator=g) * 1.5 - 1.0], 1) for h, w in hw]
