@@ -59,6 +59,19 @@ _ROWS = [
 ]
 
 
+# cfg/models/v13/yolov13_DBL2.yaml:8-52 (the sibling graph: DSC3k2 at layer 6, C3Ghost at 9 and 33, DSC3k2 neck blocks; l / x scales)
+_SCALES_DBL2 = {"l": (1.00, 1.00), "x": (1.00, 1.50)}
+_ROWS_DBL2 = list(_ROWS)
+_ROWS_DBL2[6] = (-1, 8, "DSC3k2", (256,))
+_ROWS_DBL2[9] = (-1, 8, "C3Ghost", (512,))
+_ROWS_DBL2[11] = (-1, 2, "LSKblock", ())
+_ROWS_DBL2[20] = (-1, 1, "DSC3k2", (512,))
+_ROWS_DBL2[25] = (13, 1, "DSC3k2", (256, 1.0))  # args [256, 1, 1]: dsc3k = True, e = 1
+_ROWS_DBL2[29] = (-1, 1, "DSC3k2", (512,))
+_ROWS_DBL2[33] = (-1, 1, "C3Ghost", (1024,))
+_CFGS = {"DBL": (_ROWS, _SCALES), "DBL2": (_ROWS_DBL2, _SCALES_DBL2)}
+
+
 @dataclass
 class Layer:
     i: int
@@ -74,19 +87,22 @@ def _divisible8(x: float) -> int:  # utils/ops.py:130-143
     return int(math.ceil(x / 8) * 8)
 
 
-def build_layers(scale: str = "n") -> List[Layer]:
-    """Resolve depth/width like parse_model (nn/tasks.py:979, 1047-1049, 1121-1145)."""
-    depth, width = _SCALES[scale]
+def build_layers(scale: str = "n", cfg: str = "DBL") -> List[Layer]:
+    """Resolve depth/width like parse_model (nn/tasks.py:979, 1047-1049, 1121-1145).  cfg: "DBL" (yolov13_DBL.yaml) or "DBL2"."""
+    rows, scales = _CFGS[cfg]
+    depth, width = scales[scale]
     ch: List[int] = []
     out: List[Layer] = []
-    for i, (f, n, kind, args) in enumerate(_ROWS):
+    for i, (f, n, kind, args) in enumerate(rows):
         n = max(round(n * depth), 1) if n > 1 else n
         cin = (lambda j: 3 if (i == 0) else ch[j])
         extra = {}
-        if kind in ("Conv", "Bottleneck", "DSConv", "DSC3k2"):
+        if kind in ("Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost"):
             c1, c2 = cin(f), _divisible8(args[0] * width)
             if kind in ("Conv", "DSConv"):
                 extra = {"k": args[1], "s": args[2]}
+            if kind == "DSC3k2":
+                extra = {"e": args[1] if len(args) > 1 else 0.5}
         elif kind == "HyperACE":
             c1, c2 = ch[f[1]], _divisible8(args[0] * width)
             he = args[1]
@@ -157,6 +173,22 @@ def dsc3k(sd, p, x, n=2, shortcut=True):
     a = conv_bn_silu(sd, p + ".cv1", x)
     for j in range(n):
         a = ds_bottleneck(sd, f"{p}.m.{j}", a, shortcut)
+    return conv_bn_silu(sd, p + ".cv3", torch.cat((a, conv_bn_silu(sd, p + ".cv2", x)), 1))
+
+
+def ghost_conv(sd, p, x, act=True):
+    """``GhostConv.forward`` conv.py:184-197 -- primary 1x1 Conv, cheap 5x5 depthwise Conv on its output, concatenated."""
+    y = conv_bn_silu(sd, p + ".cv1", x, act=act)
+    return torch.cat((y, conv_bn_silu(sd, p + ".cv2", y, g=y.shape[1], act=act)), 1)
+
+
+def c3ghost(sd, p, x, n):
+    """``C3Ghost`` block.py:313-320 = ``C3.forward`` block.py:271-273 with m = n x ``GhostBottleneck`` (stride 1, block.py:323-341:
+    GhostConv -> Identity -> GhostConv(act=False), identity shortcut)."""
+    a = conv_bn_silu(sd, p + ".cv1", x)
+    for j in range(n):
+        q = f"{p}.m.{j}.conv"
+        a = a + ghost_conv(sd, q + ".2", ghost_conv(sd, q + ".0", a), act=False)
     return conv_bn_silu(sd, p + ".cv3", torch.cat((a, conv_bn_silu(sd, p + ".cv2", x)), 1))
 
 
@@ -329,23 +361,24 @@ def _rounded(fn):
     return wrapped
 
 
+ghost_conv = _rounded(ghost_conv)
 conv_bn_silu, dsconv, bottleneck, ds_bottleneck = _rounded(conv_bn_silu), _rounded(dsconv), _rounded(bottleneck), _rounded(ds_bottleneck)
 lskblock, c3ah, dysample, downsample_conv, fullpad = _rounded(lskblock), _rounded(c3ah), _rounded(dysample), _rounded(downsample_conv), _rounded(fullpad)
 
 
-def forward(sd: Dict[str, Tensor], x: Tensor, scale: str = "n", collect: bool = False, round_bf16: bool = False):
+def forward(sd: Dict[str, Tensor], x: Tensor, scale: str = "n", collect: bool = False, round_bf16: bool = False, cfg: str = "DBL"):
     """Returns (y, head_feats[, per-layer outputs]).  x: (B,3,H,W) fp32 in 0..1, H,W % 32 == 0.
     round_bf16: emulate bf16 activation storage (see ROUND_BF16); the head's last 1x1 convs and the decode stay fp32."""
     global ROUND_BF16
     ROUND_BF16 = bool(round_bf16)
     try:
-        return _forward(sd, x.to(torch.bfloat16).float() if round_bf16 else x, scale, collect)
+        return _forward(sd, x.to(torch.bfloat16).float() if round_bf16 else x, scale, collect, cfg)
     finally:
         ROUND_BF16 = False
 
 
-def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool):
-    layers = build_layers(scale)
+def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool, cfg: str = "DBL"):
+    layers = build_layers(scale, cfg)
     outs: List[Tensor] = []
     with torch.inference_mode():
         for L in layers:
@@ -361,6 +394,8 @@ def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool):
                     o = bottleneck(sd, f"{p}.{r}" if L.n > 1 else p, o, True)
             elif L.kind == "DSC3k2":
                 o = dsc3k2(sd, p, src(L.f), L.n)
+            elif L.kind == "C3Ghost":
+                o = c3ghost(sd, p, src(L.f), L.n)
             elif L.kind == "LSKblock":
                 o = src(L.f)
                 for r in range(L.n):

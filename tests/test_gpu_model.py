@@ -331,3 +331,32 @@ def test_config4_l_scale_640_batch_and_config5_1280_batch16():
                 assert int(counts[j]) == len(w) and rows[j, : len(w)].cpu().numpy().tobytes() == w.tobytes(), (scale, j)
         del eng
         torch.cuda.empty_cache()
+
+
+def test_sibling_graph_dbl2_c3ghost():
+    """yolov13l_DBL2.yaml: C3Ghost / GhostBottleneck / GhostConv and the DSC3k2 variants on the B200 path, teacher-forced
+    per layer and free-running against the oracle (which is pinned to the reference's own DBL2 output, tests/test_oracle_golden.py)."""
+    spec = resolve("yolov13l_DBL2.yaml", "l", 3)
+    sd = synth_state_dict(param_shapes(spec), 9)
+    x = synth_images(1, 64, 96, 10)
+    eng = DBLEngine(spec, sd, 1, 64, 96, use_graph=False, keep_layers=True)
+    y_ref, feats_ref, outs_ref = O.forward(sd, x, "l", collect=True, cfg="DBL2")
+    _, _, outs_b16 = O.forward(sd, x, "l", collect=True, round_bf16=True, cfg="DBL2")
+    head_ref = torch.cat([f.reshape(1, f.shape[1], -1) for f in feats_ref], 2)
+    forced = eng.debug_layers_forced(x.cuda(), outs_ref)
+    errs = [(_rel_l2(o, r), i, spec.layers[i].kind) for i, (o, r) in enumerate(zip(forced, outs_ref + [head_ref]))]
+    print("[DBL2 l 64x96] teacher-forced rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in errs))
+    for e, i, kind in errs:
+        assert e <= 1.5e-2, f"teacher-forced layer {i} ({kind}) relative L2 error {e:.3g}"
+    outs = eng.debug_layers(x.cuda())
+    for i, (o, r, q) in enumerate(zip(outs, outs_ref, outs_b16)):
+        if o is not None:
+            assert _rel_l2(o, r) <= 2.0 * _rel_l2(q, r) + 3e-3, f"free-running layer {i} ({spec.layers[i].kind})"
+    # production engine (graph, fused head) through the facade, detections bit-exact vs the oracle NMS of its own y
+    m = DBLBackend.synthetic("l", 3, seed=9, cfg="yolov13l_DBL2.yaml", device="cuda:0")
+    y, _ = m(x.cuda())
+    rows, counts = m.detect(x.cuda(), conf=0.01, iou=0.7)
+    torch.cuda.synchronize()
+    want, _ = N.non_max_suppression(y.cpu().numpy(), 0.01, 0.7, max_det=300)
+    assert counts.tolist() == [len(w) for w in want] and rows[0, : len(want[0])].cpu().numpy().tobytes() == want[0].tobytes()
+    assert _rel_l2(y.cpu(), y_ref) <= 2.0 * _rel_l2(O.forward(sd, x, "l", round_bf16=True, cfg="DBL2")[0], y_ref) + 3e-3

@@ -203,3 +203,23 @@ def test_oracle_forward_nc80_640_matches_reference_on_the_benchmarked_weights():
     c = g["counts"].tolist()
     assert len(rows[0]) == c[0] and rows[0].tobytes() == g["rows"][: c[0]].tobytes()  # image 0: the reference's own y -> identical rows
     assert abs(len(rows[1]) - c[1]) <= 2  # image 1: the oracle's y (fp32 noise may flip a box at the threshold)
+
+
+def test_dbl2_graph_matches_reference_inventory_and_forward():
+    """Sibling graph yolov13l_DBL2.yaml: parameter inventory == the reference's state_dict, oracle forward (C3Ghost,
+    GhostBottleneck, GhostConv, DSC3k2 with e = 1) == the reference's output and per-layer samples."""
+    shapes = json.load(open(os.path.join(GOLDEN, "shapes_l_DBL2_nc3.json")))
+    spec = resolve("yolov13l_DBL2.yaml", "l", 3)
+    mine = param_shapes(spec)
+    assert list(mine.keys()) == list(shapes.keys()) and all(list(mine[k]) == list(shapes[k]) for k in shapes)
+    assert [L.kind for L in spec.layers if L.kind in ("C3Ghost", "DSC3k2")] == ["DSC3k2", "C3Ghost", "DSC3k2", "DSC3k2", "DSC3k2", "C3Ghost"]
+    g = _load("fwd_l_DBL2_nc3_small.npz")
+    sd = synth_state_dict(shapes, 9)
+    x = synth_images(1, 64, 96, seed=10)
+    y, feats, outs = O.forward(sd, x, "l", collect=True, cfg="DBL2")
+    torch.testing.assert_close(y, torch.from_numpy(g["y_unfused"]), rtol=2e-4, atol=2e-3)
+    torch.testing.assert_close(y, torch.from_numpy(g["y"]), rtol=1e-3, atol=2e-2)  # reference after fuse()
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == tuple(g[f"layer{i}_shape"]), f"layer {i}"
+        samp = o.reshape(-1)[torch.from_numpy(g[f"layer{i}_index"])]
+        torch.testing.assert_close(samp, torch.from_numpy(g[f"layer{i}_samples"]), rtol=5e-4, atol=5e-4, msg=lambda m, i=i: f"layer {i}: {m}")

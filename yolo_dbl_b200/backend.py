@@ -96,6 +96,17 @@ class DBLBackend(nn.Module):
         return cls(G.resolve(y, y.get("scale", "n"), y.get("nc")), sd, names=getattr(model, "names", None), cfg=y, **kw)
 
     @classmethod
+    def from_pt(cls, path, cfg=None, scale=None, **kw) -> "DBLBackend":
+        """A reference ``.pt`` checkpoint (``torch.save({"model": DetectionModel, ...})``) without the reference package: weights, graph
+        (the yaml embedded in the checkpoint), class names (``nn/tasks.py:897-924`` attempt_load_one_weight)."""
+        from .checkpoint import load_pt
+
+        sd, info = load_pt(path)
+        y = cfg if cfg is not None else info["yaml"]
+        sc = scale or info["scale"] or (G.scale_from_name(str(y.get("yaml_file", ""))) if isinstance(y, dict) else "n")
+        return cls(G.resolve(y, sc, info["nc"]), sd, names=info["names"], cfg=y if isinstance(y, dict) else None, **kw)
+
+    @classmethod
     def synthetic(cls, scale="n", nc=80, seed=0, cfg=None, **kw) -> "DBLBackend":
         spec = G.resolve(cfg, scale, nc)
         return cls(spec, synth_state_dict(G.param_shapes(spec), seed), cfg=cfg, **kw)
@@ -449,8 +460,13 @@ class YOLO:
             raise NotImplementedError("only the detect task is on the YOLO-DBL hot path")
         import os
 
+        if isinstance(model, str) and model.endswith(".pt"):  # trained / saved weights (engine/model.py:287-311 _load)
+            self.model = DBLBackend.from_pt(model, device=device)
+            self.names = self.model.names
+            self.overrides = {"conf": 0.25, "iou": 0.7, "max_det": 300, "agnostic_nms": False, "classes": None}
+            return
         scale = G.scale_from_name(os.path.basename(str(model)))
-        cfg = model if (isinstance(model, dict) or (isinstance(model, str) and os.path.exists(model))) else None
+        cfg = model if (isinstance(model, dict) or (isinstance(model, str) and (os.path.exists(model) or G.builtin_cfg_name(model)))) else None
         spec = G.resolve(cfg, scale, nc)
         sd = state_dict if state_dict is not None else synth_state_dict(G.param_shapes(spec), seed)
         self.model = DBLBackend(spec, sd, device=device, cfg=cfg)

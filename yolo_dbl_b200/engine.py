@@ -290,6 +290,30 @@ class DBLEngine:
             self._lower_dsc3k(z.slice((1 + j) * c, c), f"{p}.m.{j}", z.slice((2 + j) * c, c))
         self._conv_bn(z, p + ".cv2", y)
 
+    def _dw_bn(self, x: Act, p: str, y: Act, act: int):
+        """depthwise Conv module: Conv(c, c, k, g=c) + BN (+ SiLU), BN folded into the filter (GhostConv.cv2, conv.py:192)"""
+        w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
+        self._dw(x, w, b, y, w.shape[-1], 1, 1, act, p)
+
+    def _lower_c3ghost(self, x: Act, L_: LayerSpec, p: str, y: Act):
+        """C3Ghost (block.py:313-320) over C3.forward (block.py:271-273); m = n GhostBottleneck(c_, c_), stride 1 (block.py:323-341):
+        x + GhostConv(act=False)(GhostConv(x)), GhostConv = [1x1 Conv | 5x5 depthwise Conv of it] (conv.py:184-197).  Both halves of a
+        GhostConv are channel slices of one buffer, so its torch.cat costs nothing."""
+        c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
+        t = self._alloc(x.h, x.w, 2 * c_)
+        self._conv_bn_pair(x, p + ".cv1", p + ".cv2", t)
+        a = t.slice(0, c_)
+        for j in range(L_.n):
+            q = f"{p}.m.{j}.conv"
+            h = self.sd[q + ".0.cv1.conv.weight"].shape[0] * 2   # GhostBottleneck hidden width = c_ / 2
+            g1, g2 = self._alloc(x.h, x.w, h), self._alloc(x.h, x.w, c_)
+            self._conv_bn(a, q + ".0.cv1", g1.slice(0, h // 2))
+            self._dw_bn(g1.slice(0, h // 2), q + ".0.cv2", g1.slice(h // 2, h // 2), L.ACT_SILU)
+            self._conv_bn(g1, q + ".2.cv1", g2.slice(0, c_ // 2), act=L.ACT_NONE)
+            self._dw_bn(g2.slice(0, c_ // 2), q + ".2.cv2", g2.slice(c_ // 2, c_ // 2), L.ACT_NONE)
+            self._emit(self.lib.dbl_gated_add, (C.byref(a.desc), C.byref(g2.desc), C.c_float(1.0), C.byref(a.desc), None), f"{p}.m.{j}.add")
+        self._conv_bn(t, p + ".cv3", y)
+
     def _lower_lsk(self, x: Act, p: str, y: Act):
         """LSKblock.forward (nn/modules_attention/LSKA.py:28-52)"""
         d, sd = x.c, self.sd
@@ -503,6 +527,8 @@ class DBLEngine:
                     cur = dst
             elif Lx.kind == "DSC3k2":
                 self._lower_dsc3k2(ins[0], Lx, p, y)
+            elif Lx.kind == "C3Ghost":
+                self._lower_c3ghost(ins[0], Lx, p, y)
             elif Lx.kind == "LSKblock":
                 cur = ins[0]
                 for r in range(Lx.n):

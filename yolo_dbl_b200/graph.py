@@ -59,7 +59,57 @@ YOLO_DBL_CFG = {
     ],
 }
 
-SUPPORTED = {"Conv", "Bottleneck", "DSConv", "DSC3k2", "LSKblock", "HyperACE", "DySample", "DownsampleConv",
+# cfg/models/v13/yolov13_DBL2.yaml:1-52 -- the sibling graph of the same repository: layer 6 becomes a
+# DSC3k2 stack, layers 9 and 33 become C3Ghost (GhostBottleneck / GhostConv, nn/modules/block.py:313-341, conv.py:184-197), the
+# P4 / P3 neck blocks become DSC3k2; only the l and x scales are defined.
+YOLO_DBL2_CFG = {
+    "nc": 80,
+    "scales": {"l": [1.00, 1.00, 114514], "x": [1.00, 1.50, 114514]},
+    "backbone": [
+        [-1, 1, "Conv", [32, 3, 1]],
+        [-1, 1, "Conv", [64, 3, 2]],
+        [-1, 1, "Bottleneck", [64]],
+        [-1, 1, "Conv", [128, 3, 2]],
+        [-1, 2, "Bottleneck", [128]],
+        [-1, 1, "Conv", [256, 3, 2]],
+        [-1, 8, "DSC3k2", [256, True]],
+        [-1, 1, "Conv", [512, 1, 1]],
+        [-1, 1, "DSConv", [512, 3, 2]],
+        [-1, 8, "C3Ghost", [512, True]],
+        [-1, 1, "DSConv", [1024, 3, 2]],
+        [-1, 2, "LSKblock", [1024]],
+    ],
+    "head": [
+        [[7, 9, 11], 2, "HyperACE", [512, 8, True, True, 0.5, 1, "both", True]],
+        [-1, 1, "DySample", []],
+        [12, 1, "DownsampleConv", [True]],
+        [[9, 12], 1, "FullPAD_Tunnel", []],
+        [[7, 13], 1, "FullPAD_Tunnel", []],
+        [[11, 14], 1, "FullPAD_Tunnel", []],
+        [-1, 1, "DySample", []],
+        [[-1, 15], 1, "Concat", [1]],
+        [-1, 1, "DSC3k2", [512, True]],
+        [[-1, 12], 1, "FullPAD_Tunnel", []],
+        [-2, 1, "DySample", []],
+        [[-1, 16], 1, "Concat", [1]],
+        [-1, 1, "Bottleneck", [256, True]],
+        [13, 1, "DSC3k2", [256, 1, 1]],
+        [[-2, -1], 1, "FullPAD_Tunnel", []],
+        [-1, 1, "Conv", [256, 3, 2]],
+        [[-1, 21], 1, "Concat", [1]],
+        [-1, 1, "DSC3k2", [512, True]],
+        [[-1, 12], 1, "FullPAD_Tunnel", []],
+        [-2, 1, "Conv", [512, 3, 2]],
+        [[-1, 17], 1, "Concat", [1]],
+        [-1, 1, "C3Ghost", [1024, True]],
+        [[-1, 14], 1, "FullPAD_Tunnel", []],
+        [[26, 30, 34], 1, "Detect", ["nc"]],
+    ],
+}
+
+BUILTIN_CFGS = {"yolov13_DBL.yaml": YOLO_DBL_CFG, "yolov13_DBL2.yaml": YOLO_DBL2_CFG}
+
+SUPPORTED = {"Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost", "LSKblock", "HyperACE", "DySample", "DownsampleConv",
              "FullPAD_Tunnel", "Concat", "Detect"}
 
 
@@ -99,15 +149,31 @@ def make_divisible(x: float, d: int = 8) -> int:
 
 
 def load_cfg(cfg) -> dict:
-    """Accepts None (built-in YOLO-DBL), a dict, or a path to a yaml with the same schema."""
+    """Accepts None (built-in YOLO-DBL), a dict, the NAME of a built-in graph ('yolov13l_DBL2.yaml': the scale letter is ignored
+    here) or a path to a yaml with the same schema."""
     if cfg is None:
         return YOLO_DBL_CFG
     if isinstance(cfg, dict):
         return cfg
+    import os
+    import re
+
+    base = re.sub(r"(yolov\d+)[nslmx](_|\.)", r"\1\2", os.path.basename(str(cfg)))
+    if base in BUILTIN_CFGS and not os.path.exists(str(cfg)):
+        return BUILTIN_CFGS[base]
     import yaml
 
     with open(cfg, "r", errors="ignore") as f:
         return yaml.safe_load(f)
+
+
+def builtin_cfg_name(name) -> str | None:
+    """'yolov13l_DBL2.yaml' -> 'yolov13_DBL2.yaml' when that graph is built in, else None"""
+    import os
+    import re
+
+    base = re.sub(r"(yolov\d+)[nslmx](_|\.)", r"\1\2", os.path.basename(str(name)))
+    return base if base in BUILTIN_CFGS else None
 
 
 def scale_from_name(name: str, default: str = "n") -> str:
@@ -152,8 +218,12 @@ def resolve(cfg=None, scale: str = "n", nc: int | None = None) -> GraphSpec:
         elif kind == "DSC3k2":
             L.c2 = make_divisible(min(args[0], max_ch) * width)
             L.extra["dsc3k"] = bool(args[1]) if len(args) > 1 else False
+            L.extra["e"] = float(args[2]) if len(args) > 2 else 0.5  # DSC3k2(c1, c2, n, dsc3k, e=0.5, ...) (block.py:1505-1530)
             if not L.extra["dsc3k"]:
                 raise NotImplementedError("DSC3k2(dsc3k=False) is not used by YOLO-DBL")
+        elif kind == "C3Ghost":
+            L.c2 = make_divisible(min(args[0], max_ch) * width)
+            L.shortcut = bool(args[1]) if len(args) > 1 else True  # unused by GhostBottleneck (its own identity shortcut)
         elif kind == "HyperACE":
             L.c1 = cin[1]
             L.c2 = make_divisible(min(args[0], max_ch) * width)
@@ -167,6 +237,8 @@ def resolve(cfg=None, scale: str = "n", nc: int | None = None) -> GraphSpec:
                            context=args[6], channel_adjust=bool(args[7]), cins=cin)
             if not (L.extra["dsc3k"] and L.extra["context"] == "both" and L.extra["channel_adjust"]):
                 raise NotImplementedError("HyperACE variant outside YOLO-DBL")
+            if not L.extra["shortcut"]:  # the lowering always emits the residual DSBottleneck (DSBottleneck.add = shortcut and c1 == c2)
+                raise NotImplementedError("HyperACE(shortcut=False) is not used by YOLO-DBL")
             if sum(cin) != 4 * L.c1:
                 raise ValueError("FuseModule(channel_adjust=True) needs c(P3)+c(P4)+c(P5) == 4*c(P4)")
             st = sin[1]
@@ -257,11 +329,23 @@ def param_shapes(spec: GraphSpec) -> Dict[str, list]:
                 _conv(sh, rep(r) + ".cv1", c1, int(L.c2 * 0.5), 3)
                 _conv(sh, rep(r) + ".cv2", int(L.c2 * 0.5), L.c2, 3)
         elif L.kind == "DSC3k2":
-            c = int(L.c2 * 0.5)
+            c = int(L.c2 * L.extra.get("e", 0.5))
             _conv(sh, p + ".cv1", L.c1, 2 * c, 1)
             _conv(sh, p + ".cv2", (2 + L.n) * c, L.c2, 1)
             for j in range(L.n):
                 _dsc3k(sh, f"{p}.m.{j}", c, c, 2, 1.0)
+        elif L.kind == "C3Ghost":  # C3 (block.py:259-273) whose m = n GhostBottleneck(c_, c_) (block.py:313-341)
+            c_ = int(L.c2 * 0.5)
+            _conv(sh, p + ".cv1", L.c1, c_, 1)
+            _conv(sh, p + ".cv2", L.c1, c_, 1)
+            _conv(sh, p + ".cv3", 2 * c_, L.c2, 1)
+            for j in range(L.n):
+                q = f"{p}.m.{j}.conv"
+                h = c_ // 2                      # GhostBottleneck hidden width
+                _conv(sh, q + ".0.cv1", c_, h // 2, 1)             # GhostConv(c_, h): primary 1x1 ...
+                _conv(sh, q + ".0.cv2", h // 2, h // 2, 5, g=h // 2)  # ... and cheap 5x5 depthwise (conv.py:184-197)
+                _conv(sh, q + ".2.cv1", h, c_ // 2, 1)              # GhostConv(h, c_, act=False)
+                _conv(sh, q + ".2.cv2", c_ // 2, c_ // 2, 5, g=c_ // 2)
         elif L.kind == "LSKblock":
             d = L.c1
             for r in range(L.n):
