@@ -459,7 +459,8 @@ def test_dsconv_fused(k, s, cin, cout, dw_act, epi, n, h, w):
     (3, 32, 32, 0, L.EPI_NONE, 1, 24, 36), (7, 32, 32, 0, L.EPI_ADD, 3, 40, 40), (3, 128, 128, 0, L.EPI_NONE, 2, 20, 20),
     (7, 128, 128, 0, L.EPI_ADD, 5, 20, 20), (3, 64, 80, 1, L.EPI_NONE, 1, 80, 80), (3, 80, 80, 1, L.EPI_NONE, 2, 40, 40),
     (3, 128, 80, 1, L.EPI_NONE, 1, 40, 40), (3, 128, 64, 1, L.EPI_NONE, 1, 13, 19), (7, 64, 64, 0, L.EPI_ADD, 1, 33, 50),
-    (3, 64, 64, 0, L.EPI_MUL, 1, 7, 9), (7, 64, 64, 0, L.EPI_NONE, 40, 20, 20)])
+    (3, 64, 64, 0, L.EPI_MUL, 1, 7, 9), (7, 64, 64, 0, L.EPI_NONE, 40, 20, 20), (3, 256, 80, 1, L.EPI_NONE, 2, 20, 20),
+    (3, 256, 64, 1, L.EPI_NONE, 1, 10, 10)])
 def test_dsconv_tc(k, cin, cout, dw_act, epi, n, h, w):
     """every (k, cin, cout) instantiation; tiles that hang over the image on every side (TMA zero fill / store clipping), more tiles
     than SMs (persistent loop, both pipeline parities), channel-slice views with a foreign pitch, and the engine's in-place residual

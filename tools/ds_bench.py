@@ -23,6 +23,7 @@ SHAPES = {  # name: (n, h, w, cin, cout, k, epi, dw_act)
     "det_p3_80to80@80": (64, 80, 80, 80, 80, 3, 0, 1),
     "det_p4_128to80@40": (64, 40, 40, 128, 80, 3, 0, 1),
     "det_p4_80to80@40": (64, 40, 40, 80, 80, 3, 0, 1),
+    "det_p5_256to80@20": (64, 20, 20, 256, 80, 3, 0, 1),
     "det_p5_80to80@20": (64, 20, 20, 80, 80, 3, 0, 1),
 }
 

@@ -56,18 +56,23 @@ struct DtCfg {
     static constexpr int B_BYTES = NCH * B_CHUNK;
     static constexpr int O_BYTES = NOC * (int)DT_OCHUNK_BYTES;
     static constexpr int WD_BYTES = K * K * CIN * 4;
-    static constexpr int MISC = dt_round1k(WD_BYTES + (COUT + CIN) * 4 + 256);
-    static constexpr int total(int nbuf) { return 1024 + 2 * IN_BYTES + nbuf * A_BYTES + B_BYTES + nbuf * O_BYTES + (RES ? nbuf * O_BYTES : 0) + MISC; }
-    static constexpr int NBUF = total(2) <= DT_SMEM_LIMIT ? 2 : 1;  // A / staging / residual buffers: double when they fit
-    static constexpr int SMEM = total(NBUF);
+    static constexpr int MISC = dt_round1k(WD_BYTES + (COUT + CIN) * 4 + 512);
+    static constexpr int total(int nbuf, int nin) { return 1024 + nin * IN_BYTES + nbuf * A_BYTES + B_BYTES + nbuf * O_BYTES + (RES ? nbuf * O_BYTES : 0) + MISC; }
+    static constexpr int NBUF = total(2, 2) <= DT_SMEM_LIMIT ? 2 : 1;  // A / staging / residual buffers: double when they fit
+    static constexpr int NIN = total(NBUF, 3) <= DT_SMEM_LIMIT ? 3 : 2; // input stages: a third one hides the TMA round trip of the short 3x3 tiles
+    static constexpr int SMEM = total(NBUF, NIN);
+    // epilogue groups: with two staging buffers the eight epilogue warps split into two groups of four that drain ALTERNATE tiles
+    // concurrently (group g owns accumulator g, staging buffer g, residual slot g); the per-tile chain tcgen05.ld -> SiLU -> staging ->
+    // barrier -> TMA store is latency-bound (1.2 us), and it paced the 3x3 tiles
+    static constexpr int EG = 1;  // measured: two groups of four warps (alternate tiles) hold each accumulator twice as long -> 3x3 64 ch 12.7 -> 18.0 us; one group of eight is kept
     static constexpr int TMEM_COLS = 2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256);
-    static_assert(total(1) <= DT_SMEM_LIMIT, "tile does not fit shared memory");
-    static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128 && CIN <= 128, "channel counts");
+    static_assert(total(1, 2) <= DT_SMEM_LIMIT, "tile does not fit shared memory");
+    static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128 && CIN <= 256, "channel counts");
 };
 
 struct DtMaps {
     CUtensorMap x;     // input [C, W, H, N], box [CW, IC, IR, 1], no swizzle
-    CUtensorMap b[2];  // pointwise weights [Cin, Cout], box [chunk width, Cout], swizzle = chunk row bytes
+    CUtensorMap b[4];  // pointwise weights [Cin, Cout], box [chunk width, Cout], swizzle = chunk row bytes
     CUtensorMap y[2];  // output [Cout, W, H, N], box [chunk width, TW, TH, 1], swizzle = chunk row bytes
     CUtensorMap r[2];  // residual, like y
 };
@@ -112,9 +117,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
     constexpr int NBUF = C::NBUF;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // carve (every region 1024-byte aligned): [2 x input][NBUF x A][B][NBUF x out][NBUF x res][dw weights | biases | barriers]
+    // carve (every region 1024-byte aligned): [NIN x input][NBUF x A][B][NBUF x out][NBUF x res][dw weights | biases | barriers]
     uint8_t* sIn = smem;
-    uint8_t* sA = sIn + 2 * C::IN_BYTES;
+    uint8_t* sA = sIn + C::NIN * C::IN_BYTES;
     uint8_t* sB = sA + NBUF * C::A_BYTES;
     uint8_t* sOut = sB + C::B_BYTES;
     uint8_t* sRes = sOut + NBUF * C::O_BYTES;
@@ -123,31 +128,33 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
     float* sBp = sWd + K * K * CIN;
     float* sBd = sBp + COUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sBd + CIN) + 15) & ~(uintptr_t)15);
-    uint64_t* in_full = bars;         // [2]  TMA -> depthwise
-    uint64_t* in_empty = bars + 2;    // [2]  depthwise -> TMA           (count = depthwise warps)
-    uint64_t* a_full = bars + 4;      // [2]  depthwise -> MMA           (count = depthwise warps)
-    uint64_t* a_empty = bars + 6;     // [2]  MMA (tcgen05.commit) -> depthwise
-    uint64_t* t_full = bars + 8;      // [2]  MMA (tcgen05.commit) -> epilogue
-    uint64_t* t_empty = bars + 10;    // [2]  epilogue -> MMA            (count = epilogue warps)
-    uint64_t* r_full = bars + 12;     // [2]  TMA -> epilogue
-    uint64_t* r_empty = bars + 14;    // [2]  epilogue -> TMA            (count = epilogue warps)
-    uint64_t* w_full = bars + 16;     // pointwise weights landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* in_full = bars;         // [3]  TMA -> depthwise
+    uint64_t* in_empty = bars + 3;    // [3]  depthwise -> TMA           (count = depthwise warps)
+    uint64_t* a_full = bars + 6;      // [2]  depthwise -> MMA           (count = depthwise warps)
+    uint64_t* a_empty = bars + 8;     // [2]  MMA (tcgen05.commit) -> depthwise
+    uint64_t* t_full = bars + 10;     // [2]  MMA (tcgen05.commit) -> epilogue
+    uint64_t* t_empty = bars + 12;    // [2]  epilogue -> MMA            (count = warps of one epilogue group)
+    uint64_t* r_full = bars + 14;     // [2]  TMA -> epilogue
+    uint64_t* r_empty = bars + 16;    // [2]  epilogue -> TMA            (count = warps of one epilogue group)
+    uint64_t* w_full = bars + 18;     // pointwise weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.x);
         prefetch_tmap(&maps.b[0]);
         prefetch_tmap(&maps.y[0]);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 3; ++s) {
             mbar_init(&in_full[s], 1);
             mbar_init(&in_empty[s], DT_DW_WARPS);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(&a_full[s], DT_DW_WARPS);
             mbar_init(&a_empty[s], 1);
             mbar_init(&t_full[s], 1);
-            mbar_init(&t_empty[s], DT_EPI_WARPS);
+            mbar_init(&t_empty[s], DT_EPI_WARPS / C::EG);
             mbar_init(&r_full[s], 1);
-            mbar_init(&r_empty[s], DT_EPI_WARPS);
+            mbar_init(&r_empty[s], DT_EPI_WARPS / C::EG);
         }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
             const int y0 = (t / p.tiles_x) * DT_TH, x0 = (t % p.tiles_x) * DT_TW;
 #pragma unroll 1
             for (int c = 0; c < C::NST; ++c, ++q) {
-                const uint32_t s = q & 1, ph = (q >> 1) & 1;
+                const uint32_t s = q % C::NIN, ph = (q / C::NIN) & 1;
                 mbar_wait_parked(&in_empty[s], ph ^ 1);
                 if (c == 0 && lane == 0) dt_stamp(p, 0, it, 0);
                 if (elect_one()) {
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
             if (dtid == 0) dt_stamp(p, 2, it, 0);
 #pragma unroll 1
             for (int c = 0; c < C::NST; ++c, ++q) {
-                const uint32_t s = q & 1, ph = (q >> 1) & 1;
+                const uint32_t s = q % C::NIN, ph = (q / C::NIN) & 1;
                 const int cwid = CIN - C::CW * c < C::CW ? CIN - C::CW * c : C::CW;  // channels staged in this round
                 const int np = cwid >> 1;                                            // channel pairs
                 const uint32_t in_s = smem_u32(sIn + s * C::IN_BYTES);
@@ -325,73 +332,88 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
         }
     } else {
         // ===================== epilogue warps =====================
-        const int lg = warp & 3;                          // TMEM lane group this warp may access
-        const int half = (warp - DT_EPI_WARP0) >> 2;      // which interleaved share of the 16-column groups this warp converts
-        constexpr int NG = (COUT / 16 + 1) / 2;           // 16-column groups per warp (the second half has one fewer when COUT/16 is odd)
+        constexpr int EG = C::EG, GW = DT_EPI_WARPS / EG;  // epilogue groups, warps per group
+        constexpr int NPASS = EG;                          // a group of four warps converts its columns in two passes (register budget)
+        constexpr int NG = (COUT / 16 + 1) / 2;            // 16-column groups per warp and pass
+        const int wi = warp - DT_EPI_WARP0;
+        const int lg = warp & 3;                           // TMEM lane group this warp may access
+        const int grp = EG == 2 ? (wi >> 2) : 0;           // EG = 2: group g drains the tiles with (iteration & 1) == g
+        const int half0 = EG == 2 ? 0 : (wi >> 2);         // EG = 1: the two warps of a lane group share the columns
         const uint32_t row = (uint32_t)(lg * 32 + lane);
         const bool valid = row < (uint32_t)DT_PIX;
-        const bool issuer = (warp == DT_EPI_WARP0 && lane == 0);
+        const bool issuer = (wi == grp * 4 && lane == 0);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+            if (EG == 2 && (int)(it & 1) != grp) continue;
             const uint32_t acc = it & 1, tph = (it >> 1) & 1;
             const uint32_t ob = it % NBUF, oph = (it / NBUF) & 1;
             if (RES) mbar_wait_parked(&r_full[ob], oph);
             mbar_wait_parked(&t_full[acc], tph);
             tc_fence_after();
             if (issuer) dt_stamp(p, 3, it, 0);
-            // all of this warp's accumulator columns with ONE wait (four dependent tcgen05.ld round trips cost ~1 us per tile)
-            uint32_t v[NG][16];
-#pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                const int c0 = (2 * gi + half) * 16;
-                if (c0 < COUT) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)COUT + c0, v[gi]);
-            }
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[acc]);  // the accumulator is in registers: the MMA warp may reuse these TMEM columns
-            if (issuer) {  // the bulk store that last read this staging buffer has finished reading it
-                if (NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * DT_EPI_WARPS) : "memory");
-            if (issuer) dt_stamp(p, 3, it, 1);
             const uint32_t o_s = smem_u32(sOut + ob * C::O_BYTES), r_s = smem_u32(sRes + (RES ? ob * C::O_BYTES : 0));
 #pragma unroll
-            for (int gi = 0; gi < NG; ++gi) {
-                const int c0 = (2 * gi + half) * 16;
-                if (c0 >= COUT) continue;
-                const int oc = c0 >> 6, rowb = dt_cw(COUT, oc) * 2;
-                const uint32_t j = (uint32_t)((c0 & 63) >> 3);
-                float f[16];
+            for (int pass = 0; pass < NPASS; ++pass) {
+                const int half = half0 + pass;
+                // this pass's accumulator columns with ONE wait (dependent tcgen05.ld round trips cost ~0.25 us each)
+                uint32_t v[NG][16];
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const float4 bq = lds_f4(sBp + c0 + 4 * qd);
-                    f[4 * qd + 0] = silu_fast(__uint_as_float(v[gi][4 * qd + 0]) + bq.x);
-                    f[4 * qd + 1] = silu_fast(__uint_as_float(v[gi][4 * qd + 1]) + bq.y);
-                    f[4 * qd + 2] = silu_fast(__uint_as_float(v[gi][4 * qd + 2]) + bq.z);
-                    f[4 * qd + 3] = silu_fast(__uint_as_float(v[gi][4 * qd + 3]) + bq.w);
+                for (int gi = 0; gi < NG; ++gi) {
+                    const int c0 = (2 * gi + half) * 16;
+                    if (c0 < COUT) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)COUT + c0, v[gi]);
                 }
-                if (valid) {
-                    const uint32_t off0 = (uint32_t)oc * DT_OCHUNK_BYTES + row * (uint32_t)rowb + (dt_swz(j, row, rowb) << 4);
-                    const uint32_t off1 = (uint32_t)oc * DT_OCHUNK_BYTES + row * (uint32_t)rowb + (dt_swz(j + 1, row, rowb) << 4);
-                    if (RES) {
-                        float rr[16];
-                        bf16x8 r0, r1;
-                        r0.u = lds128(r_s + off0), r1.u = lds128(r_s + off1);
-                        unpack8(r0, rr);
-                        unpack8(r1, rr + 8);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) f[i] = p.epi == DBL_EPI_MUL ? f[i] * rr[i] : f[i] + rr[i];
+                if (pass == 0) {
+                    if (issuer) {  // the bulk store that last read this staging buffer has finished reading it
+                        if (EG == 1 && NBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
-                    sts128(o_s + off0, pack8(f).u);
-                    sts128(o_s + off1, pack8(f + 8).u);
+                    if (EG == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * GW) : "memory");
+                    else asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
+                    if (issuer) dt_stamp(p, 3, it, 1);
+                }
+                tmem_ld_wait();
+                if (pass == NPASS - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[acc]);  // the accumulator is in registers: the MMA warp may reuse these TMEM columns
+                }
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    const int c0 = (2 * gi + half) * 16;
+                    if (c0 >= COUT) continue;
+                    const int oc = c0 >> 6, rowb = dt_cw(COUT, oc) * 2;
+                    const uint32_t j = (uint32_t)((c0 & 63) >> 3);
+                    float f[16];
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float4 bq = lds_f4(sBp + c0 + 4 * qd);
+                        f[4 * qd + 0] = silu_fast(__uint_as_float(v[gi][4 * qd + 0]) + bq.x);
+                        f[4 * qd + 1] = silu_fast(__uint_as_float(v[gi][4 * qd + 1]) + bq.y);
+                        f[4 * qd + 2] = silu_fast(__uint_as_float(v[gi][4 * qd + 2]) + bq.z);
+                        f[4 * qd + 3] = silu_fast(__uint_as_float(v[gi][4 * qd + 3]) + bq.w);
+                    }
+                    if (valid) {
+                        const uint32_t off0 = (uint32_t)oc * DT_OCHUNK_BYTES + row * (uint32_t)rowb + (dt_swz(j, row, rowb) << 4);
+                        const uint32_t off1 = (uint32_t)oc * DT_OCHUNK_BYTES + row * (uint32_t)rowb + (dt_swz(j + 1, row, rowb) << 4);
+                        if (RES) {
+                            float rr[16];
+                            bf16x8 r0, r1;
+                            r0.u = lds128(r_s + off0), r1.u = lds128(r_s + off1);
+                            unpack8(r0, rr);
+                            unpack8(r1, rr + 8);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) f[i] = p.epi == DBL_EPI_MUL ? f[i] * rr[i] : f[i] + rr[i];
+                        }
+                        sts128(o_s + off0, pack8(f).u);
+                        sts128(o_s + off1, pack8(f + 8).u);
+                    }
                 }
             }
             __syncwarp();
             if (RES && lane == 0) mbar_arrive(&r_empty[ob]);
             fence_proxy_async();
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * DT_EPI_WARPS) : "memory");
+            if (EG == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(32 * GW) : "memory");
+            else asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
             if (issuer) {
                 const int img = tile / per_img, t = tile - img * per_img;
                 const int y0 = (t / p.tiles_x) * DT_TH, x0 = (t % p.tiles_x) * DT_TW;
@@ -514,7 +536,7 @@ using namespace dbl;
 
 // (k, cin, cout): DSBottleneck halves at n / s scale and the Detect class-branch pairs (nc = 80: c3 = 80; nc <= 64: c3 = 64)
 #define DBL_DT_TABLE(X) \
-    X(3, 32, 32) X(7, 32, 32) X(3, 64, 64) X(7, 64, 64) X(3, 128, 128) X(7, 128, 128) X(3, 64, 80) X(3, 80, 80) X(3, 128, 80) X(3, 128, 64)
+    X(3, 32, 32) X(7, 32, 32) X(3, 64, 64) X(7, 64, 64) X(3, 128, 128) X(7, 128, 128) X(3, 64, 80) X(3, 80, 80) X(3, 128, 80) X(3, 128, 64) X(3, 256, 80) X(3, 256, 64)
 
 extern "C" int dbl_dsconv_tc_debug_trace(void* device_buffer) {
     g_dt_trace = reinterpret_cast<unsigned long long*>(device_buffer);
