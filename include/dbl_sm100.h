@@ -133,7 +133,8 @@ int dbl_dsconv(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw
  * tiles (zero fill = padding), depthwise on the fp32 pipes writing the UMMA-swizzled A tile in place, pointwise on tcgen05 with the
  * accumulator in TMEM, TMA-store epilogue -- whose phases overlap across consecutive tiles.  Differences to dbl_dsconv:
  * w_pw is the PLAIN bf16 [cout][cin] matrix (the dbl_conv2d layout, BN folded), not the mma.sync fragment order; dw_act and a residual
- * are not combined.  (k, cin, cout) from dbl_dsconv_tc_supported(); x and y must not alias (r may alias y). */
+ * are not combined; the stride (1 or 2) is implied by the shape of y.  (k, stride, cin, cout) from dbl_dsconv_tc_supported(); x and y
+ * must not alias (r may alias y). */
 int dbl_dsconv_tc_supported(int k, int stride, int cin, int cout);
 int dbl_dsconv_tc(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw_act, const void* w_pw, const float* b_pw,
                   const dbl_tensor* r, const dbl_tensor* y, int k, int epi, dbl_stream_t stream);

@@ -462,18 +462,28 @@ def test_dsconv_fused(k, s, cin, cout, dw_act, epi, n, h, w):
     (3, 64, 64, 0, L.EPI_MUL, 1, 7, 9), (7, 64, 64, 0, L.EPI_NONE, 40, 20, 20), (3, 256, 80, 1, L.EPI_NONE, 2, 20, 20),
     (3, 256, 64, 1, L.EPI_NONE, 1, 10, 10)])
 def test_dsconv_tc(k, cin, cout, dw_act, epi, n, h, w):
+    _run_dsconv_tc(k, 1, cin, cout, dw_act, epi, n, h, w)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 80, 80), (1, 33, 50), (3, 40, 24), (1, 6, 10)])
+def test_dsconv_tc_stride2(n, h, w):
+    """DSConv [512, 3, 2] of the backbone (layer 8 at n scale: 128 -> 128): the strided instantiation, even and odd map sizes"""
+    _run_dsconv_tc(3, 2, 128, 128, 0, L.EPI_NONE, n, h, w)
+
+
+def _run_dsconv_tc(k, s, cin, cout, dw_act, epi, n, h, w):
     """every (k, cin, cout) instantiation; tiles that hang over the image on every side (TMA zero fill / store clipping), more tiles
     than SMs (persistent loop, both pipeline parities), channel-slice views with a foreign pitch, and the engine's in-place residual
     (r aliases y)."""
     lib = L.require_device()
-    assert lib.dbl_dsconv_tc_supported(k, 1, cin, cout) == 1 and lib.dbl_dsconv_tc_supported(k, 2, cin, cout) == 0
+    assert lib.dbl_dsconv_tc_supported(k, s, cin, cout) == 1 and lib.dbl_dsconv_tc_supported(k, 3, cin, cout) == 0
     g = torch.Generator().manual_seed(k * 100 + cin + cout + n)
     x = bf16_round(torch.randn(n, cin, h, w, generator=g))
     wdw = torch.randn(cin, 1, k, k, generator=g) / k
     bdw = torch.randn(cin, generator=g) * 0.3 if dw_act else None
     wpw = bf16_round(torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5)
     bpw = torch.randn(cout, generator=g) * 0.3
-    d = F.conv2d(x, wdw, bdw, 1, (k - 1) // 2, 1, cin)
+    d = F.conv2d(x, wdw, bdw, s, (k - 1) // 2, 1, cin)
     if dw_act:
         d = F.silu(d)
     d = bf16_round(d)  # the depthwise result is held as bf16 in shared memory (the A operand of the pointwise GEMM)
@@ -484,7 +494,7 @@ def test_dsconv_tc(k, cin, cout, dw_act, epi, n, h, w):
     elif epi == L.EPI_MUL:
         ref = ref * r
     xbuf, xv = to_nhwc(x, pad_c=8, c_off=0)
-    ybuf, yv = empty_nhwc(n, h, w, cout, pad_c=16, c_off=8)
+    ybuf, yv = empty_nhwc(n, ref.shape[2], ref.shape[3], cout, pad_c=16, c_off=8)
     rv = None
     if epi:  # in place, like DSBottleneck's `x = x + cv2(cv1(x))` in the engine: the residual IS the output view
         ybuf[..., 8:8 + cout] = r.permute(0, 2, 3, 1).to(dev(), torch.bfloat16)

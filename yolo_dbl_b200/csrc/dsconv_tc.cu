@@ -40,13 +40,13 @@ constexpr int DT_SMEM_LIMIT = 227 * 1024;
 __host__ __device__ constexpr int dt_round1k(int v) { return (v + 1023) / 1024 * 1024; }
 __host__ __device__ constexpr int dt_cw(int c, int chunk) { return c - 64 * chunk < 64 ? c - 64 * chunk : 64; }  // channels of a 64-channel chunk
 
-template <int K, int CIN, int COUT, bool RES>
+template <int K, int CIN, int COUT, bool RES, int S = 1>
 struct DtCfg {
-    static constexpr int PAD = (K - 1) / 2, IC = DT_TW + K - 1, IR = DT_TH + K - 1;
+    static constexpr int PAD = (K - 1) / 2, IC = (DT_TW - 1) * S + K, IR = (DT_TH - 1) * S + K;
     static constexpr int NCH = (CIN + 63) / 64;     // K chunks of the pointwise GEMM (64 channels = one 128-byte swizzle row)
     // channels per staged input box: the whole CIN when two such stages fit next to everything else (one stage round per tile),
     // else 64-channel chunks
-    static constexpr int CW = (CIN <= 64 || 2 * dt_round1k((DT_TH + K - 1) * (DT_TW + K - 1) * CIN * 2) > 96 * 1024) ? (CIN < 64 ? CIN : 64) : CIN;
+    static constexpr int CW = (CIN <= 64 || 2 * dt_round1k(IR * IC * CIN * 2) > 96 * 1024) ? (CIN < 64 ? CIN : 64) : CIN;
     static constexpr int NST = (CIN + CW - 1) / CW;  // stage rounds per tile
     static constexpr int NOC = (COUT + 63) / 64;    // output-channel chunks (staging / store granularity)
     static constexpr int IN_TX = IR * IC * CW * 2;  // bytes one input box delivers
@@ -111,9 +111,9 @@ __device__ __forceinline__ uint64_t dt_desc(uint32_t saddr, uint32_t row_bytes) 
     return d;
 }
 
-template <int K, int CIN, int COUT, int DW_ACT, bool RES>
+template <int K, int CIN, int COUT, int DW_ACT, bool RES, int S>
 __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_constant__ DtMaps maps, const DtParams p) {
-    using C = DtCfg<K, CIN, COUT, RES>;
+    using C = DtCfg<K, CIN, COUT, RES, S>;
     constexpr int NBUF = C::NBUF;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
                 if (c == 0 && lane == 0) dt_stamp(p, 0, it, 0);
                 if (elect_one()) {
                     mbar_expect_tx(&in_full[s], (uint32_t)C::IN_TX);
-                    tma_load_4d(&maps.x, &in_full[s], sIn + s * C::IN_BYTES, C::CW * c, x0 - C::PAD, y0 - C::PAD, img);
+                    tma_load_4d(&maps.x, &in_full[s], sIn + s * C::IN_BYTES, C::CW * c, x0 * S - C::PAD, y0 * S - C::PAD, img);
                 }
                 __syncwarp();
             }
@@ -284,31 +284,51 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dsconv_tc_kernel(const __grid_c
 #pragma unroll
                         for (int r = 0; r < DT_TH; ++r) acc[r][0] = acc[r][1] = b2;
                     }
-                    const uint32_t xbase = in_s + (uint32_t)(2 * xp * C::CW + 2 * cp) * 2;  // staged box: CW channels per pixel
+                    const uint32_t xbase = in_s + (uint32_t)(2 * S * xp * C::CW + 2 * cp) * 2;  // staged box: CW channels per pixel
                     unsigned long long wprev[K], wcur[K];
 #pragma unroll
-                    for (int kxp = 0; kxp <= K; ++kxp) {  // input column 2*xp + kxp feeds output column 0 with filter column kxp and output column 1 with kxp - 1
-                        if (kxp < K) {
+                    for (int kxp = 0; kxp < K + S; ++kxp) {  // input column 2*S*xp + kxp feeds output column 0 with filter column kxp and output column 1 with kxp - S
+                        if (S == 1) {
+                            if (kxp < K) {
+#pragma unroll
+                                for (int ky = 0; ky < K; ++ky) {
+                                    const uint2 w0 = lds64(wd_s + (uint32_t)(((ky * K + kxp) * CIN + ch0) * 4));
+                                    wcur[ky] = ((unsigned long long)w0.y << 32) | w0.x;
+                                }
+                            }
+                        } else {  // stride 2: the two filter columns in flight are not neighbours; k = 3, so reloading is cheap
 #pragma unroll
                             for (int ky = 0; ky < K; ++ky) {
-                                const uint2 w0 = lds64(wd_s + (uint32_t)(((ky * K + kxp) * CIN + ch0) * 4));
-                                wcur[ky] = ((unsigned long long)w0.y << 32) | w0.x;
-                            }
-                        }
-#pragma unroll
-                        for (int iy = 0; iy < C::IR; ++iy) {
-                            const unsigned long long xv = bf16x2_to_f32x2(lds32(xbase + (uint32_t)((iy * C::IC + kxp) * C::CW) * 2));
-#pragma unroll
-                            for (int r = 0; r < DT_TH; ++r) {
-                                const int d = iy - r;
-                                if (d >= 0 && d < K) {
-                                    if (kxp < K) ffma2(acc[r][0], xv, wcur[d]);
-                                    if (kxp >= 1) ffma2(acc[r][1], xv, wprev[d]);
+                                if (kxp < K) {
+                                    const uint2 w0 = lds64(wd_s + (uint32_t)(((ky * K + kxp) * CIN + ch0) * 4));
+                                    wcur[ky] = ((unsigned long long)w0.y << 32) | w0.x;
+                                }
+                                if (kxp >= S && kxp - S < K) {
+                                    const uint2 w1 = lds64(wd_s + (uint32_t)(((ky * K + kxp - S) * CIN + ch0) * 4));
+                                    wprev[ky] = ((unsigned long long)w1.y << 32) | w1.x;
                                 }
                             }
                         }
 #pragma unroll
-                        for (int ky = 0; ky < K; ++ky) wprev[ky] = wcur[ky];
+                        for (int iy = 0; iy < C::IR; ++iy) {
+                            bool used = false;
+#pragma unroll
+                            for (int r = 0; r < DT_TH; ++r) used = used || (iy - S * r >= 0 && iy - S * r < K);
+                            if (!used) continue;
+                            const unsigned long long xv = bf16x2_to_f32x2(lds32(xbase + (uint32_t)((iy * C::IC + kxp) * C::CW) * 2));
+#pragma unroll
+                            for (int r = 0; r < DT_TH; ++r) {
+                                const int d = iy - S * r;
+                                if (d >= 0 && d < K) {
+                                    if (kxp < K) ffma2(acc[r][0], xv, wcur[d]);
+                                    if (kxp >= S && kxp - S < K) ffma2(acc[r][1], xv, wprev[d]);
+                                }
+                            }
+                        }
+                        if (S == 1) {
+#pragma unroll
+                            for (int ky = 0; ky < K; ++ky) wprev[ky] = wcur[ky];
+                        }
                     }
 #pragma unroll
                     for (int r = 0; r < DT_TH; ++r) {
@@ -485,11 +505,11 @@ static bool dt_map_nhwc(CUtensorMap* m, const dbl_tensor* t, int c0, int cw, int
 
 static unsigned long long* g_dt_trace = nullptr;  // developer aid, see dbl_dsconv_tc_debug_trace
 
-template <int K, int CIN, int COUT, int DW_ACT, bool RES>
+template <int K, int CIN, int COUT, int DW_ACT, bool RES, int S = 1>
 static int launch_dt(const dbl_tensor* x, const float* wdw, const float* bdw, const void* wpw, const float* bpw, const dbl_tensor* r,
                      const dbl_tensor* y, int epi, cudaStream_t st) {
-    using C = DtCfg<K, CIN, COUT, RES>;
-    auto kern = dsconv_tc_kernel<K, CIN, COUT, DW_ACT, RES>;
+    using C = DtCfg<K, CIN, COUT, RES, S>;
+    auto kern = dsconv_tc_kernel<K, CIN, COUT, DW_ACT, RES, S>;
     static DevOnce once;  // one per template instantiation, one bit per device
     if (once.need()) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
@@ -519,7 +539,7 @@ static int launch_dt(const dbl_tensor* x, const float* wdw, const float* bdw, co
     memset(&p, 0, sizeof(p));
     p.wdw = wdw, p.bdw = bdw, p.bpw = bpw;
     p.n = x->n, p.h = x->h, p.w = x->w, p.epi = epi, p.trace = g_dt_trace;
-    p.tiles_x = cdiv(x->w, DT_TW), p.tiles_y = cdiv(x->h, DT_TH);
+    p.tiles_x = cdiv(y->w, DT_TW), p.tiles_y = cdiv(y->h, DT_TH);
     const long long nt = (long long)x->n * p.tiles_x * p.tiles_y;
     DBL_REQUIRE(nt < (1ll << 31), DBL_E_UNSUPPORTED, "dbl_dsconv_tc: too many tiles");
     p.ntiles = (int)nt;
@@ -544,6 +564,7 @@ extern "C" int dbl_dsconv_tc_debug_trace(void* device_buffer) {
 }
 
 extern "C" int dbl_dsconv_tc_supported(int k, int stride, int cin, int cout) {
+    if (stride == 2) return k == 3 && cin == 128 && cout == 128;  // DSConv [512, 3, 2] of the backbone at n scale (layer 8)
     if (stride != 1) return 0;
 #define X(K_, CI_, CO_) \
     if (k == K_ && cin == CI_ && cout == CO_) return 1;
@@ -556,7 +577,11 @@ extern "C" int dbl_dsconv_tc(const dbl_tensor* x, const float* w_dw, const float
                              const dbl_tensor* r, const dbl_tensor* y, int k, int epi, dbl_stream_t stream) {
     DBL_REQUIRE(valid_tensor(x) && valid_tensor(y) && w_dw && w_pw, DBL_E_ARG, "dbl_dsconv_tc: null/invalid argument");
     DBL_REQUIRE(vec8_ok(x) && vec8_ok(y), DBL_E_ARG, "dbl_dsconv_tc: x and y must be bf16 NHWC views, 16-byte aligned, pitch %% 8 == 0");
-    DBL_REQUIRE(y->n == x->n && y->h == x->h && y->w == x->w, DBL_E_ARG, "dbl_dsconv_tc: output shape mismatch (stride 1, same padding)");
+    DBL_REQUIRE(y->n == x->n, DBL_E_ARG, "dbl_dsconv_tc: batch mismatch");
+    const bool s2 = y->h != x->h || y->w != x->w;  // stride 2 is recognised by the output shape: (h + 2*pad - k) / 2 + 1
+    if (s2)
+        DBL_REQUIRE(y->n == x->n && y->h == (x->h + 2 * ((k - 1) / 2) - k) / 2 + 1 && y->w == (x->w + 2 * ((k - 1) / 2) - k) / 2 + 1, DBL_E_ARG,
+                    "dbl_dsconv_tc: output shape matches neither stride 1 nor stride 2");
     DBL_REQUIRE(((reinterpret_cast<uintptr_t>(w_dw) | reinterpret_cast<uintptr_t>(w_pw)) & 15) == 0, DBL_E_ARG, "dbl_dsconv_tc: weights must be 16-byte aligned");
     DBL_REQUIRE(!dw_act || b_dw, DBL_E_ARG, "dbl_dsconv_tc: dw_act needs the depthwise bias");
     if (epi != DBL_EPI_NONE) DBL_REQUIRE(valid_tensor(r) && same_shape(r, y) && vec8_ok(r), DBL_E_ARG, "dbl_dsconv_tc: residual mismatch");
@@ -565,6 +590,10 @@ extern "C" int dbl_dsconv_tc(const dbl_tensor* x, const float* w_dw, const float
     cudaStream_t st = as_stream(stream);
     const bool res = epi != DBL_EPI_NONE;
     DBL_REQUIRE(!(dw_act && res), DBL_E_UNSUPPORTED, "dbl_dsconv_tc: dw_act with a residual is not instantiated");
+    if (s2) {
+        DBL_REQUIRE(k == 3 && x->c == 128 && y->c == 128 && !dw_act && !res, DBL_E_UNSUPPORTED, "dbl_dsconv_tc: stride 2 is instantiated for k 3, 128 -> 128, no residual");
+        return launch_dt<3, 128, 128, 0, false, 2>(x, w_dw, b_dw, w_pw, b_pw, nullptr, y, epi, st);
+    }
 #define X(K_, CI_, CO_)                                                                                                       \
     if (k == K_ && x->c == CI_ && y->c == CO_) {                                                                              \
         if (dw_act) return launch_dt<K_, CI_, CO_, 1, false>(x, w_dw, b_dw, w_pw, b_pw, nullptr, y, epi, st);                 \

@@ -211,7 +211,7 @@ class DBLEngine:
         k, cin, cout = wdw.shape[-1], wdw.shape[0], wpw.shape[0]
         # Blackwell data path first (csrc/dsconv_tc.cu: TMA + tcgen05 + TMEM, persistent, phases of consecutive tiles overlap): faster
         # than both the warp-MMA kernel and the two-launch form on every shape measured (tools/ds_bench.py, 1.2x .. 2.3x)
-        if (self.fuse_thin and self.ds_impl != "mma" and self.fuse_ds != "0" and s == 1 and x.buf.data_ptr() != y.buf.data_ptr()
+        if (self.fuse_thin and self.ds_impl != "mma" and self.fuse_ds != "0" and x.buf.data_ptr() != y.buf.data_ptr()
                 and not (bdw is not None and r is not None) and self.lib.dbl_dsconv_tc_supported(k, s, cin, cout)):
             wd = self._dev(wdw.reshape(cin, k * k).t(), torch.float32)
             bd = self._dev(bdw, torch.float32) if bdw is not None else None
