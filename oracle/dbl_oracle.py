@@ -69,7 +69,21 @@ _ROWS_DBL2[20] = (-1, 1, "DSC3k2", (512,))
 _ROWS_DBL2[25] = (13, 1, "DSC3k2", (256, 1.0))  # args [256, 1, 1]: dsc3k = True, e = 1
 _ROWS_DBL2[29] = (-1, 1, "DSC3k2", (512,))
 _ROWS_DBL2[33] = (-1, 1, "C3Ghost", (1024,))
-_CFGS = {"DBL": (_ROWS, _SCALES), "DBL2": (_ROWS_DBL2, _SCALES_DBL2)}
+# cfg/models/v13/yolov13.yaml:10-60 (stock YOLOv13: grouped stem convs, DSC3k2 with plain DSBottlenecks, A2C2f area attention, nn.Upsample)
+_SCALES_V13 = {"n": (0.50, 0.25), "s": (0.50, 0.50), "l": (1.00, 1.00), "x": (1.00, 1.50)}
+_ROWS_V13 = [
+    (-1, 1, "Conv", (64, 3, 2)), (-1, 1, "Conv", (128, 3, 2, 2)), (-1, 2, "DSC3k2", (256, 0.25, False)), (-1, 1, "Conv", (256, 3, 2, 4)),
+    (-1, 2, "DSC3k2", (512, 0.25, False)), (-1, 1, "DSConv", (512, 3, 2)), (-1, 4, "A2C2f", (512, 4)), (-1, 1, "DSConv", (1024, 3, 2)),
+    (-1, 4, "A2C2f", (1024, 1)),
+    ((4, 6, 8), 2, "HyperACE", (512, 8)), (-1, 1, "Upsample", ()), (9, 1, "DownsampleConv", ()),
+    ((6, 9), 1, "FullPAD", ()), ((4, 10), 1, "FullPAD", ()), ((8, 11), 1, "FullPAD", ()),
+    (-1, 1, "Upsample", ()), ((-1, 12), 1, "Concat", ()), (-1, 2, "DSC3k2", (512,)), ((-1, 9), 1, "FullPAD", ()),
+    (17, 1, "Upsample", ()), ((-1, 13), 1, "Concat", ()), (-1, 2, "DSC3k2", (256,)), (10, 1, "Conv", (256, 1, 1)),
+    ((21, 22), 1, "FullPAD", ()), (-1, 1, "Conv", (256, 3, 2)), ((-1, 18), 1, "Concat", ()), (-1, 2, "DSC3k2", (512,)),
+    ((-1, 9), 1, "FullPAD", ()), (26, 1, "Conv", (512, 3, 2)), ((-1, 14), 1, "Concat", ()), (-1, 2, "DSC3k2", (1024,)),
+    ((-1, 11), 1, "FullPAD", ()), ((23, 27, 31), 1, "Detect", ()),
+]
+_CFGS = {"DBL": (_ROWS, _SCALES), "DBL2": (_ROWS_DBL2, _SCALES_DBL2), "V13": (_ROWS_V13, _SCALES_V13)}
 
 
 @dataclass
@@ -97,12 +111,14 @@ def build_layers(scale: str = "n", cfg: str = "DBL") -> List[Layer]:
         n = max(round(n * depth), 1) if n > 1 else n
         cin = (lambda j: 3 if (i == 0) else ch[j])
         extra = {}
-        if kind in ("Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost"):
+        if kind in ("Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost", "A2C2f"):
             c1, c2 = cin(f), _divisible8(args[0] * width)
             if kind in ("Conv", "DSConv"):
-                extra = {"k": args[1], "s": args[2]}
+                extra = {"k": args[1], "s": args[2], "g": args[3] if len(args) > 3 else 1}
             if kind == "DSC3k2":
-                extra = {"e": args[1] if len(args) > 1 else 0.5}
+                extra = {"e": args[1] if len(args) > 1 else 0.5, "dsc3k": args[2] if len(args) > 2 else True}
+            if kind == "A2C2f":
+                extra = {"area": args[1], "residual": scale in "lx"}
         elif kind == "HyperACE":
             c1, c2 = ch[f[1]], _divisible8(args[0] * width)
             he = args[1]
@@ -120,7 +136,7 @@ def build_layers(scale: str = "n", cfg: str = "DBL") -> List[Layer]:
         elif kind == "Detect":
             c1 = [ch[j] for j in f]
             c2 = 0
-        else:  # LSKblock, DySample: channel preserving (tasks.py:1156-1187)
+        else:  # LSKblock, DySample, nn.Upsample: channel preserving (tasks.py:1156-1187, 1201)
             c1 = c2 = ch[f]
         out.append(Layer(i, f, kind, n, c1, c2, extra))
         ch.append(c2)
@@ -192,12 +208,58 @@ def c3ghost(sd, p, x, n):
     return conv_bn_silu(sd, p + ".cv3", torch.cat((a, conv_bn_silu(sd, p + ".cv2", x)), 1))
 
 
-def dsc3k2(sd, p, x, n):
-    """``DSC3k2`` (dsc3k=True) block.py:1505-1580 on top of ``C2f.forward`` block.py:245-249."""
+def dsc3k2(sd, p, x, n, use_dsc3k=True):
+    """``DSC3k2`` block.py:1505-1580 on top of ``C2f.forward`` block.py:245-249; m = DSC3k (dsc3k=True) or plain DSBottleneck
+    (e=1, k1=3, k2=7; block.py:1565-1577)."""
     y = list(conv_bn_silu(sd, p + ".cv1", x).chunk(2, 1))
     for j in range(n):
-        y.append(dsc3k(sd, f"{p}.m.{j}", y[-1], 2, True))
+        y.append(dsc3k(sd, f"{p}.m.{j}", y[-1], 2, True) if use_dsc3k else ds_bottleneck(sd, f"{p}.m.{j}", y[-1], True))
     return conv_bn_silu(sd, p + ".cv2", torch.cat(y, 1))
+
+
+def aattn(sd, p, x, heads, area):
+    """``AAttn.forward`` block.py:1236-1268 -- qkv 1x1 Conv (no act), tokens split into `area` row bands, per-head softmax(q k^T / sqrt(hd)) v,
+    + pe (7x7 depthwise Conv, no act) of v, proj 1x1 Conv (no act)."""
+    B, C, H, W = x.shape
+    N = H * W
+    hd = C // heads
+    qkv = conv_bn_silu(sd, p + ".qkv", x, act=False).flatten(2).transpose(1, 2)
+    Bq, Nq = B, N
+    if area > 1:
+        qkv = qkv.reshape(B * area, N // area, C * 3)
+        Bq, Nq = qkv.shape[:2]
+    q, k, v = qkv.view(Bq, Nq, heads, hd * 3).permute(0, 2, 3, 1).split([hd, hd, hd], dim=2)
+    attn = ((q.transpose(-2, -1) @ k) * (hd ** -0.5)).softmax(dim=-1)
+    o = (v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)
+    v = v.permute(0, 3, 1, 2)
+    if area > 1:
+        o = o.reshape(Bq // area, Nq * area, C)
+        v = v.reshape(Bq // area, Nq * area, C)
+    o = o.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    v = v.reshape(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    o = o + conv_bn_silu(sd, p + ".pe", v, g=C, act=False)
+    return conv_bn_silu(sd, p + ".proj", o, act=False)
+
+
+def ablock(sd, p, x, heads, area):
+    """``ABlock.forward`` block.py:1318-1322"""
+    x = x + aattn(sd, p + ".attn", x, heads, area)
+    return x + conv_bn_silu(sd, p + ".mlp.1", conv_bn_silu(sd, p + ".mlp.0", x), act=False)
+
+
+def a2c2f(sd, p, x, n, area):
+    """``A2C2f.forward`` block.py:1392-1405 (a2=True: m = n x Sequential(ABlock, ABlock), heads = c_ // 32; gamma residual at l / x)"""
+    y = [conv_bn_silu(sd, p + ".cv1", x)]
+    heads = y[0].shape[1] // 32
+    for j in range(n):
+        t = y[-1]
+        for b in range(2):
+            t = ablock(sd, f"{p}.m.{j}.{b}", t, heads, area)
+        y.append(t)
+    o = conv_bn_silu(sd, p + ".cv2", torch.cat(y, 1))
+    if p + ".gamma" in sd:
+        return x + sd[p + ".gamma"].view(1, -1, 1, 1) * o
+    return o
 
 
 def lskblock(sd, p, x):
@@ -361,7 +423,7 @@ def _rounded(fn):
     return wrapped
 
 
-ghost_conv = _rounded(ghost_conv)
+ghost_conv, aattn, ablock = _rounded(ghost_conv), _rounded(aattn), _rounded(ablock)
 conv_bn_silu, dsconv, bottleneck, ds_bottleneck = _rounded(conv_bn_silu), _rounded(dsconv), _rounded(bottleneck), _rounded(ds_bottleneck)
 lskblock, c3ah, dysample, downsample_conv, fullpad = _rounded(lskblock), _rounded(c3ah), _rounded(dysample), _rounded(downsample_conv), _rounded(fullpad)
 
@@ -385,7 +447,7 @@ def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool, cfg: s
             p = f"model.{L.i}"
             src = (lambda j: x if (L.i == 0) else outs[j if j >= 0 else L.i + j])
             if L.kind == "Conv":
-                o = conv_bn_silu(sd, p, src(L.f), L.extra["s"])
+                o = conv_bn_silu(sd, p, src(L.f), L.extra["s"], L.extra.get("g", 1))
             elif L.kind == "DSConv":
                 o = dsconv(sd, p, src(L.f), L.extra["s"])
             elif L.kind == "Bottleneck":
@@ -393,7 +455,11 @@ def _forward(sd: Dict[str, Tensor], x: Tensor, scale: str, collect: bool, cfg: s
                 for r in range(L.n):
                     o = bottleneck(sd, f"{p}.{r}" if L.n > 1 else p, o, True)
             elif L.kind == "DSC3k2":
-                o = dsc3k2(sd, p, src(L.f), L.n)
+                o = dsc3k2(sd, p, src(L.f), L.n, L.extra.get("dsc3k", True))
+            elif L.kind == "A2C2f":
+                o = a2c2f(sd, p, src(L.f), L.n, L.extra["area"])
+            elif L.kind == "Upsample":
+                o = F.interpolate(src(L.f), scale_factor=2.0, mode="nearest")
             elif L.kind == "C3Ghost":
                 o = c3ghost(sd, p, src(L.f), L.n)
             elif L.kind == "LSKblock":

@@ -104,6 +104,36 @@ def match_cases():
         print(f"match_{name}: tp@0.5 {int(correct[:, 0].sum())} tp@0.95 {int(correct[:, -1].sum())} of {nd} detections / {nl} labels")
 
 
+def fwd_sibling(name, yaml_name, seed, xseed, hw):
+    """a sibling graph of the repository on the synthetic recipe: the reference's fused / unfused outputs + per-layer samples"""
+    from ultralytics.nn.tasks import DetectionModel, yaml_model_load
+    from yolo_dbl_b200.synth import synth_state_dict
+
+    cfg = yaml_model_load(yaml_name)
+    m = DetectionModel(cfg, ch=3, nc=3, verbose=False).eval()
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, f"shapes_{name}.json"), "w") as f:
+        json.dump(shapes, f)
+    sd = synth_state_dict(shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    x = synth_images(1, hw[0], hw[1], seed=xseed)
+    per_layer = {}
+    hooks = [mod.register_forward_hook(lambda _m, _i, o, i=i: per_layer.__setitem__(i, o.detach().clone())) for i, mod in enumerate(m.model[:-1])]
+    with torch.inference_mode():
+        y_unfused = m(x)[0].clone()
+        for h in hooks:
+            h.remove()
+        m.fuse(verbose=False)
+        y = m(x)[0]
+    rec = dict(y=y.numpy(), y_unfused=y_unfused.numpy())
+    for i, t in per_layer.items():
+        flat = t.reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, 64).long()
+        rec[f"layer{i}_samples"], rec[f"layer{i}_index"], rec[f"layer{i}_shape"] = flat[idx].numpy(), idx.numpy(), np.array(t.shape)
+    np.savez_compressed(os.path.join(OUT, f"fwd_{name}_small.npz"), **rec)
+    print(f"fwd_{name}_small: y", tuple(y.shape), "max score", float(y[:, 4:].max()), "|fused-unfused|", float((y - y_unfused).abs().max()))
+
+
 def fwd_dbl2():
     """yolov13l_DBL2.yaml (C3Ghost / GhostBottleneck / DSC3k2 variants): the reference's output on the synthetic recipe (seed 9)"""
     from ultralytics.nn.tasks import DetectionModel, yaml_model_load
@@ -141,3 +171,4 @@ if __name__ == "__main__":
     nms_labels()
     fwd_nc80()
     fwd_dbl2()
+    fwd_sibling("n_V13_nc3", "yolov13n.yaml", 13, 14, (128, 160))  # stock yolov13.yaml: A2C2f area attention (area 4 and 1), grouped convs

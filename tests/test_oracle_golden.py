@@ -223,3 +223,25 @@ def test_dbl2_graph_matches_reference_inventory_and_forward():
         assert tuple(o.shape) == tuple(g[f"layer{i}_shape"]), f"layer {i}"
         samp = o.reshape(-1)[torch.from_numpy(g[f"layer{i}_index"])]
         torch.testing.assert_close(samp, torch.from_numpy(g[f"layer{i}_samples"]), rtol=5e-4, atol=5e-4, msg=lambda m, i=i: f"layer {i}: {m}")
+
+
+def test_yolov13_graph_matches_reference_inventory_and_forward():
+    """Stock yolov13.yaml: parameter inventory == the reference's state_dict; oracle forward (grouped convs, DSC3k2 with
+    plain DSBottlenecks, A2C2f / ABlock / AAttn with area 4 and 1, nn.Upsample) == the reference's output and per-layer samples."""
+    shapes = json.load(open(os.path.join(GOLDEN, "shapes_n_V13_nc3.json")))
+    spec = resolve("yolov13n.yaml", "n", 3)
+    mine = param_shapes(spec)
+    assert list(mine.keys()) == list(shapes.keys()) and all(list(mine[k]) == list(shapes[k]) for k in shapes)
+    assert [L.kind for L in spec.layers[:9]] == ["Conv", "Conv", "DSC3k2", "Conv", "DSC3k2", "DSConv", "A2C2f", "DSConv", "A2C2f"]
+    g = _load("fwd_n_V13_nc3_small.npz")
+    sd = synth_state_dict(shapes, 13)
+    x = synth_images(1, 128, 160, seed=14)
+    y, feats, outs = O.forward(sd, x, "n", collect=True, cfg="V13")
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == tuple(g[f"layer{i}_shape"]), f"layer {i}"
+        samp = o.reshape(-1)[torch.from_numpy(g[f"layer{i}_index"])]
+        torch.testing.assert_close(samp, torch.from_numpy(g[f"layer{i}_samples"]), rtol=5e-4, atol=5e-4, msg=lambda m, i=i: f"layer {i}: {m}")
+    torch.testing.assert_close(y, torch.from_numpy(g["y_unfused"]), rtol=2e-4, atol=5e-3)
+    # the l / x variants add the gamma residual and mlp_ratio 1.5 (tasks.py:1088-1092): shapes only (the model is 100+ MB)
+    big = param_shapes(resolve("yolov13l.yaml", "l", 3))
+    assert big["model.6.gamma"] == [512] and big["model.6.m.0.0.mlp.0.conv.weight"][0] == int(256 * 1.5)

@@ -107,10 +107,55 @@ YOLO_DBL2_CFG = {
     ],
 }
 
-BUILTIN_CFGS = {"yolov13_DBL.yaml": YOLO_DBL_CFG, "yolov13_DBL2.yaml": YOLO_DBL2_CFG}
+# cfg/models/v13/yolov13.yaml:1-60 -- the stock YOLOv13 graph shipped beside the DBL variants: strided / grouped stem convolutions,
+# DSC3k2 with plain DSBottlenecks (dsc3k = False, e = 0.25), A2C2f area-attention blocks (nn/modules/block.py:1170-1405), nearest
+# upsampling instead of DySample, no LSKblock.
+YOLOV13_CFG = {
+    "nc": 80,
+    "scales": {"n": [0.50, 0.25, 65536], "s": [0.50, 0.50, 65536], "l": [1.00, 1.00, 65536], "x": [1.00, 1.50, 65536]},
+    "backbone": [
+        [-1, 1, "Conv", [64, 3, 2]],
+        [-1, 1, "Conv", [128, 3, 2, 1, 2]],
+        [-1, 2, "DSC3k2", [256, False, 0.25]],
+        [-1, 1, "Conv", [256, 3, 2, 1, 4]],
+        [-1, 2, "DSC3k2", [512, False, 0.25]],
+        [-1, 1, "DSConv", [512, 3, 2]],
+        [-1, 4, "A2C2f", [512, True, 4]],
+        [-1, 1, "DSConv", [1024, 3, 2]],
+        [-1, 4, "A2C2f", [1024, True, 1]],
+    ],
+    "head": [
+        [[4, 6, 8], 2, "HyperACE", [512, 8, True, True, 0.5, 1, "both"]],
+        [-1, 1, "nn.Upsample", [None, 2, "nearest"]],
+        [9, 1, "DownsampleConv", []],
+        [[6, 9], 1, "FullPAD_Tunnel", []],
+        [[4, 10], 1, "FullPAD_Tunnel", []],
+        [[8, 11], 1, "FullPAD_Tunnel", []],
+        [-1, 1, "nn.Upsample", [None, 2, "nearest"]],
+        [[-1, 12], 1, "Concat", [1]],
+        [-1, 2, "DSC3k2", [512, True]],
+        [[-1, 9], 1, "FullPAD_Tunnel", []],
+        [17, 1, "nn.Upsample", [None, 2, "nearest"]],
+        [[-1, 13], 1, "Concat", [1]],
+        [-1, 2, "DSC3k2", [256, True]],
+        [10, 1, "Conv", [256, 1, 1]],
+        [[21, 22], 1, "FullPAD_Tunnel", []],
+        [-1, 1, "Conv", [256, 3, 2]],
+        [[-1, 18], 1, "Concat", [1]],
+        [-1, 2, "DSC3k2", [512, True]],
+        [[-1, 9], 1, "FullPAD_Tunnel", []],
+        [26, 1, "Conv", [512, 3, 2]],
+        [[-1, 14], 1, "Concat", [1]],
+        [-1, 2, "DSC3k2", [1024, True]],
+        [[-1, 11], 1, "FullPAD_Tunnel", []],
+        [[23, 27, 31], 1, "Detect", ["nc"]],
+    ],
+}
 
-SUPPORTED = {"Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost", "LSKblock", "HyperACE", "DySample", "DownsampleConv",
-             "FullPAD_Tunnel", "Concat", "Detect"}
+BUILTIN_CFGS = {"yolov13_DBL.yaml": YOLO_DBL_CFG, "yolov13_DBL2.yaml": YOLO_DBL2_CFG, "yolov13.yaml": YOLOV13_CFG}
+
+SUPPORTED = {"Conv", "Bottleneck", "DSConv", "DSC3k2", "C3Ghost", "A2C2f", "LSKblock", "HyperACE", "DySample", "nn.Upsample",
+             "DownsampleConv", "FullPAD_Tunnel", "Concat", "Detect"}
 
 
 @dataclass
@@ -211,6 +256,9 @@ def resolve(cfg=None, scale: str = "n", nc: int | None = None) -> GraphSpec:
         if kind in ("Conv", "DSConv"):
             L.c2 = make_divisible(min(args[0], max_ch) * width)
             L.k, L.s = int(args[1]), int(args[2])
+            L.extra["g"] = int(args[4]) if (kind == "Conv" and len(args) > 4) else 1  # Conv(c1, c2, k, s, p, g) (conv.py:39-52)
+            if len(args) > 3 and args[3] is not None and int(args[3]) != L.k // 2:
+                raise NotImplementedError(f"layer {i}: padding {args[3]} != k//2")
             st *= L.s
         elif kind == "Bottleneck":
             L.c2 = make_divisible(min(args[0], max_ch) * width)
@@ -218,9 +266,18 @@ def resolve(cfg=None, scale: str = "n", nc: int | None = None) -> GraphSpec:
         elif kind == "DSC3k2":
             L.c2 = make_divisible(min(args[0], max_ch) * width)
             L.extra["dsc3k"] = bool(args[1]) if len(args) > 1 else False
-            L.extra["e"] = float(args[2]) if len(args) > 2 else 0.5  # DSC3k2(c1, c2, n, dsc3k, e=0.5, ...) (block.py:1505-1530)
-            if not L.extra["dsc3k"]:
-                raise NotImplementedError("DSC3k2(dsc3k=False) is not used by YOLO-DBL")
+            L.extra["e"] = float(args[2]) if len(args) > 2 else 0.5  # DSC3k2(c1, c2, n, dsc3k, e=0.5, ...) (block.py:1505-1580)
+        elif kind == "A2C2f":  # A2C2f(c1, c2, n, a2, area, [residual, mlp_ratio for l/x]) (tasks.py:1088-1092, block.py:1350-1405)
+            L.c2 = make_divisible(min(args[0], max_ch) * width)
+            L.extra.update(a2=bool(args[1]), area=int(args[2]), residual=scale in "lx", mlp_ratio=1.5 if scale in "lx" else 2.0)
+            if not L.extra["a2"]:
+                raise NotImplementedError("A2C2f(a2=False) is not used by the v13 graphs")
+            if int(L.c2 * 0.5) % 32:
+                raise ValueError("Dimension of ABlock must be a multiple of 32")
+        elif kind == "nn.Upsample":
+            if list(args) != [None, 2, "nearest"]:
+                raise NotImplementedError("only nn.Upsample(None, 2, 'nearest')")
+            st = max(st // 2, 1)
         elif kind == "C3Ghost":
             L.c2 = make_divisible(min(args[0], max_ch) * width)
             L.shortcut = bool(args[1]) if len(args) > 1 else True  # unused by GhostBottleneck (its own identity shortcut)
@@ -234,7 +291,7 @@ def resolve(cfg=None, scale: str = "n", nc: int | None = None) -> GraphSpec:
                 he = int(he * 1.5)
             L.he = he
             L.extra.update(dsc3k=bool(args[2]), shortcut=bool(args[3]), e1=float(args[4]), e2=float(args[5]),
-                           context=args[6], channel_adjust=bool(args[7]), cins=cin)
+                           context=args[6], channel_adjust=bool(args[7]) if len(args) > 7 else True, cins=cin)  # default: block.py:1874
             if not (L.extra["dsc3k"] and L.extra["context"] == "both" and L.extra["channel_adjust"]):
                 raise NotImplementedError("HyperACE variant outside YOLO-DBL")
             if not L.extra["shortcut"]:  # the lowering always emits the residual DSBottleneck (DSBottleneck.add = shortcut and c1 == c2)
@@ -320,7 +377,7 @@ def param_shapes(spec: GraphSpec) -> Dict[str, list]:
         p = f"model.{L.i}"
         rep = (lambda r, L=L, p=p: f"{p}.{r}" if L.n > 1 else p)
         if L.kind == "Conv":
-            _conv(sh, p, L.c1, L.c2, L.k)
+            _conv(sh, p, L.c1, L.c2, L.k, g=L.extra.get("g", 1))
         elif L.kind == "DSConv":
             _dsconv(sh, p, L.c1, L.c2, L.k)
         elif L.kind == "Bottleneck":
@@ -333,7 +390,26 @@ def param_shapes(spec: GraphSpec) -> Dict[str, list]:
             _conv(sh, p + ".cv1", L.c1, 2 * c, 1)
             _conv(sh, p + ".cv2", (2 + L.n) * c, L.c2, 1)
             for j in range(L.n):
-                _dsc3k(sh, f"{p}.m.{j}", c, c, 2, 1.0)
+                if L.extra.get("dsc3k", True):
+                    _dsc3k(sh, f"{p}.m.{j}", c, c, 2, 1.0)
+                else:  # plain DSBottleneck(c, c, e=1.0, k1=3, k2=7) (block.py:1565-1577)
+                    _dsconv(sh, f"{p}.m.{j}.cv1", c, c, 3)
+                    _dsconv(sh, f"{p}.m.{j}.cv2", c, c, 7)
+        elif L.kind == "A2C2f":
+            c_ = int(L.c2 * 0.5)
+            hid = int(c_ * L.extra["mlp_ratio"])
+            if L.extra["residual"]:
+                sh[p + ".gamma"] = [L.c2]  # a parameter of the module itself: precedes the children in state_dict order
+            _conv(sh, p + ".cv1", L.c1, c_, 1)
+            _conv(sh, p + ".cv2", (1 + L.n) * c_, L.c2, 1)
+            for j in range(L.n):
+                for b in range(2):  # nn.Sequential(ABlock, ABlock)
+                    q = f"{p}.m.{j}.{b}"
+                    _conv(sh, q + ".attn.qkv", c_, 3 * c_, 1)
+                    _conv(sh, q + ".attn.proj", c_, c_, 1)
+                    _conv(sh, q + ".attn.pe", c_, c_, 7, g=c_)
+                    _conv(sh, q + ".mlp.0", c_, hid, 1)
+                    _conv(sh, q + ".mlp.1", hid, c_, 1)
         elif L.kind == "C3Ghost":  # C3 (block.py:259-273) whose m = n GhostBottleneck(c_, c_) (block.py:313-341)
             c_ = int(L.c2 * 0.5)
             _conv(sh, p + ".cv1", L.c1, c_, 1)
@@ -368,6 +444,8 @@ def param_shapes(spec: GraphSpec) -> Dict[str, list]:
         elif L.kind == "DySample":
             sh[p + ".init_pos"] = [1, 32, 1, 1]
             sh[p + ".offset.weight"], sh[p + ".offset.bias"] = [32, L.c1, 1, 1], [32]
+        elif L.kind == "nn.Upsample":
+            pass
         elif L.kind == "DownsampleConv":
             _conv(sh, p + ".channel_adjust", L.c1, L.c2, 1)
         elif L.kind == "FullPAD_Tunnel":
