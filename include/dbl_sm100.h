@@ -169,6 +169,13 @@ int dbl_lsk_squeeze(const dbl_tensor* attn, const dbl_tensor* agg, dbl_stream_t 
 int dbl_lsk_gate(const dbl_tensor* attn, const dbl_tensor* agg, const float* w_sq, const float* b_sq, const dbl_tensor* y,
                  dbl_stream_t stream);
 
+/* ---- area attention (stock yolov13.yaml) ----------------------------------------------------
+ * The core of AAttn.forward (nn/modules/block.py:1236-1262) between the qkv convolution and the pe / proj convolutions.
+ *   qkv: bf16 NHWC (n,h,w,3*heads*32) as the 1x1 qkv Conv writes it (per head [q | k | v], 32 channels each); tokens = pixels in
+ *   row-major order, split into `area` contiguous bands that attend within themselves (h*w %% area == 0).
+ *   o (n,h,w,heads*32) = softmax(q k^T / sqrt(32)) v per head; v_out (n,h,w,heads*32) = the v part (input of the pe depthwise conv). */
+int dbl_area_attention(const dbl_tensor* qkv, const dbl_tensor* o, const dbl_tensor* v_out, int heads, int area, dbl_stream_t stream);
+
 /* ---- adaptive hypergraph (AdaHGComputation / AdaHGConv / AdaHyperedgeGen, block.py:1582-1752) -------------------
  * x: bf16 tokens (n, h, w, d) == (B, N=h*w, D).  All weights f32, row-major [out][in] like nn.Linear.
  * Scratch `ws` must hold dbl_hypergraph_workspace_bytes(B, N, D, E) bytes.  y = node_proj(A·edge_proj(AᵀX)) + X. */

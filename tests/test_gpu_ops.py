@@ -517,3 +517,37 @@ def _run_dsconv_tc(k, s, cin, cout, dw_act, epi, n, h, w):
                                  C.byref(yv), k, epi, stream()) == 0
         torch.cuda.synchronize()
         assert torch.equal(y1, ybuf)
+
+
+# ---- area attention of the stock yolov13.yaml (csrc/attention.cu) ---------------------------------------------------------
+@pytest.mark.parametrize("n,h,w,heads,area", [(2, 40, 40, 2, 4), (3, 20, 20, 4, 1), (1, 16, 20, 2, 4), (1, 8, 10, 1, 1), (2, 12, 25, 2, 4)])
+def test_area_attention(n, h, w, heads, area):
+    """AAttn.forward between the qkv conv and pe / proj (reference block.py:1245-1262), restated with torch fp32 on bf16-rounded inputs"""
+    lib = L.require_device()
+    hd = 32
+    c = heads * hd
+    g = torch.Generator().manual_seed(n * 1000 + h * w + heads)
+    qkv = bf16_round(torch.randn(n, 3 * c, h, w, generator=g) * 1.5)
+    B, N = n, h * w
+    t = qkv.flatten(2).transpose(1, 2)
+    if area > 1:
+        t = t.reshape(B * area, N // area, 3 * c)
+    Bq, Nq = t.shape[:2]
+    q, k, v = t.view(Bq, Nq, heads, hd * 3).permute(0, 2, 3, 1).split([hd, hd, hd], dim=2)
+    attn = ((q.transpose(-2, -1) @ k) * (hd ** -0.5)).softmax(dim=-1)
+    o = (v @ attn.transpose(-2, -1)).permute(0, 3, 1, 2)
+    vv = v.permute(0, 3, 1, 2)
+    if area > 1:
+        o, vv = o.reshape(B, N, c), vv.reshape(B, N, c)
+    o = o.reshape(B, h, w, c).permute(0, 3, 1, 2)
+    vv = vv.reshape(B, h, w, c).permute(0, 3, 1, 2)
+    qbuf, qv = to_nhwc(qkv, pad_c=8)
+    obuf, ov = empty_nhwc(n, h, w, c, pad_c=16, c_off=8)
+    vbuf, vview = empty_nhwc(n, h, w, c)
+    rc = lib.dbl_area_attention(C.byref(qv), C.byref(ov), C.byref(vview), heads, area, stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    assert_close_bf16(from_nhwc(obuf, 8, c), o, f"area attention {h}x{w} heads {heads} area {area}", rel=2.0 ** -6, abs_=2e-2)
+    assert torch.equal(from_nhwc(vbuf, 0, c), vv.contiguous())  # v is a copy
+    assert bool((obuf[..., :8].float() == -3.0).all()) and bool((obuf[..., 8 + c:].float() == -3.0).all())
+    assert lib.dbl_area_attention(C.byref(qv), C.byref(ov), C.byref(vview), heads + 1, area, stream()) != 0  # head dim != 32

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "dbl_dsconv_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbl_dsconv_tc": (C.c_int, [_TP, _P, _P, C.c_int, _P, _P, _TP, _TP, C.c_int, C.c_int, _P]),
     "dbl_dsconv_tc_debug_trace": (C.c_int, [_P]),
+    "dbl_area_attention": (C.c_int, [_TP, _TP, _TP, C.c_int, C.c_int, _P]),
     "dbl_letterbox_u8": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_dwconv2d": (C.c_int, [_TP, _P, _P, _TP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_avgpool2": (C.c_int, [_TP, _TP, _P]),
