@@ -157,6 +157,8 @@ int dbl_upsample2_nearest(const dbl_tensor* x, const dbl_tensor* y, dbl_stream_t
  * tunnel output lands in its consumer's concat buffer as well as in its own. */
 int dbl_gated_add(const dbl_tensor* a, const dbl_tensor* b, float gate, const dbl_tensor* y, const dbl_tensor* y2,
                   dbl_stream_t stream);
+/* A2C2f's learnable residual (nn/modules/block.py:1403-1404): y = a + gamma[c] * b, gamma f32 [c] (16-byte aligned); y may alias a or b */
+int dbl_channel_scale_add(const dbl_tensor* a, const dbl_tensor* b, const float* gamma, const dbl_tensor* y, dbl_stream_t stream);
 /* copy a view (Concat of a tensor that could not be produced in place, conv.py:349-359) */
 int dbl_copy(const dbl_tensor* x, const dbl_tensor* y, dbl_stream_t stream);
 /* DySample.forward_lp + sample (nn/modules_upsample/DySample.py:49-68), scale 2.  off: f32 NHWC (n,h,w,2*groups*4) =

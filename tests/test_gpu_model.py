@@ -360,3 +360,43 @@ def test_sibling_graph_dbl2_c3ghost():
     want, _ = N.non_max_suppression(y.cpu().numpy(), 0.01, 0.7, max_det=300)
     assert counts.tolist() == [len(w) for w in want] and rows[0, : len(want[0])].cpu().numpy().tobytes() == want[0].tobytes()
     assert _rel_l2(y.cpu(), y_ref) <= 2.0 * _rel_l2(O.forward(sd, x, "l", round_bf16=True, cfg="DBL2")[0], y_ref) + 3e-3
+
+
+def test_sibling_graph_yolov13_area_attention():
+    """Stock yolov13.yaml at n scale: strided / grouped stem, DSC3k2 with plain DSBottlenecks, A2C2f area attention
+    (area 4 at P4, area 1 at P5), nn.Upsample -- teacher-forced per layer and free-running against the oracle (pinned to the reference's
+    own yolov13n output, tests/test_oracle_golden.py), then the production engine's detections bit-exact against the oracle's NMS."""
+    spec = resolve("yolov13n.yaml", "n", 3)
+    sd = synth_state_dict(param_shapes(spec), 13)
+    x = synth_images(2, 128, 160, 14)
+    eng = DBLEngine(spec, sd, 2, 128, 160, use_graph=False, keep_layers=True)
+    y_ref, feats_ref, outs_ref = O.forward(sd, x, "n", collect=True, cfg="V13")
+    _, _, outs_b16 = O.forward(sd, x, "n", collect=True, round_bf16=True, cfg="V13")
+    head_ref = torch.cat([f.reshape(2, f.shape[1], -1) for f in feats_ref], 2)
+    forced = eng.debug_layers_forced(x.cuda(), outs_ref)
+    errs = [(_rel_l2(o, r), i, spec.layers[i].kind) for i, (o, r) in enumerate(zip(forced, outs_ref + [head_ref]))]
+    print("[yolov13n 128x160] teacher-forced rel-L2:", " ".join(f"{i}:{e:.3g}" for e, i, _ in errs))
+    for e, i, kind in errs:
+        assert e <= 1.5e-2, f"teacher-forced layer {i} ({kind}) relative L2 error {e:.3g}"
+    outs = eng.debug_layers(x.cuda())
+    fr = [(_rel_l2(o, r), _rel_l2(q, r), i) for i, (o, r, q) in enumerate(zip(outs, outs_ref, outs_b16)) if o is not None]
+    print("[yolov13n 128x160] free-running rel-L2 (ours/oracle-bf16):", " ".join(f"{i}:{e:.3g}/{q:.3g}" for e, q, i in fr))
+    for e, q, i in fr:
+        assert e <= 2.0 * q + 3e-3, f"free-running layer {i} ({spec.layers[i].kind}): {e:.3g} vs bf16 drift {q:.3g}"
+    m = DBLBackend.synthetic("n", 3, seed=13, cfg="yolov13n.yaml", device="cuda:0")
+    y, _ = m(x.cuda())
+    rows, counts = m.detect(x.cuda(), conf=0.01, iou=0.7)
+    torch.cuda.synchronize()
+    want, _ = N.non_max_suppression(y.cpu().numpy(), 0.01, 0.7, max_det=300)
+    assert counts.tolist() == [len(w) for w in want]
+    for i, w in enumerate(want):
+        assert rows[i, : len(w)].cpu().numpy().tobytes() == w.tobytes()
+    # the l scale adds A2C2f's gamma-scaled residual and mlp_ratio 1.5 (tasks.py:1088-1092): one teacher-forced pass over every layer
+    spec_l = resolve("yolov13l.yaml", "l", 3)
+    sd_l = synth_state_dict(param_shapes(spec_l), 1)
+    xl = synth_images(1, 64, 64, 2)
+    e_l = DBLEngine(spec_l, sd_l, 1, 64, 64, use_graph=False, keep_layers=True)
+    _, feats_l, outs_l = O.forward(sd_l, xl, "l", collect=True, cfg="V13")
+    head_l = torch.cat([f.reshape(1, f.shape[1], -1) for f in feats_l], 2)
+    for i, (o, r) in enumerate(zip(e_l.debug_layers_forced(xl.cuda(), outs_l), outs_l + [head_l])):
+        assert _rel_l2(o, r) <= 1.5e-2, f"yolov13l teacher-forced layer {i} ({spec_l.layers[i].kind}): {_rel_l2(o, r):.3g}"

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "dbl_upsample2_nearest": (C.c_int, [_TP, _TP, _P]),
     "dbl_gated_add": (C.c_int, [_TP, _TP, C.c_float, _TP, _TP, _P]),
     "dbl_copy": (C.c_int, [_TP, _TP, _P]),
+    "dbl_channel_scale_add": (C.c_int, [_TP, _TP, _P, _TP, _P]),
     "dbl_dysample": (C.c_int, [_TP, _TP, _TP, C.c_int, _P]),
     "dbl_lsk_squeeze": (C.c_int, [_TP, _TP, _P]),
     "dbl_lsk_gate": (C.c_int, [_TP, _TP, _P, _P, _TP, _P]),

@@ -458,7 +458,9 @@ static int stem_launch(const TIN* x, int n, int h, int w_, const float* w, const
         case 8: launch_k(stem_conv_kernel<8, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
         case 16: launch_k(stem_conv_kernel<16, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
         case 32: launch_k(stem_conv_kernel<32, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;
-        default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_stem_conv: cout %d not in {8,16,32}", y->c);
+        case 64: launch_k(stem_conv_kernel<64, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;   // yolov13l stem
+        case 96: launch_k(stem_conv_kernel<96, TIN>, grid, block, 0, st, x, w, bias, yp, n, h, w_, ho, wo, stride, y->pitch); break;   // yolov13x stem
+        default: DBL_REQUIRE(false, DBL_E_UNSUPPORTED, "dbl_stem_conv: cout %d not in {8,16,32,64,96}", y->c);
     }
     count_launch();
     return check_launch("dbl_stem_conv");

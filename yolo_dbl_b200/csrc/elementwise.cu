@@ -59,6 +59,26 @@ __global__ void __launch_bounds__(256) gated_add_kernel(const __nv_bfloat16* __r
     if (y2) stg8(y2 + pix * y2pitch + g * 8, o);
 }
 
+// y = a + gamma[c] * b with a per-channel scale (A2C2f's learnable residual, reference block.py:1403-1404)
+__global__ void __launch_bounds__(256) channel_scale_add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                                const float* __restrict__ gamma, __nv_bfloat16* __restrict__ y, long long npix, int c,
+                                                                int apitch, int bpitch, int ypitch) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cg = c / 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npix * cg) return;
+    const int g = (int)(idx % cg);
+    const long long pix = idx / cg;
+    float av[8], bv[8];
+    unpack8(ldg8(a + pix * apitch + g * 8), av);
+    unpack8(ldg8(b + pix * bpitch + g * 8), bv);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8 + 4));
+    av[0] = fmaf(g0.x, bv[0], av[0]), av[1] = fmaf(g0.y, bv[1], av[1]), av[2] = fmaf(g0.z, bv[2], av[2]), av[3] = fmaf(g0.w, bv[3], av[3]);
+    av[4] = fmaf(g1.x, bv[4], av[4]), av[5] = fmaf(g1.y, bv[5], av[5]), av[6] = fmaf(g1.z, bv[6], av[6]), av[7] = fmaf(g1.w, bv[7], av[7]);
+    stg8(y + pix * ypitch + g * 8, pack8(av));
+}
+
 // DySample: output pixel (2h+i, 2w+j) of channel group g samples the input of that group bilinearly at
 // (w + off_x, h + off_y), off = conv_out*0.25 + init_pos, border clamped (grid_sample align_corners=False).
 __global__ void __launch_bounds__(256) dysample_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ off,
@@ -337,6 +357,18 @@ extern "C" int dbl_gated_add(const dbl_tensor* a, const dbl_tensor* b, float gat
         a->pitch, b->pitch, y->pitch, y2 ? y2->pitch : 0);
     count_launch();
     return check_launch("dbl_gated_add");
+}
+
+extern "C" int dbl_channel_scale_add(const dbl_tensor* a, const dbl_tensor* b, const float* gamma, const dbl_tensor* y, dbl_stream_t s) {
+    DBL_REQUIRE(valid_tensor(a) && valid_tensor(b) && valid_tensor(y) && gamma && vec8_ok(a) && vec8_ok(b) && vec8_ok(y), DBL_E_ARG,
+                "dbl_channel_scale_add: needs bf16 views with c %% 8 == 0");
+    DBL_REQUIRE(same_shape(a, b) && same_shape(a, y) && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0, DBL_E_ARG, "dbl_channel_scale_add: shape / alignment");
+    const long long npix = (long long)a->n * a->h * a->w;
+    const long long total = npix * (a->c / 8);
+    launch_k(channel_scale_add_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(s), reinterpret_cast<const __nv_bfloat16*>(a->data),
+             reinterpret_cast<const __nv_bfloat16*>(b->data), gamma, reinterpret_cast<__nv_bfloat16*>(y->data), npix, a->c, a->pitch, b->pitch, y->pitch);
+    count_launch();
+    return check_launch("dbl_channel_scale_add");
 }
 
 extern "C" int dbl_dysample(const dbl_tensor* x, const dbl_tensor* off, const dbl_tensor* y, int groups, dbl_stream_t s) {

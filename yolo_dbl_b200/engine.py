@@ -128,6 +128,8 @@ class DBLEngine:
         n_out = 1
         if fn is self.lib.dbl_gated_add:
             n_out = len([1 for i, _ in views if i >= 3])
+        elif fn is self.lib.dbl_area_attention:
+            n_out = 2  # (qkv, o, v_out): o and v_out are written
         regs = [self._region(t) for _, t in views]
         self.op_rw.append((regs[:len(regs) - n_out], regs[len(regs) - n_out:]))
         if not nbytes:  # bandwidth-bound glue: every tensor view in the argument list, once
@@ -182,10 +184,16 @@ class DBLEngine:
                    "conv_mma", 2.0 * npix * y.c * x.c * 9, 2 * self.B * x.h * x.w * x.c + 2 * npix * y.c + 2 * w.numel() + 4 * y.c)
         return True
 
-    def _conv_bn(self, x: Act, p: str, y: Act, s: int = 1, act: int = L.ACT_SILU, epi=L.EPI_NONE, r=None):
-        """Conv module: conv(bias=False)+BN+SiLU (nn/modules/conv.py:39-63)"""
+    def _conv_bn(self, x: Act, p: str, y: Act, s: int = 1, act: int = L.ACT_SILU, epi=L.EPI_NONE, r=None, g: int = 1):
+        """Conv module: conv(bias=False)+BN+SiLU (nn/modules/conv.py:39-63).  Grouped convolutions (g > 1: the strided stem of the stock
+        yolov13.yaml) run as g dense convolutions on channel slices of x and y -- no copy, no extra kernel."""
         w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
-        self._conv(x, w, b, y, w.shape[-1], s, act, epi, r, what=p)
+        if g == 1:
+            return self._conv(x, w, b, y, w.shape[-1], s, act, epi, r, what=p)
+        ci, co = x.c // g, y.c // g
+        for gi in range(g):
+            self._conv(x.slice(gi * ci, ci), w[gi * co:(gi + 1) * co], b[gi * co:(gi + 1) * co], y.slice(gi * co, co), w.shape[-1], s, act, epi,
+                       r.slice(gi * co, co) if r is not None else None, what=f"{p}.g{gi}")
 
     def _conv_bn_pair(self, x: Act, p1: str, p2: str, y: Act):
         """two 1x1 Conv modules reading the same input as ONE GEMM writing [p1 | p2] (C3-style cv1 / cv2)"""
@@ -287,8 +295,46 @@ class DBLEngine:
         z = self._alloc(x.h, x.w, (2 + L_.n) * c)
         self._conv_bn(x, p + ".cv1", z.slice(0, 2 * c))
         for j in range(L_.n):
-            self._lower_dsc3k(z.slice((1 + j) * c, c), f"{p}.m.{j}", z.slice((2 + j) * c, c))
+            src, dst = z.slice((1 + j) * c, c), z.slice((2 + j) * c, c)
+            if L_.extra.get("dsc3k", True):
+                self._lower_dsc3k(src, f"{p}.m.{j}", dst)
+            else:  # plain DSBottleneck(c, c, e=1, k1=3, k2=7) (block.py:1565-1577): dst = src + cv2(cv1(src))
+                t = self._alloc(x.h, x.w, c)
+                self._dsconv(src, f"{p}.m.{j}.cv1", t)
+                self._dsconv(t, f"{p}.m.{j}.cv2", dst, epi=L.EPI_ADD, r=src)
         self._conv_bn(z, p + ".cv2", y)
+
+    def _lower_a2c2f(self, x: Act, L_: LayerSpec, p: str, y: Act):
+        """A2C2f.forward (block.py:1392-1405), a2 = True: cv1 -> n x [ABlock, ABlock] -> cat -> cv2.  ABlock (block.py:1318-1322):
+        x + AAttn(x), then x + mlp(x); AAttn (block.py:1236-1268): qkv 1x1 -> area attention (dbl_area_attention) -> + pe(v) (7x7 depthwise)
+        -> proj 1x1.  Residual adds ride in the epilogues of proj and mlp.1."""
+        c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
+        heads, area = c_ // 32, L_.extra["area"]
+        z = self._alloc(x.h, x.w, (1 + L_.n) * c_)
+        self._conv_bn(x, p + ".cv1", z.slice(0, c_))
+        for j in range(L_.n):
+            cur = z.slice(j * c_, c_)
+            for b in range(2):
+                q = f"{p}.m.{j}.{b}"
+                out = z.slice((j + 1) * c_, c_) if b == 1 else self._alloc(x.h, x.w, c_)
+                qkv, o, v, pe = (self._alloc(x.h, x.w, 3 * c_), self._alloc(x.h, x.w, c_), self._alloc(x.h, x.w, c_), self._alloc(x.h, x.w, c_))
+                self._conv_bn(cur, q + ".attn.qkv", qkv, act=L.ACT_NONE)
+                self._emit(self.lib.dbl_area_attention, (C.byref(qkv.desc), C.byref(o.desc), C.byref(v.desc), heads, area), q + ".attn.core")
+                self._dw_bn(v, q + ".attn.pe", pe, L.ACT_NONE)
+                self._emit(self.lib.dbl_gated_add, (C.byref(o.desc), C.byref(pe.desc), C.c_float(1.0), C.byref(o.desc), None), q + ".attn.pe_add")
+                x1 = self._alloc(x.h, x.w, c_)
+                self._conv_bn(o, q + ".attn.proj", x1, act=L.ACT_NONE, epi=L.EPI_ADD, r=cur)
+                hdn = self._alloc(x.h, x.w, self.sd[q + ".mlp.0.conv.weight"].shape[0])
+                self._conv_bn(x1, q + ".mlp.0", hdn)
+                self._conv_bn(hdn, q + ".mlp.1", out, act=L.ACT_NONE, epi=L.EPI_ADD, r=x1)
+                cur = out
+        if L_.extra.get("residual"):  # l / x scales: x + gamma * cv2(...) with a per-channel learnable gamma (block.py:1403-1404)
+            t = self._alloc(x.h, x.w, y.c)
+            self._conv_bn(z, p + ".cv2", t)
+            gm = self._dev(self.sd[p + ".gamma"], torch.float32)
+            self._emit(self.lib.dbl_channel_scale_add, (C.byref(x.desc), C.byref(t.desc), L.ptr(gm), C.byref(y.desc)), p + ".gamma")
+        else:
+            self._conv_bn(z, p + ".cv2", y)
 
     def _dw_bn(self, x: Act, p: str, y: Act, act: int):
         """depthwise Conv module: Conv(c, c, k, g=c) + BN (+ SiLU), BN folded into the filter (GhostConv.cv2, conv.py:192)"""
@@ -515,8 +561,9 @@ class DBLEngine:
                 self._stem_u8 = (self.x_in_u8.data_ptr(), self.B, self.H, self.W, L.ptr(wd), L.ptr(bd), C.byref(y.desc), Lx.s)
                 self._stem_fn_u8 = self.lib.dbl_stem_conv_u8
             elif Lx.kind == "Conv":
-                if not self._conv_bn_thin(ins[0], p, y, Lx.s):
-                    self._conv_bn(ins[0], p, y, s=Lx.s)
+                g = Lx.extra.get("g", 1)
+                if g > 1 or not self._conv_bn_thin(ins[0], p, y, Lx.s):
+                    self._conv_bn(ins[0], p, y, s=Lx.s, g=g)
             elif Lx.kind == "DSConv":
                 self._dsconv(ins[0], p, y, s=Lx.s)
             elif Lx.kind == "Bottleneck":
@@ -529,6 +576,10 @@ class DBLEngine:
                 self._lower_dsc3k2(ins[0], Lx, p, y)
             elif Lx.kind == "C3Ghost":
                 self._lower_c3ghost(ins[0], Lx, p, y)
+            elif Lx.kind == "A2C2f":
+                self._lower_a2c2f(ins[0], Lx, p, y)
+            elif Lx.kind == "nn.Upsample":
+                self._emit(self.lib.dbl_upsample2_nearest, (C.byref(ins[0].desc), C.byref(y.desc)), p + ".up")
             elif Lx.kind == "LSKblock":
                 cur = ins[0]
                 for r in range(Lx.n):

@@ -58,6 +58,8 @@ def synth_tensor(key: str, shape: Sequence[int], seed: int = 0, siblings=(), rec
         return uniform(0.5, 1.5)
     if leaf == "gate":
         return torch.full(shape, 0.5)
+    if leaf == "gamma":  # A2C2f residual scale at the l / x scales (reference block.py:1386: 0.01 * ones; a visible value here)
+        return torch.full(shape, 0.25)
     if leaf == "init_pos":
         return _init_pos().reshape(shape)
     if leaf == "prototype_base":
