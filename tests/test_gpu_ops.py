@@ -114,6 +114,29 @@ def test_conv3x3_halo_reuse_kernel(case):
     _run_conv_case(case, L.IMPL_DIRECT, seed=7)
 
 
+S2_TC_CASES = [  # thin stride-2 down-samplers on the tcgen05 pixel-pair kernel (conv_s2_tc.cu), reached through dbl_conv2d(AUTO)
+    (2, 40, 40, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 64, 96, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 32),   # output into a channel slice
+    (3, 34, 38, 16, 32, 3, 2, L.ACT_NONE, L.EPI_NONE, torch.bfloat16, 0, 0),    # partial tiles in both directions
+    (2, 40, 40, 32, 64, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 50, 130, 32, 64, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 64),
+    (4, 160, 160, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),  # more tiles than SMs: every CTA loops
+    (8, 160, 160, 32, 64, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 8, 8, 16, 32, 3, 2, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", S2_TC_CASES)
+def test_conv3x3_stride2_pixel_pair_kernel(case):
+    n, h, w, cin, cout = case[:5]
+    lib = L.require_device()
+    xt = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=dev())
+    yt = torch.empty(n, h // 2, w // 2, cout, dtype=torch.bfloat16, device=dev())
+    xv, yv = L.view(xt), L.view(yt)
+    assert lib.dbl_conv2d_which(C.byref(xv), C.byref(yv), 3, 2, 1, 1, L.IMPL_AUTO) == 5
+    _run_conv_case(case, L.IMPL_AUTO, seed=11)
+
+
 def test_conv2d_tcgen05_many_tiles_persistent():
     # more tiles than SMs so every CTA loops (pipeline phases, TMEM double buffering)
     _run_conv_case((8, 80, 80, 64, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=3)

@@ -1,10 +1,8 @@
-for v in 32 16; do
-DBL_FUSE_BN_MAXC=$v python bench.py --no-cpu-baseline --steps 10 --kernel-table gpurun_out/kt_bn$v.json 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('FUSE_BN_MAXC=$v value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['repetitions_ms_per_step'])"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/kt_bn$v.json'))
-for r in d['launches']:
-    if r['what'].startswith(('model.2','model.4','model.3','model.5')): print('   ', r['what'], r['kern'], round(r['ms']*1e3,1))
-PY
+for p in 2 3 4; do
+python bench.py --no-cpu-baseline --steps 20 --inflight $p 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('inflight=$p value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'])"
+done
+for l in 4 16; do
+DBL_LANES=$l python bench.py --no-cpu-baseline --steps 20 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('lanes=$l value', d['value'], 'ms', d['ms_per_step'], 'lat', d['latency_single_step_ms'])"
 done

@@ -155,7 +155,7 @@ class DBLEngine:
         ysz = 2 if y.buf.dtype == torch.bfloat16 else 4
         nbytes = 2 * self.B * x.h * x.w * x.c + ysz * npix * y.c + 2 * w.numel() + 4 * y.c + (2 * npix * y.c if r is not None else 0)
         which = self.lib.dbl_conv2d_which(C.byref(x.desc), C.byref(y.desc), k, s, k // 2, 1, self.conv_impl)
-        kern = {0: "conv_direct", 1: "conv_tc_1x1" if k == 1 else "conv_tc_tma", 3: "conv_tc3", 4: "conv_tc4"}.get(which, "conv_direct")
+        kern = {0: "conv_direct", 1: "conv_tc_1x1" if k == 1 else "conv_tc_tma", 3: "conv_tc3", 4: "conv_tc4", 5: "conv_s2_tc"}.get(which, "conv_direct")
         self._emit(self.lib.dbl_conv2d, args, what, kern, 2.0 * npix * y.c * x.c * k * k, nbytes)
 
     def _pack_mma(self, w: torch.Tensor) -> torch.Tensor:
@@ -178,6 +178,8 @@ class DBLEngine:
         w, b = _fold(self.sd[p + ".conv.weight"], self.sd, p + ".bn")
         if not (self.fuse_thin and w.shape[-1] == 3 and s == 2 and (x.c, y.c) in self.THIN_S2 and x.buf.data_ptr() != y.buf.data_ptr()):
             return False
+        if self.lib.dbl_conv2d_which(C.byref(x.desc), C.byref(y.desc), 3, s, 1, 1, self.conv_impl) == 5:
+            return False  # dbl_conv2d runs it on the tcgen05 pixel-pair kernel (conv_s2_tc.cu)
         wp, bd = self._pack_mma(w), self._dev(b, torch.float32)
         npix = self.B * y.h * y.w
         self._emit(self.lib.dbl_conv3x3_mma, (C.byref(x.desc), L.ptr(wp), L.ptr(bd), None, C.byref(y.desc), s, L.ACT_SILU, L.EPI_NONE), p,
@@ -402,12 +404,16 @@ class DBLEngine:
                    p + ".hypergraph")
         self._conv_bn(t, p + ".cv3", y)
 
-    def _lower_hyperace(self, xs: Sequence[Act], L_: LayerSpec, p: str, y: Act):
-        """HyperACE.forward (block.py:1884-1895) incl. FuseModule.forward (block.py:1833-1840)"""
+    def _lower_hyperace(self, xs: Sequence[Act], L_: LayerSpec, p: str, y: Act, f: Optional[Act] = None):
+        """HyperACE.forward (block.py:1884-1895) incl. FuseModule.forward (block.py:1833-1840).  `f`: the fuse buffer when the P4 producer
+        already wrote its slice there (no copy of the middle input)."""
         x0, x1, x2 = xs
-        f = self._alloc(x1.h, x1.w, x0.c + x1.c + x2.c)
+        aliased = f is not None and x1.buf.data_ptr() == f.buf.data_ptr() and x1.off == x0.c
+        if not aliased:
+            f = self._alloc(x1.h, x1.w, x0.c + x1.c + x2.c)
         self._emit(self.lib.dbl_avgpool2, (C.byref(x0.desc), C.byref(f.slice(0, x0.c).desc)), p + ".fuse.down")
-        self._emit(self.lib.dbl_copy, (C.byref(x1.desc), C.byref(f.slice(x0.c, x1.c).desc)), p + ".fuse.copy")
+        if not aliased:
+            self._emit(self.lib.dbl_copy, (C.byref(x1.desc), C.byref(f.slice(x0.c, x1.c).desc)), p + ".fuse.copy")
         self._emit(self.lib.dbl_upsample2_nearest, (C.byref(x2.desc), C.byref(f.slice(x0.c + x1.c, x2.c).desc)), p + ".fuse.up")
         x = self._alloc(x1.h, x1.w, x1.c)
         self._conv_bn(f, p + ".fuse.conv_out", x)
@@ -519,6 +525,10 @@ class DBLEngine:
                     if j >= 0 and j not in alias and spec.layers[j].kind != "Concat":
                         alias[j] = (Lc.i, off)
                     off += cj
+            elif Lc.kind == "HyperACE":  # FuseModule's cat([down(P3), P4, up(P5)]) (block.py:1833-1840): the P4 producer writes its slice directly
+                j = Lc.src[1]
+                if j >= 0 and j not in alias and spec.layers[j].kind != "Concat":
+                    alias[j] = (Lc.i, Lc.extra["cins"][0])
         cat_buf: Dict[int, Act] = {}
 
         def out_act(Lx: LayerSpec) -> Act:
@@ -526,7 +536,8 @@ class DBLEngine:
             if Lx.i in alias:
                 ci, off = alias[Lx.i]
                 if ci not in cat_buf:
-                    cat_buf[ci] = self._alloc(h, w, spec.layers[ci].c2)
+                    tgt = spec.layers[ci]
+                    cat_buf[ci] = self._alloc(h, w, sum(tgt.extra["cins"]) if tgt.kind == "HyperACE" else tgt.c2)
                 return cat_buf[ci].slice(off, Lx.c2)
             if Lx.kind == "Concat":
                 if Lx.i not in cat_buf:
@@ -587,7 +598,7 @@ class DBLEngine:
                     self._lower_lsk(cur, f"{p}.{r}" if Lx.n > 1 else p, dst)
                     cur = dst
             elif Lx.kind == "HyperACE":
-                self._lower_hyperace(ins, Lx, p, y)
+                self._lower_hyperace(ins, Lx, p, y, cat_buf.get(Lx.i))
             elif Lx.kind == "DySample":
                 self._lower_dysample(ins[0], p, y)
             elif Lx.kind == "DownsampleConv":
