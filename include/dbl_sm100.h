@@ -68,7 +68,8 @@ int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias, const dbl_
                int k, int stride, int pad, int dil, int act, int epi, int impl, dbl_stream_t stream);
 
 /* Which kernel dbl_conv2d runs for this problem: 0 CUDA-core direct, 1 tcgen05 + TMA (1x1 GEMM / one box per tap), 3 tcgen05 halo reuse
- * with resident weights, 4 tcgen05 halo reuse with multi-accumulator super-tiles; -1 for invalid tensors. */
+ * with resident weights, 4 tcgen05 halo reuse with multi-accumulator super-tiles, 5 tcgen05 thin stride-2 (pixel-pair planes), 6 tcgen05
+ * stride-1 3x3 whose whole reduction depth is one shared-memory tile; -1 for invalid tensors. */
 int dbl_conv2d_which(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil, int impl);
 
 /* Layer 0 of the graph (cfg/models/v13/yolov13_DBL.yaml:9, Conv [32,3,1]) fused with the input cast of

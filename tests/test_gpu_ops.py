@@ -137,6 +137,34 @@ def test_conv3x3_stride2_pixel_pair_kernel(case):
     _run_conv_case(case, L.IMPL_AUTO, seed=11)
 
 
+T5_CASES = [  # stride-1 3x3 with the whole reduction depth in one tile (conv_tc5.cu), reached through dbl_conv2d(AUTO)
+    (2, 20, 20, 64, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (2, 20, 20, 32, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (1, 33, 50, 32, 64, 3, 1, L.ACT_NONE, L.EPI_MUL, torch.bfloat16, 32, 64),   # channel slices on both sides, partial tiles
+    (1, 40, 40, 64, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 64, 0),
+    (2, 17, 23, 64, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (1, 24, 36, 32, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 40, 72, 32, 16, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 40, 72, 16, 32, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (1, 30, 30, 16, 16, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 16),
+    (8, 80, 80, 64, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),    # more tiles than SMs: every CTA loops
+    (8, 80, 80, 32, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0),
+    (6, 80, 80, 64, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+    (1, 4, 4, 64, 32, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),
+]
+
+
+@pytest.mark.parametrize("case", T5_CASES)
+def test_conv3x3_single_chunk_kernel(case):
+    n, h, w, cin, cout = case[:5]
+    lib = L.require_device()
+    xt = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=dev())
+    yt = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=dev())
+    xv, yv = L.view(xt), L.view(yt)
+    assert lib.dbl_conv2d_which(C.byref(xv), C.byref(yv), 3, 1, 1, 1, L.IMPL_AUTO) == 6
+    _run_conv_case(case, L.IMPL_AUTO, seed=13)
+
+
 def test_conv2d_tcgen05_many_tiles_persistent():
     # more tiles than SMs so every CTA loops (pipeline phases, TMEM double buffering)
     _run_conv_case((8, 80, 80, 64, 64, 3, 1, L.ACT_SILU, L.EPI_ADD, torch.bfloat16, 0, 0), L.IMPL_TCGEN05, seed=3)

@@ -15,6 +15,8 @@ bool conv3x3_tc3_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int s
 bool conv3x3_tc3_preferred(const dbl_tensor* x, const dbl_tensor* y, int stride);
 int conv3x3_tc4(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int act, int epi, cudaStream_t st);
 bool conv3x3_tc4_eligible(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil);
+int conv3x3_tc5(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* r, const dbl_tensor* y, int act, int epi, cudaStream_t st);
+bool conv3x3_tc5_eligible(const dbl_tensor* x, const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int pad, int dil, int act);
 int conv3x3s2_tc(const dbl_tensor* x, const void* w, const float* bias, const dbl_tensor* y, int act, cudaStream_t st);
 bool conv3x3s2_tc_eligible(const dbl_tensor* x, const dbl_tensor* r, const dbl_tensor* y, int k, int stride, int pad, int dil, int act);
 bool conv3x3_tc4_preferred(const dbl_tensor* x, const dbl_tensor* y);
@@ -496,6 +498,7 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
     const bool tc3_ok = conv3x3_tc3_eligible(x, y, k, stride, pad, dil);
     const bool tc4_ok = conv3x3_tc4_eligible(x, y, k, stride, pad, dil);
     if (impl == DBL_IMPL_AUTO && conv3x3s2_tc_eligible(x, epi ? r : nullptr, y, k, stride, pad, dil, act)) return conv3x3s2_tc(x, w, bias, y, act, st);
+    if (impl == DBL_IMPL_AUTO && conv3x3_tc5_eligible(x, epi ? r : nullptr, y, k, stride, pad, dil, act)) return conv3x3_tc5(x, w, bias, epi ? r : nullptr, y, act, epi, st);
     if (impl == DBL_IMPL_TCGEN05_MULTI) DBL_REQUIRE(tc4_ok, DBL_E_UNSUPPORTED, "dbl_conv2d: shape not eligible for the multi-accumulator tcgen05 path");
     if (tc4_ok && (impl == DBL_IMPL_TCGEN05_MULTI || ((impl == DBL_IMPL_AUTO || impl == DBL_IMPL_TCGEN05) && conv3x3_tc4_preferred(x, y))))
         return conv3x3_tc4(x, w, bias, epi ? r : nullptr, y, act, epi, st);
@@ -523,13 +526,14 @@ extern "C" int dbl_conv2d(const dbl_tensor* x, const void* w, const float* bias,
 }
 
 /* which kernel dbl_conv2d would run for this problem: 0 direct (CUDA cores), 1 conv_tc (TMA per tap / 1x1 GEMM), 3 conv_tc3 (halo reuse,
- * resident weights), 4 conv_tc4 (halo reuse, multi-accumulator), 5 conv_s2_tc (thin stride-2, pixel-pair planes), -1 invalid.  Lets callers attribute time to the right kernel. */
+ * resident weights), 4 conv_tc4 (halo reuse, multi-accumulator), 5 conv_s2_tc (thin stride-2, pixel-pair planes), 6 conv_tc5 (stride-1, whole K in one tile), -1 invalid.  Lets callers attribute time to the right kernel. */
 extern "C" int dbl_conv2d_which(const dbl_tensor* x, const dbl_tensor* y, int k, int stride, int pad, int dil, int impl) {
     if (!valid_tensor(x) || !valid_tensor(y)) return -1;
     const bool tc_ok = conv2d_tcgen05_eligible(x, nullptr, y, k, stride, pad, dil);
     const bool tc3_ok = conv3x3_tc3_eligible(x, y, k, stride, pad, dil);
     const bool tc4_ok = conv3x3_tc4_eligible(x, y, k, stride, pad, dil);
     if (impl == DBL_IMPL_AUTO && conv3x3s2_tc_eligible(x, nullptr, y, k, stride, pad, dil, DBL_ACT_SILU)) return 5;
+    if (impl == DBL_IMPL_AUTO && conv3x3_tc5_eligible(x, nullptr, y, k, stride, pad, dil, DBL_ACT_SILU)) return 6;
     if (tc4_ok && (impl == DBL_IMPL_TCGEN05_MULTI || ((impl == DBL_IMPL_AUTO || impl == DBL_IMPL_TCGEN05) && conv3x3_tc4_preferred(x, y)))) return 4;
     if (tc3_ok && (impl == DBL_IMPL_TCGEN05 || (impl == DBL_IMPL_AUTO && (!tc_ok || conv3x3_tc3_preferred(x, y, stride))))) return 3;
     if ((impl == DBL_IMPL_TCGEN05 || impl == DBL_IMPL_TCGEN05_TMA || impl == DBL_IMPL_AUTO) && tc_ok) return 1;

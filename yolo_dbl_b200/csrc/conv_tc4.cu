@@ -213,7 +213,11 @@ __global__ void __launch_bounds__(T4_THREADS, 1) conv3x3_tc4_kernel(const __grid
                         uint32_t acc = first, a_row = a_lo, b_t = b_lo;
 #pragma unroll 1
                         for (int dy = 0; dy < 3; ++dy) {
+#ifdef DBL_T4_ROLL_DX
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
                             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
                                 for (int ks = 0; ks < KSTEPS; ++ks) {

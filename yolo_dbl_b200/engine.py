@@ -155,7 +155,7 @@ class DBLEngine:
         ysz = 2 if y.buf.dtype == torch.bfloat16 else 4
         nbytes = 2 * self.B * x.h * x.w * x.c + ysz * npix * y.c + 2 * w.numel() + 4 * y.c + (2 * npix * y.c if r is not None else 0)
         which = self.lib.dbl_conv2d_which(C.byref(x.desc), C.byref(y.desc), k, s, k // 2, 1, self.conv_impl)
-        kern = {0: "conv_direct", 1: "conv_tc_1x1" if k == 1 else "conv_tc_tma", 3: "conv_tc3", 4: "conv_tc4", 5: "conv_s2_tc"}.get(which, "conv_direct")
+        kern = {0: "conv_direct", 1: "conv_tc_1x1" if k == 1 else "conv_tc_tma", 3: "conv_tc3", 4: "conv_tc4", 5: "conv_s2_tc", 6: "conv_tc5"}.get(which, "conv_direct")
         self._emit(self.lib.dbl_conv2d, args, what, kern, 2.0 * npix * y.c * x.c * k * k, nbytes)
 
     def _pack_mma(self, w: torch.Tensor) -> torch.Tensor:
