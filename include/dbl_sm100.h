@@ -139,7 +139,8 @@ int dbl_dsconv(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw
 int dbl_dsconv_tc_supported(int k, int stride, int cin, int cout);
 int dbl_dsconv_tc(const dbl_tensor* x, const float* w_dw, const float* b_dw, int dw_act, const void* w_pw, const float* b_pw,
                   const dbl_tensor* r, const dbl_tensor* y, int k, int epi, dbl_stream_t stream);
-/* Developer aid (tools/ds_trace.py): with a non-NULL DEVICE buffer of the returned size, CTA 0 of every later dbl_dsconv_tc launch
+/* Developer aid (tools/ds_trace.py, tools/t5_trace.py): with a non-NULL DEVICE buffer of the returned size, CTA 0 of every later dbl_dsconv_tc
+ * launch (and of the stride-1 single-tile 3x3 kernel behind dbl_conv2d)
  * records %globaltimer stamps [role: producer, mma, depthwise, epilogue][first 16 tiles][4 events]; NULL switches it off. */
 int dbl_dsconv_tc_debug_trace(void* device_buffer);
 

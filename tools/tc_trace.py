@@ -24,6 +24,9 @@ NAMES = ["entry", "prologue done", "pdl_wait done", "first TMA issued", "first s
 
 
 def main():
+    alt = os.path.join(os.path.dirname(L.LIB_PATH), "..", "lib_trace", "libdbl_sm100.so")  # a -DDBL_TRACE build kept next to the shipped one
+    if os.path.exists(alt):
+        L.LIB_PATH = alt
     lib = L.require_device()
     lib.dbl_debug_trace_read.argtypes = [C.c_void_p, C.c_size_t]
     dev = torch.device("cuda:0")

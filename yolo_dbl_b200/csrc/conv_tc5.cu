@@ -57,7 +57,17 @@ struct T5Params {
     float inv_wl;
     uint32_t tx_bytes;  // bytes of one halo box
     uint32_t r_bytes;   // bytes of one residual box
+    unsigned long long* trace;  // developer aid (dbl_dsconv_tc_debug_trace): CTA 0 writes [role][tile iteration][event] globaltimer stamps
 };
+
+unsigned long long* debug_trace_buffer();  // dsconv_tc.cu
+__device__ __forceinline__ void t5_stamp(const T5Params& p, int role, uint32_t it, int ev) {
+    if (p.trace && blockIdx.x == 0 && it < 16u) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[(role * 16 + it) * 4 + ev] = t;
+    }
+}
 
 // position of 16-byte chunk j of row p inside a swizzled tile whose rows are `rowb` bytes (TMA / UMMA 128 / 64 / 32-byte swizzle)
 __device__ __forceinline__ uint32_t t5_swz(uint32_t j, uint32_t p, int rowb) {
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
             const int y0 = (t / p.tiles_x) * p.th, x0 = (t % p.tiles_x) * p.tw;
             const uint32_t s = it % C::NIN, ph = (it / C::NIN) & 1;
             mbar_wait_parked(&in_empty[s], ph ^ 1);
+            if (lane == 0) t5_stamp(p, 0, it, 0);
             if (elect_one()) {
                 mbar_expect_tx(&in_full[s], p.tx_bytes);
                 tma_load_4d(&maps.x, &in_full[s], sIn + s * C::STAGE_BYTES, 0, x0 - 1, y0 - 1, img);
@@ -166,7 +177,9 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
             const uint32_t s = it % C::NIN, ph = (it / C::NIN) & 1;
             const uint32_t acc = it & 1, tph = (it >> 1) & 1;
             mbar_wait_parked(&t_empty[acc], tph ^ 1);
+            if (lane == 0) t5_stamp(p, 1, it, 0);
             mbar_wait_parked(&in_full[s], ph);
+            if (lane == 0) t5_stamp(p, 1, it, 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t in_s = smem_u32(sIn + s * C::STAGE_BYTES);
@@ -190,6 +203,7 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
                 umma_commit(&in_empty[s]);  // the halo tile may be overwritten once these MMAs have read it
             }
             __syncwarp();
+            if (lane == 0) t5_stamp(p, 1, it, 2);
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps =====================
@@ -209,6 +223,7 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
             if (RES) mbar_wait_parked(&r_full[rs], rph);
             mbar_wait_parked(&t_full[acc * 4 + q], tph);
             tc_fence_after();
+            if (issuer) t5_stamp(p, 3, it, 0);
             uint32_t v[COUT / 16][16];
 #pragma unroll
             for (int g = 0; g < COUT / 16; ++g) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (acc * MT + q) * (uint32_t)COUT + g * 16, v[g]);
@@ -220,6 +235,7 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);  // the accumulator is in registers: the MMA warp may reuse these TMEM columns
+            if (issuer) t5_stamp(p, 3, it, 1);
             const uint32_t o_s = smem_u32(sOut + ob * C::O_BYTES), r_s = smem_u32(sRes + (RES ? rs * C::O_BYTES : 0));
 #pragma unroll
             for (int g = 0; g < COUT / 16; ++g) {
@@ -260,7 +276,9 @@ __global__ void __launch_bounds__(T5Cfg<CIN, COUT, MT, WLMAX, RES>::THREADS, 1) 
                 const int y0 = (t / p.tiles_x) * p.th, x0 = (t % p.tiles_x) * p.tw;
                 tma_store_4d(&maps.y, sOut + ob * C::O_BYTES, 0, x0, y0, img);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                t5_stamp(p, 3, it, 2);
             }
+            if (wi == 4 * (MT - 1) && lane == 0) t5_stamp(p, 2, it, 0);  // last M tile's quad: end of its tile
         }
         if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stores read shared memory: finish before the CTA exits
     }
@@ -356,7 +374,7 @@ static int launch_t5(const dbl_tensor* x, const void* w, const float* bias, cons
     DBL_REQUIRE(nt < (1ll << 31), DBL_E_UNSUPPORTED, "conv3x3_tc5: too many tiles");
     p.ntiles = (int)nt;
     p.inv_wl = 1.0f / (float)p.wl;
-    p.bias = bias, p.epi = epi;
+    p.bias = bias, p.epi = epi, p.trace = debug_trace_buffer();
     p.tx_bytes = (uint32_t)((p.th + 2) * p.wl * C::ROWA);
     p.r_bytes = (uint32_t)(p.th * p.tw * C::ROWO);
     T5Maps maps;

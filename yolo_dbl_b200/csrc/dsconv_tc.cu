@@ -504,6 +504,7 @@ static bool dt_map_nhwc(CUtensorMap* m, const dbl_tensor* t, int c0, int cw, int
 }
 
 static unsigned long long* g_dt_trace = nullptr;  // developer aid, see dbl_dsconv_tc_debug_trace
+unsigned long long* debug_trace_buffer() { return g_dt_trace; }  // conv_tc5.cu stamps into the same buffer
 
 template <int K, int CIN, int COUT, int DW_ACT, bool RES, int S = 1>
 static int launch_dt(const dbl_tensor* x, const float* wdw, const float* bdw, const void* wpw, const float* bpw, const dbl_tensor* r,

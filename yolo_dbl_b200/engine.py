@@ -83,7 +83,7 @@ class DBLEngine:
         # (Detect P3 64->80 @80^2: 108 us fused vs 89 us as two launches).  "1" = wherever supported, "0" = never.
         self.fuse_ds = os.environ.get("DBL_FUSE_DS", "auto")
         self.ds_impl = os.environ.get("DBL_DS_IMPL", "auto")  # "mma": keep the warp-MMA kernel (A/B aid); "auto": tcgen05 kernel where instantiated
-        self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "32"))  # widest Bottleneck that uses the fused warp-MMA kernel
+        self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "16"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
         # run on `lanes` streams: inside a captured CUDA graph they become parallel branches, so small kernels overlap
