@@ -107,6 +107,15 @@ int dbl_mma_pack_weights(const void* w, int cout, int cin, int taps, void* packe
  * the residual.  x and y must not alias. */
 int dbl_bottleneck3x3(const dbl_tensor* x, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
                       int shortcut, const dbl_tensor* y, dbl_stream_t stream);
+/* The same Bottleneck on tcgen05 (csrc/bottleneck_tc.cu) for C in {16, 32}: a GEMM row is a group of 64/C consecutive pixels (one 128-byte
+ * row of the NHWC tensor), the filters are band matrices over the group's window, the hidden tensor stays in shared memory.  x and y must
+ * be dense (pitch == C) with W % (64/C) == 0 -- dbl_bottleneck_tc_supported(c, w, pitch) -- and must not alias.  The band matrices and
+ * biases are produced ONCE by dbl_bottleneck_tc_pack from the dbl_conv2d layouts (w1: bf16 [C/2][3][3][C], w2: bf16 [C][3][3][C/2], BN
+ * folded) into caller-owned, 16-byte-aligned memory of dbl_bottleneck_tc_packed_bytes(c) bytes. */
+int dbl_bottleneck_tc_supported(int c, int w, int pitch);
+size_t dbl_bottleneck_tc_packed_bytes(int c);
+int dbl_bottleneck_tc_pack(const void* w1, const float* b1, const void* w2, const float* b2, int c, void* packed, dbl_stream_t stream);
+int dbl_bottleneck3x3_tc(const dbl_tensor* x, const void* packed, int shortcut, const dbl_tensor* y, dbl_stream_t stream);
 /* One thin 3x3 Conv (pad 1, stride 1|2), act in {NONE, SILU}, optional residual; (cin,cout,stride) from the set the
  * kernel is instantiated for (else DBL_E_UNSUPPORTED): the stride-2 down-samplers 8->16, 16->32, 32->64 and the
  * stride-1 pairs 16<->8, 32<->16, 64<->32. */

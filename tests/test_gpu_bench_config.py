@@ -53,7 +53,7 @@ def test_production_engine_is_the_benchmarked_instantiation(bench):
     assert eng.fuse_stem and eng.fuse_head and eng.use_graph and eng.n_lanes == 8
     assert eng.head_fused is not None and (eng.head_fused.c2, eng.head_fused.c3, eng.head_fused.nc) == (64, 80, 80)
     kerns = {m["kern"] for m in eng.op_meta}
-    assert {"stem_pair", "bottleneck_mma", "conv_s2_tc", "conv_tc4", "conv_tc_1x1", "dsconv_tc"} <= kerns, kerns
+    assert {"stem_pair", "bottleneck_tc", "conv_s2_tc", "conv_tc5", "conv_tc4", "conv_tc_1x1", "dsconv_tc"} <= kerns, kerns
 
 
 def test_forward_vs_oracle_and_reference(bench):

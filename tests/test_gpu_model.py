@@ -199,7 +199,7 @@ def test_fused_stem_engine_matches_layerwise_engine():
     e_layer = DBLEngine(spec, sd, 2, 128, 160, use_graph=False, keep_layers=True)
     e_fused = DBLEngine(spec, sd, 2, 128, 160, use_graph=False)
     assert not e_layer.fuse_stem and e_fused.fuse_stem
-    assert any(m["kern"] == "stem_pair" for m in e_fused.op_meta) and any(m["kern"] == "bottleneck_mma" for m in e_fused.op_meta)
+    assert any(m["kern"] == "stem_pair" for m in e_fused.op_meta) and any(m["kern"] == "bottleneck_tc" for m in e_fused.op_meta)
     y_ref, _ = O.forward(sd, x, "n")
     for name, inp in (("f32", x.cuda()), ("u8", (x * 255).round().to(torch.uint8).cuda())):
         y1 = e_layer.forward(inp)[0].clone()

@@ -380,6 +380,41 @@ def test_bottleneck3x3_fused(c, n, h, w, xpad, ypad):
     assert lib.dbl_bottleneck3x3(C.byref(xv), w1p.data_ptr(), None, w2p.data_ptr(), None, 1, C.byref(xv), stream()) == 1
 
 
+@pytest.mark.parametrize("c,n,h,w,ypad", [(16, 2, 40, 72, 0), (16, 1, 33, 52, 0), (16, 1, 33, 52, 16), (32, 2, 48, 64, 32), (32, 2, 48, 64, 0), (32, 1, 17, 34, 0), (16, 1, 7, 4, 0),
+                                          (32, 1, 5, 2, 0), (16, 3, 320, 320, 0), (32, 6, 160, 160, 0)])
+def test_bottleneck3x3_tc(c, n, h, w, ypad):
+    """Bottleneck.forward on the tcgen05 pixel-group kernel (csrc/bottleneck_tc.cu) vs torch fp32 with the hidden tensor rounded to bf16"""
+    g = torch.Generator().manual_seed(c + h)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    w1 = bf16_round(torch.randn(c // 2, c, 3, 3, generator=g) / (9 * c) ** 0.5)
+    w2 = bf16_round(torch.randn(c, c // 2, 3, 3, generator=g) / (4.5 * c) ** 0.5)
+    b1, b2 = torch.randn(c // 2, generator=g) * 0.3, torch.randn(c, generator=g) * 0.3
+    hid = bf16_round(F.silu(F.conv2d(x, w1, b1, 1, 1)))
+    conv = F.silu(F.conv2d(hid, w2, b2, 1, 1))
+    xbuf, xv = to_nhwc(x)
+    ybuf, yv = empty_nhwc(n, h, w, c, pad_c=ypad, c_off=ypad // 2 // 8 * 8)
+    lib = L.require_device()
+    assert lib.dbl_bottleneck_tc_supported(c, w, xv.pitch) == 1
+    packed = torch.zeros((lib.dbl_bottleneck_tc_packed_bytes(c) + 15) // 16 * 4, dtype=torch.int32, device=dev())
+    b1d, b2d = b1.to(dev()), b2.to(dev())
+    assert lib.dbl_bottleneck_tc_pack(pack_w(w1).data_ptr(), b1d.data_ptr(), pack_w(w2).data_ptr(), b2d.data_ptr(), c, packed.data_ptr(), stream()) == 0
+    torch.cuda.synchronize()
+    off = (yv.data - ybuf.data_ptr()) // 2
+    if ypad:  # the output is stored through its pixel-group view as well: a channel slice is refused, not mis-written
+        assert lib.dbl_bottleneck3x3_tc(C.byref(xv), packed.data_ptr(), 1, C.byref(yv), stream()) == 2  # DBL_E_UNSUPPORTED
+        assert bool((ybuf.float() == -3.0).all())
+        return
+    for shortcut in (1, 0):
+        rc = lib.dbl_bottleneck3x3_tc(C.byref(xv), packed.data_ptr(), shortcut, C.byref(yv), stream())
+        torch.cuda.synchronize()
+        assert rc == 0, L.load().dbl_last_error().decode()
+        assert_close_bf16(from_nhwc(ybuf, off, c), (x + conv) if shortcut else conv, f"bottleneck_tc c={c} {h}x{w} shortcut={shortcut}", abs_=3e-2)
+    # a channel slice as input has no pixel-group view
+    xb2, xv2 = to_nhwc(x, pad_c=16, c_off=8)
+    assert lib.dbl_bottleneck_tc_supported(c, w, xv2.pitch) == 0
+    assert lib.dbl_bottleneck3x3_tc(C.byref(xv2), packed.data_ptr(), 1, C.byref(yv), stream()) == 2  # DBL_E_UNSUPPORTED
+
+
 @pytest.mark.parametrize("cin,cout,s,n,h,w,epi", [(8, 16, 2, 2, 64, 96, L.EPI_NONE), (16, 32, 2, 2, 40, 72, L.EPI_NONE), (32, 64, 2, 1, 34, 38, L.EPI_NONE),
                                                   (16, 8, 1, 1, 33, 50, L.EPI_NONE), (8, 16, 1, 2, 24, 40, L.EPI_ADD), (32, 16, 1, 1, 40, 40, L.EPI_NONE),
                                                   (16, 32, 1, 1, 18, 70, L.EPI_MUL), (64, 32, 1, 1, 20, 36, L.EPI_NONE), (32, 64, 1, 2, 20, 20, L.EPI_ADD),

@@ -2,6 +2,7 @@
 // Issue-to-completion rate of tcgen05.mma.cta_group::1.kind::f16 (M = 128, K = 16) with BOTH operands in shared memory, as a function
 // of N and of the row width / swizzle of the A tile: what does a narrow-N implicit-GEMM convolution pay per MMA?
 //   mode 0: every MMA reads the same A tile        mode 1: the A start walks through a 64 KB window in steps of one row (conv taps)
+//   mode 4: mode 1 + the B tile changes with every MMA (eight 1 KB blocks)      mode 5: mode 4 + the A start also steps through the 32-byte pieces of its row
 //   mode 3: the A start walks in steps of 40 rows (8-row aligned)
 //   accumulators: consecutive MMAs accumulate into 1 / 2 / 4 different TMEM tiles in turn (dependent chain vs interleaved)
 //   mode 2: no-swizzle A, the two 8-byte... (LBO) core matrices `lbo` bytes apart (two filter taps of an 8-channel tensor in one k-step)
@@ -46,11 +47,14 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int n, int rowb, int
         const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 1024);
         const uint64_t bd = desc(b0, 32);
         // eight descriptors precomputed (the issue loop must not be bound by its own address arithmetic)
-        uint64_t ad[8];
+        uint64_t ad[8], bdv[8];
+        for (int j = 0; j < 8; ++j) bdv[j] = desc(b0 + (uint32_t)((mode == 4 || mode == 5) ? j * 1024 : 0), 32);
         for (int j = 0; j < 8; ++j) {
             const uint32_t row = mode == 0 ? 0u : (mode == 3 ? (uint32_t)(j * 8 * 5) : (uint32_t)(j * 37 + 1));
-            ad[j] = mode == 2 ? desc_noswz(a0 + row * 16, lbo, 128) : desc(a0 + row * rowb, rowb);
+            ad[j] = mode == 2 ? desc_noswz(a0 + row * 16, lbo, 128) : desc(a0 + row * rowb + (mode == 5 ? (uint32_t)((j & 3) * 32) % rowb : 0u), rowb);
         }
+        unsigned long long g0, g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
         const long long t0 = clock64();
         for (int i = 0; i < iters; i += 8) {
 #pragma unroll
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int n, int rowb, int
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + (uint32_t)((j % nacc) * n)),
-                    "l"(ad[j]), "l"(bd), "r"(idesc), "r"(1u)
+                    "l"(ad[j]), "l"(bdv[j]), "r"(idesc), "r"(1u)
                     : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -66,7 +70,8 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int n, int rowb, int
         while (!done)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
         const long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        if (blockIdx.x == 0) out[0] = t1 - t0, out[1] = (long long)(g1 - g0);
         }
         __syncwarp();
     }
@@ -80,17 +85,19 @@ int main() {
     cudaMalloc(&out, 64);
     const int smem = 162 * 1024 + 1024;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const int iters = 4000;
+    const int iters = 40000;
     const int ns[] = {16, 32, 64, 128, 256};
     for (int nacc : {1, 2, 4})
-    for (int mode : {1})
+    for (int mode : {1, 4, 5})
         for (int rowb : {64, 128})
             for (int n : ns) {
                 if (nacc * n > 256) continue;
                 k<<<148, 128, smem>>>(out, n, rowb, mode, iters, 0, nacc);
-                long long c = 0;
-                cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
-                printf("accumulators %d  mode %d  A rows %3d B  N %3d: %6.1f clk per MMA  (%s)\n", nacc, mode, rowb, n, (double)c / iters, cudaGetErrorString(cudaGetLastError()));
+                long long c2[2] = {0, 0};
+                cudaMemcpy(c2, out, 16, cudaMemcpyDeviceToHost);
+                const long long c = c2[0];
+                printf("accumulators %d  mode %d  A rows %3d B  N %3d: %6.1f clk per MMA = %5.1f ns (SM clock %.0f MHz)  (%s)\n", nacc, mode, rowb, n, (double)c / iters,
+                       (double)c2[1] / iters, 1e3 * c / (double)c2[1], cudaGetErrorString(cudaGetLastError()));
             }
     for (int lbo : {16, 48, 1040})
         for (int n : {16, 32}) {

@@ -79,6 +79,10 @@ _SIGNATURES = {
     "dbl_mma_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dbl_mma_pack_weights": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dbl_bottleneck3x3": (C.c_int, [_TP, _P, _P, _P, _P, C.c_int, _TP, _P]),
+    "dbl_bottleneck_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "dbl_bottleneck_tc_packed_bytes": (C.c_size_t, [C.c_int]),
+    "dbl_bottleneck_tc_pack": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "dbl_bottleneck3x3_tc": (C.c_int, [_TP, _P, C.c_int, _TP, _P]),
     "dbl_conv3x3_mma": (C.c_int, [_TP, _P, _P, _TP, _TP, C.c_int, C.c_int, C.c_int, _P]),
     "dbl_stem_pair": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _TP, _P]),
     "dbl_dsconv_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -83,6 +83,7 @@ class DBLEngine:
         # (Detect P3 64->80 @80^2: 108 us fused vs 89 us as two launches).  "1" = wherever supported, "0" = never.
         self.fuse_ds = os.environ.get("DBL_FUSE_DS", "auto")
         self.ds_impl = os.environ.get("DBL_DS_IMPL", "auto")  # "mma": keep the warp-MMA kernel (A/B aid); "auto": tcgen05 kernel where instantiated
+        self.bn_tc = os.environ.get("DBL_BN_TC", "1") != "0"  # thin Bottlenecks (C = 16, 32) on the tcgen05 pixel-group kernel; "0": round-1 kernels (A/B aid)
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "16"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
         # independent branches of the graph (Detect's six conv chains, HyperACE's three branches, the neck's side paths)
@@ -262,6 +263,21 @@ class DBLEngine:
         """Bottleneck.forward (block.py:344-357)"""
         c_ = self.sd[p + ".cv1.conv.weight"].shape[0]
         add = shortcut and x.c == y.c
+        k33 = self.sd[p + ".cv1.conv.weight"].shape[-1] == 3 and self.sd[p + ".cv2.conv.weight"].shape[-1] == 3
+        if self.fuse_thin and self.bn_tc and k33 and x.c == y.c and c_ * 2 == x.c and x.buf.data_ptr() != y.buf.data_ptr() \
+                and self.lib.dbl_bottleneck_tc_supported(x.c, x.w, x.desc.pitch) and y.desc.pitch == y.c:
+            # cv1 -> cv2 -> +x in one tcgen05 kernel over pixel-group rows with band-matrix filters (csrc/bottleneck_tc.cu)
+            w1, b1 = _fold(self.sd[p + ".cv1.conv.weight"], self.sd, p + ".cv1.bn")
+            w2, b2 = _fold(self.sd[p + ".cv2.conv.weight"], self.sd, p + ".cv2.bn")
+            packed = torch.zeros((self.lib.dbl_bottleneck_tc_packed_bytes(x.c) + 15) // 16 * 4, dtype=torch.int32, device=self.dev)
+            L.check(self.lib.dbl_bottleneck_tc_pack(L.ptr(self._pack_w(w1)), L.ptr(self._dev(b1, torch.float32)), L.ptr(self._pack_w(w2)),
+                                                    L.ptr(self._dev(b2, torch.float32)), x.c, L.ptr(packed), L.current_stream()), "dbl_bottleneck_tc_pack")
+            torch.cuda.synchronize(self.dev)
+            self._keep.append(packed)
+            npix = self.B * y.h * y.w
+            self._emit(self.lib.dbl_bottleneck3x3_tc, (C.byref(x.desc), L.ptr(packed), 1 if add else 0, C.byref(y.desc)), p, "bottleneck_tc",
+                       2.0 * npix * 9 * 2 * x.c * c_, 2 * npix * (x.c + y.c) + 2 * (w1.numel() + w2.numel()) + 4 * (c_ + y.c))
+            return
         if self.fuse_thin and add and x.c in (16, 32, 64) and x.c <= self.fuse_bn_max_c and c_ * 2 == x.c and x.buf.data_ptr() != y.buf.data_ptr() \
                 and self.sd[p + ".cv1.conv.weight"].shape[-1] == 3 and self.sd[p + ".cv2.conv.weight"].shape[-1] == 3:
             # cv1 -> cv2 -> +x in one kernel, hidden tensor in shared memory (csrc/conv_mma.cu)
