@@ -413,7 +413,7 @@ def main():
         for s in side:
             main_s.wait_stream(s)
 
-    clk = ClockSampler(local) if rank == 0 and not args.quick else None  # samples SM clocks / throttle reasons every 100 ms until the e2e legs are done
+    clk = ClockSampler(local) if rank == 0 and not args.quick and not os.environ.get("DBL_NO_CLK") else None  # samples SM clocks / throttle reasons every 100 ms until the e2e legs are done
     run_steps(max(warmup, P))
     ms_total = timed(lambda: run_steps(steps), 1)
     value = args.batch * world * steps / (ms_total * 1e-3)
@@ -479,8 +479,11 @@ def main():
     e2e_run, e2e_state, out_rows, out_cnt = make_e2e(args.batch, model)
     e2e_steps = max(3, steps)
     e2e_run(3, x_u8)
-    e2e_reps = sorted(timed(lambda: e2e_run(e2e_steps, x_u8), 1) for _ in range(3))  # K steps each; the MEDIAN repetition is reported
-    e2e_ms = e2e_reps[1]
+    e2e_raw = [timed(lambda: e2e_run(e2e_steps, x_u8), 1) for _ in range(5)]
+    if os.environ.get("DBL_E2E_DIAG"):
+        print("e2e repetitions in order (ms/step):", [round(t / e2e_steps, 3) for t in e2e_raw], file=sys.stderr)
+    e2e_reps = sorted(e2e_raw)  # K steps each; the MEDIAN repetition is reported (host / PCIe noise on shared boxes: one run saw 3.07, 5.16, 7.19 ms)
+    e2e_ms = e2e_reps[len(e2e_reps) // 2]
     e2e_value = args.batch * world * e2e_steps / (e2e_ms * 1e-3)
     detections = e2e_state["det"]
     x_f32 = [x_host, x_host.clone().pin_memory()]
@@ -541,7 +544,7 @@ def main():
             "data": "synthetic", "config": config_dict(args, world), "clocks": clocks,
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": x_u8[0].numel(),
                     "d2h_bytes_per_step": out_rows[0].numel() * 4 + out_cnt[0].numel() * 4, "ms_per_step": round(e2e_ms / e2e_steps, 4),
-                    "repetitions_ms_per_step": [round(t / e2e_steps, 4) for t in e2e_reps], "reported": "median of three repetitions of K steps",
+                    "repetitions_ms_per_step": [round(t / e2e_steps, 4) for t in e2e_raw], "reported": "median of five repetitions of K steps (listed in run order)",
                     "numa": numa,
                     "input": "uint8 NCHW in pinned host memory (image source; /255 fused into the stem kernel), copy of batch i+1 "
                              "overlapped with compute of batch i, detections (gathered over all ranks when N > 1) read back to pinned host memory every step",
