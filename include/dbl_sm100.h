@@ -129,6 +129,16 @@ int dbl_conv3x3_mma(const dbl_tensor* x, const void* w_packed, const float* bias
 int dbl_stem_pair(const void* x_nchw, int x_is_u8, int n, int h, int w, const float* w0, const float* b0, int c0,
                   const void* w1_packed, const float* b1, const dbl_tensor* y, dbl_stream_t stream);
 
+/* The same stem pair on tcgen05 (csrc/stem_tc.cu) for (c0, c1) = (8, 16): 8-pixel groups as GEMM rows, band-matrix filters, layer 0's output
+ * in shared memory.  y must be dense (pitch == 16), h even, w % 16 == 0, x 16-byte aligned -- dbl_stem_tc_supported(c0, c1, h, w, ypitch).  The band matrices are
+ * produced ONCE by dbl_stem_tc_pack (w0: f32 [8][3][3][3] = [c0][ci][ky][kx], w1: bf16 [16][3][3][8] in the dbl_conv2d layout, BN folded;
+ * x_is_u8 folds the /255 into layer 0) into caller-owned, 16-byte-aligned memory of dbl_stem_tc_packed_bytes() bytes; a blob packed for
+ * u8 input must be used with x_is_u8 = 1. */
+int dbl_stem_tc_supported(int c0, int c1, int h, int w, int ypitch);
+size_t dbl_stem_tc_packed_bytes(void);
+int dbl_stem_tc_pack(const float* w0, const float* b0, const void* w1, const float* b1, int x_is_u8, void* packed, dbl_stream_t stream);
+int dbl_stem_pair_tc(const void* x_nchw, int x_is_u8, int n, int h, int w, const void* packed, const dbl_tensor* y, dbl_stream_t stream);
+
 /* ---- fused depthwise-separable convolution (csrc/dsconv_mma.cu) -------------------------------------------------
  * DSConv.forward (nn/modules/conv.py:91-108): y = SiLU(pw(dw(x)) + b_pw) [+|* r], depthwise k x k (pad (k-1)/2, stride 1|2) and
  * pointwise 1x1 in ONE kernel; with dw_act = 1 the depthwise stage is DWConv + BN + SiLU (bias b_dw, Detect's class branch,

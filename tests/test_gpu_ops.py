@@ -472,6 +472,41 @@ def test_stem_pair(c0, c1, u8, n, h, w):
     assert bool((ybuf[..., c1:].float() == -3.0).all())
 
 
+@pytest.mark.parametrize("u8,n,h,w", [(False, 2, 64, 96), (True, 2, 64, 96), (False, 1, 34, 48), (True, 1, 34, 48), (True, 1, 2, 16), (False, 3, 128, 160),
+                                      (True, 2, 640, 640)])
+def test_stem_pair_tc(u8, n, h, w):
+    """Layers 0+1 on the tcgen05 pixel-group kernel (csrc/stem_tc.cu) vs torch fp32 with layer 0's output rounded to bf16"""
+    c0, c1 = 8, 16
+    g = torch.Generator().manual_seed(h + int(u8))
+    if u8:
+        xi = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
+        x = xi.float() / 255.0
+    else:
+        x = torch.rand(n, 3, h, w, generator=g)
+    w0 = torch.randn(c0, 3, 3, 3, generator=g) / 27 ** 0.5
+    b0 = torch.randn(c0, generator=g) * 0.3
+    w1 = bf16_round(torch.randn(c1, c0, 3, 3, generator=g) / (9 * c0) ** 0.5)
+    b1 = torch.randn(c1, generator=g) * 0.3
+    l0 = bf16_round(F.silu(F.conv2d(x, w0, b0, 1, 1)))  # layer 0's output is held as bf16 in shared memory
+    ref = F.silu(F.conv2d(l0, w1, b1, 2, 1))
+    lib = L.require_device()
+    ybuf, yv = empty_nhwc(n, h // 2, w // 2, c1)
+    assert lib.dbl_stem_tc_supported(c0, c1, h, w, yv.pitch) == 1
+    xd = (xi if u8 else x).to(dev())
+    w0d, b0d, b1d, w1d = w0.to(dev()), b0.to(dev()), b1.to(dev()), pack_w(w1)
+    packed = torch.zeros((lib.dbl_stem_tc_packed_bytes() + 15) // 16 * 4, dtype=torch.int32, device=dev())
+    assert lib.dbl_stem_tc_pack(w0d.data_ptr(), b0d.data_ptr(), w1d.data_ptr(), b1d.data_ptr(), int(u8), packed.data_ptr(), stream()) == 0
+    rc = lib.dbl_stem_pair_tc(xd.data_ptr(), int(u8), n, h, w, packed.data_ptr(), C.byref(yv), stream())
+    torch.cuda.synchronize()
+    assert rc == 0, L.load().dbl_last_error().decode()
+    # layer 0 runs on bf16-rounded pixels / weights here (fp32 in the reference): one extra 2^-9 rounding per operand
+    assert_close_bf16(from_nhwc(ybuf, 0, c1), ref, f"stem_pair_tc u8={u8} {h}x{w}", rel=2.0 ** -6, abs_=4e-2)
+    # a channel-slice output has no pixel-group view: refused, not mis-written
+    yb2, yv2 = empty_nhwc(n, h // 2, w // 2, c1, pad_c=8)
+    assert lib.dbl_stem_tc_supported(c0, c1, h, w, yv2.pitch) == 0
+    assert lib.dbl_stem_pair_tc(xd.data_ptr(), int(u8), n, h, w, packed.data_ptr(), C.byref(yv2), stream()) == 2  # DBL_E_UNSUPPORTED
+
+
 # ---- multi-accumulator tcgen05 3x3 kernel (csrc/conv_tc4.cu): large reduction depth --------------------------------
 TC4_CASES = [
     (2, 40, 40, 384, 64, 3, 1, L.ACT_SILU, L.EPI_NONE, torch.bfloat16, 0, 0),

@@ -79,6 +79,10 @@ _SIGNATURES = {
     "dbl_mma_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "dbl_mma_pack_weights": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dbl_bottleneck3x3": (C.c_int, [_TP, _P, _P, _P, _P, C.c_int, _TP, _P]),
+    "dbl_stem_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dbl_stem_tc_packed_bytes": (C.c_size_t, []),
+    "dbl_stem_tc_pack": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "dbl_stem_pair_tc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _TP, _P]),
     "dbl_bottleneck_tc_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "dbl_bottleneck_tc_packed_bytes": (C.c_size_t, [C.c_int]),
     "dbl_bottleneck_tc_pack": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),

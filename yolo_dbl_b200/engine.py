@@ -83,6 +83,9 @@ class DBLEngine:
         # (Detect P3 64->80 @80^2: 108 us fused vs 89 us as two launches).  "1" = wherever supported, "0" = never.
         self.fuse_ds = os.environ.get("DBL_FUSE_DS", "auto")
         self.ds_impl = os.environ.get("DBL_DS_IMPL", "auto")  # "mma": keep the warp-MMA kernel (A/B aid); "auto": tcgen05 kernel where instantiated
+        # layers 0+1 on the tcgen05 pixel-group kernel (csrc/stem_tc.cu): measured SLOWER than the warp-MMA stem (280 vs 253 us on f32 input, 237 vs
+        # ~250 on u8: bound by shared-memory bandwidth), so it is opt-in
+        self.stem_tc = os.environ.get("DBL_STEM_TC", "0") == "1"
         self.bn_tc = os.environ.get("DBL_BN_TC", "1") != "0"  # thin Bottlenecks (C = 16, 32) on the tcgen05 pixel-group kernel; "0": round-1 kernels (A/B aid)
         self.fuse_bn_max_c = int(os.environ.get("DBL_FUSE_BN_MAXC", "16"))  # widest Bottleneck that uses the fused warp-MMA kernel
         self.use_graph = use_graph
@@ -520,12 +523,28 @@ class DBLEngine:
         w0, b0 = _fold(sd["model.0.conv.weight"], sd, "model.0.bn")
         w1, b1 = _fold(sd["model.1.conv.weight"], sd, "model.1.bn")
         w0d, b0d, b1d = self._dev(w0, torch.float32), self._dev(b0, torch.float32), self._dev(b1, torch.float32)
-        w1p = self._pack_mma(w1)
         c0 = w0.shape[0]
         npix0, npix1 = self.B * self.H * self.W, self.B * y.h * y.w
+        flops = 2.0 * 27 * c0 * npix0 + 2.0 * 9 * c0 * y.c * npix1
+        if self.stem_tc and self.lib.dbl_stem_tc_supported(c0, y.c, self.H, self.W, y.desc.pitch):
+            # tcgen05 form (csrc/stem_tc.cu): band matrices packed once per input type (the u8 blob carries the /255)
+            w1d = self._pack_w(w1)
+            blobs = []
+            for u8 in (0, 1):
+                blob = torch.zeros((self.lib.dbl_stem_tc_packed_bytes() + 15) // 16 * 4, dtype=torch.int32, device=self.dev)
+                L.check(self.lib.dbl_stem_tc_pack(L.ptr(w0d), L.ptr(b0d), L.ptr(w1d), L.ptr(b1d), u8, L.ptr(blob), L.current_stream()), "dbl_stem_tc_pack")
+                blobs.append(blob)
+            torch.cuda.synchronize(self.dev)
+            self._keep.extend(blobs)
+            self._emit(self.lib.dbl_stem_pair_tc, (self.x_in.data_ptr(), 0, self.B, self.H, self.W, L.ptr(blobs[0]), C.byref(y.desc)),
+                       "model.0+1.stem_pair", "stem_tc", flops, self.x_in.numel() * 4 + 2 * npix1 * y.c)
+            self._stem_u8 = (self.x_in_u8.data_ptr(), 1, self.B, self.H, self.W, L.ptr(blobs[1]), C.byref(y.desc))
+            self._stem_fn_u8 = self.lib.dbl_stem_pair_tc
+            return
+        w1p = self._pack_mma(w1)
         tail = (self.B, self.H, self.W, L.ptr(w0d), L.ptr(b0d), c0, L.ptr(w1p), L.ptr(b1d), C.byref(y.desc))
-        self._emit(self.lib.dbl_stem_pair, (self.x_in.data_ptr(), 0) + tail, "model.0+1.stem_pair", "stem_pair",
-                   2.0 * 27 * c0 * npix0 + 2.0 * 9 * c0 * y.c * npix1, self.x_in.numel() * 4 + 2 * npix1 * y.c)
+        self._emit(self.lib.dbl_stem_pair, (self.x_in.data_ptr(), 0) + tail, "model.0+1.stem_pair", "stem_pair", flops,
+                   self.x_in.numel() * 4 + 2 * npix1 * y.c)
         self._stem_u8 = (self.x_in_u8.data_ptr(), 1) + tail
         self._stem_fn_u8 = self.lib.dbl_stem_pair
 
