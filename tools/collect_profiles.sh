@@ -19,10 +19,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-fil
 F="--set full --clock-control none"
 T=/tmp/ncu_$R
 mkdir -p $T
-ncu $F -k regex:conv3x3_tc4 -c 20 -f -o $T/prof_tc4_$R $B > $O/ncu_tc4.log 2>&1
+ncu $F -k 'regex:conv3x3_tc4|conv3x3_tc5|conv3x3s2_tc|bottleneck_tc' -c 24 -f -o $T/prof_tc4_$R $B > $O/ncu_tc4.log 2>&1
 ncu $F -k regex:conv_tc_kernel -c 20 -f -o $T/prof_tc_$R $B > $O/ncu_tc.log 2>&1
 ncu $F -k 'regex:dwconv_tile3|dsconv_mma|dsconv_tc' -c 20 -f -o $T/prof_dw_$R $B > $O/ncu_dw.log 2>&1
-ncu $F -k 'regex:stem_pair|bottleneck_mma|conv3x3_mma|head_decode|sort_nms|dysample|gated_add' -c 14 -f -o $T/prof_misc_$R $B > $O/ncu_misc.log 2>&1
+ncu $F -k 'regex:stem_pair|head_decode|sort_nms|dysample|gated_add|hg_' -c 16 -f -o $T/prof_misc_$R $B > $O/ncu_misc.log 2>&1
 python tools/ncu_summary.py $T/prof_tc4_$R.ncu-rep $T/prof_tc_$R.ncu-rep $T/prof_dw_$R.ncu-rep $T/prof_misc_$R.ncu-rep > $O/${R}_ncu_table.md 2> $O/ncu_summary.err
 python tools/ncu_traffic.py $T/prof_tc4_$R.ncu-rep $T/prof_tc_$R.ncu-rep $T/prof_dw_$R.ncu-rep $T/prof_misc_$R.ncu-rep > $O/${R}_ncu_traffic.json 2> $O/ncu_traffic.err
 ls -la $O $T

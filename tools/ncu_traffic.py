@@ -9,9 +9,11 @@ import json
 import subprocess
 import sys
 
-FAMILY = [("conv3x3_tc4_kernel", "conv_tc4"), ("conv_tc_kernel", "conv_tc_1x1"), ("stem_pair_kernel", "stem_pair"),
+FAMILY = [("dsconv_tc_kernel", "dsconv_tc"),  # before "conv_tc_kernel", which is a substring of it
+          ("conv3x3_tc4_kernel", "conv_tc4"), ("conv3x3_tc5_kernel", "conv_tc5"), ("conv3x3s2_tc_kernel", "conv_s2_tc"), ("bottleneck_tc_kernel", "bottleneck_tc"),
+          ("stem_tc_kernel", "stem_tc"), ("conv_tc_kernel", "conv_tc_1x1"), ("stem_pair_kernel", "stem_pair"),
           ("bottleneck_mma_kernel", "bottleneck_mma"), ("conv3x3_mma_kernel", "conv_mma"), ("head_decode_kernel", "head_decode"),
-          ("dwconv_tile3_kernel", "dwconv"), ("dsconv_mma_kernel", "dsconv"), ("dsconv_tc_kernel", "dsconv_tc"), ("sort_nms_kernel", "sort_nms"),
+          ("dwconv_tile3_kernel", "dwconv"), ("dsconv_mma_kernel", "dsconv"), ("sort_nms_kernel", "sort_nms"),
           ("dysample", "dbl_dysample"), ("gated_add_kernel", "dbl_gated_add")]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"]
 

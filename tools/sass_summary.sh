@@ -2,7 +2,7 @@
 # SASS evidence per kernel (runs HERE, no GPU): mnemonic histogram of every kernel in the built objects -> profiles/<tag>_sass_<file>.txt
 #   bash tools/sass_summary.sh r02
 R=${1:-r02}
-for f in conv_tc conv_tc4 dsconv_tc conv_mma dsconv_mma head_fused detect_post conv_direct elementwise hypergraph; do
+for f in conv_tc conv_tc4 conv_tc5 conv_s2_tc bottleneck_tc stem_tc dsconv_tc conv_mma dsconv_mma head_fused detect_post conv_direct elementwise hypergraph; do
   o=yolo_dbl_b200/build/$f.o
   [ -f $o ] || continue
   cuobjdump -sass $o 2>/dev/null | python3 -c "
