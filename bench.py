@@ -15,6 +15,7 @@ replays); `e2e` goes through the public API with pinned HOST input and a device-
 region.  With N > 1 the line also carries a `strong` block: the SAME global batch of 64 images sharded 64/N per GPU, gather included.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -381,12 +382,17 @@ def main():
 
     def timed(fn, k):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(k):
-            fn()
-        e1.record()
-        barrier()
+        gc.collect()
+        gc.disable()  # the e2e legs have the host in the loop: a generation-2 collection inside a 60 ms region would double it
+        try:
+            barrier()
+            e0.record()
+            for _ in range(k):
+                fn()
+            e1.record()
+            barrier()
+        finally:
+            gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
