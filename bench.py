@@ -465,7 +465,10 @@ def main():
         def run(k, src):
             pending = []  # (event, slot): results whose D2H copy has been queued but not yet read by the host
             n = 0
+            diag = [] if os.environ.get("DBL_E2E_DIAG") else None
+            t_prev = time.perf_counter()
             for rows, counts, ev in mdl.detect_stream((src[i & 1] for i in range(k)), with_event=True, in_flight=P, **NMS):
+                t_gen = time.perf_counter()  # time spent inside the generator: copy + launch of the NEXT batch
                 slot = n % 3
                 d2h.wait_event(ev)  # this batch's result is complete; the next batch is already queued on the compute stream
                 with torch.cuda.stream(d2h):
@@ -476,14 +479,24 @@ def main():
                     done = torch.cuda.Event()
                     done.record(d2h)
                 pending.append((done, slot))
+                t_enq = time.perf_counter()
                 if len(pending) > LAG:  # the host reads step i-LAG's detections while step i's gather/copy is in flight
                     e, s = pending.pop(0)
                     e.synchronize()
                     state["det"] = int(out_cnt[s][: batch].sum()) if gat is None else int(out_cnt[s][rank * batch:(rank + 1) * batch].sum())
                 n += 1
+                if diag is not None:
+                    t_end = time.perf_counter()
+                    diag.append((t_gen - t_prev, t_enq - t_gen, t_end - t_enq))
+                    t_prev = t_end
             for e, s in pending:
                 e.synchronize()
                 state["det"] = int(out_cnt[s][: batch].sum()) if gat is None else int(out_cnt[s][rank * batch:(rank + 1) * batch].sum())
+            if diag:
+                tot = [sum(d[i] for d in diag) * 1e3 for i in range(3)]
+                mx = [max(d[i] for d in diag) * 1e3 for i in range(3)]
+                print(f"  e2e diag ({k} steps): host ms in [launch of next batch, D2H enqueue, wait for step i-{LAG}] = {tot[0]:.1f} / {tot[1]:.1f} / {tot[2]:.1f}, "
+                      f"longest single {mx[0]:.2f} / {mx[1]:.2f} / {mx[2]:.2f}", file=sys.stderr)
             return n
 
         return run, state, out_rows, out_cnt
