@@ -463,7 +463,7 @@ static uint32_t bt_round1k(size_t v) { return (uint32_t)((v + 1023) / 1024 * 102
 
 template <int C>
 static int launch_bt(const dbl_tensor* x, const uint8_t* packed, int shortcut, const dbl_tensor* y, cudaStream_t st) {
-    constexpr int G = 64 / C, P = G, KC = C / 16, S1 = (G + 2) * KC, K1 = 3 * S1 * 16;
+    constexpr int G = 64 / C, KC = C / 16, S1 = (G + 2) * KC, K1 = 3 * S1 * 16;
     auto kern = bottleneck_tc_kernel<C>;
     static DevOnce once;
     if (once.need()) {
@@ -548,7 +548,6 @@ static int launch_bt(const dbl_tensor* x, const uint8_t* packed, int shortcut, c
         const uint32_t box[4] = {64, (uint32_t)(p.gw - 2), (uint32_t)p.th, 1};
         if (!bt_encode(&maps.y, y->data, 4, dims, strides, box, 128)) return DBL_E_CUDA;
     }
-    (void)P;
     const int grid = p.ntiles < sms ? p.ntiles : sms;
     launch_k(kern, grid, BT_THREADS, best_smem, st, maps, p);
     count_launch();
