@@ -450,6 +450,8 @@ def main():
     # final gather of the fixed-capacity detections, runs every step: ONE packed all-gather into preallocated, double-buffered
     # storage; the host reads step i's gathered result while step i+1 is already running (one step of slack between the ranks).
     x_u8 = [(x_host * 255.0).round().to(torch.uint8).pin_memory() for _ in range(2)]
+    if os.environ.get("DBL_E2E_SRC") == "device":  # diagnostic only (never a bench value): the same pipeline without the PCIe copy
+        x_u8 = [t.to(dev) for t in x_u8]
     d2h = torch.cuda.Stream(device=dev)
     use_gather = world > 1 and not args.no_gather
 
