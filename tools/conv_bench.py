@@ -29,6 +29,9 @@ SHAPES = {  # name: (n, h, w, cin, cout, k, s, epi, ydtype)
     "l31_128to128_s2_40": (64, 40, 40, 128, 128, 3, 2, 0, torch.bfloat16),
     "p5_384to256_1x1_20": (64, 20, 20, 384, 256, 1, 1, 0, torch.bfloat16),
     "head_64to80_f32_80": (64, 80, 80, 80, 80, 1, 1, 0, torch.float32),
+    "lsk_128to256_mul_20": (64, 20, 20, 128, 256, 1, 1, 2, torch.bfloat16),
+    "lsk_128to256_20": (64, 20, 20, 128, 256, 1, 1, 0, torch.bfloat16),
+    "lsk_256to128_20": (64, 20, 20, 256, 128, 1, 1, 0, torch.bfloat16),
 }
 
 
